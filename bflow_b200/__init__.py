@@ -1,0 +1,11 @@
+"""bflow_b200 — B200-native (sm_100a) RAFT-spline inference hot path of uzh-rpg/bflow.
+
+Public surface = the reference's own: ``RAFTSpline`` and ``BezierCurves``
+(models/raft_spline/raft.py), plus the ``corr`` mirrors of models/raft_utils/corr.py.
+"""
+from .bezier import BezierCurves
+from .raft import RAFTSpline
+from . import config
+
+__all__ = ['RAFTSpline', 'BezierCurves', 'config']
+__version__ = '0.1.0'

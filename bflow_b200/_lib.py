@@ -1,0 +1,93 @@
+"""ctypes binding of libbflow_b200.so (the C ABI declared in include/bflow_b200.h).
+
+There is no fallback: if the library is missing it is built with nvcc (in-tree); if that is impossible,
+or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+MAX_SLOTS, MAX_TARGETS, MAX_DEGREE = 16, 8, 16
+ACT = {'none': 0, 'relu': 1, 'sigmoid': 2, 'tanh': 3}
+
+c_float_p = C.c_void_p   # device pointers travel as integers
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [('x0', C.c_void_p), ('c0', C.c_int), ('ld0', C.c_int),
+                ('x1', C.c_void_p), ('c1', C.c_int), ('ld1', C.c_int),
+                ('w', C.c_void_p), ('ldw', C.c_int),
+                ('bias', C.c_void_p),
+                ('res', C.c_void_p), ('ldr', C.c_int),
+                ('y', C.c_void_p), ('ldy', C.c_int),
+                ('N', C.c_int), ('H', C.c_int), ('W', C.c_int), ('Ho', C.c_int), ('Wo', C.c_int), ('Cout', C.c_int),
+                ('KH', C.c_int), ('KW', C.c_int), ('stride', C.c_int), ('pad_h', C.c_int), ('pad_w', C.c_int),
+                ('act1', C.c_int), ('act2', C.c_int),
+                ('scale', C.c_float)]
+
+
+class LookupDesc(C.Structure):
+    _fields_ = [('n_slots', C.c_int), ('n_targets', C.c_int), ('B', C.c_int), ('h', C.c_int), ('w', C.c_int), ('radius', C.c_int),
+                ('vol', C.c_void_p * MAX_SLOTS),
+                ('hl', C.c_int * MAX_SLOTS), ('wl', C.c_int * MAX_SLOTS),
+                ('target', C.c_int * MAX_SLOTS),
+                ('inv_scale', C.c_float * MAX_SLOTS),
+                ('coords', C.c_void_p),
+                ('params', C.c_void_p), ('params_ld', C.c_int), ('degree', C.c_int),
+                ('coef', (C.c_float * MAX_DEGREE) * MAX_TARGETS),
+                ('out', C.c_void_p),
+                ('out_nhwc', C.c_int),
+                ('out_ld', C.c_int)]
+
+
+_SIGNATURES = {
+    'bflow_abi_version': (C.c_int, []),
+    'bflow_last_error': (C.c_char_p, []),
+    'bflow_built_for_sm': (C.c_int, []),
+    'bflow_zero': (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_void_p]),
+    'bflow_nchw_to_nhwc': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_float, C.c_float, C.c_void_p]),
+    'bflow_nhwc_to_nchw': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
+    'bflow_conv2d_nhwc': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    'bflow_plane_sums': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'bflow_instnorm_relu': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    'bflow_corr_volume': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'bflow_corr_pool': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    'bflow_corr_lookup': (C.c_int, [C.POINTER(LookupDesc), C.c_void_p]),
+    'bflow_gru_rh': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
+    'bflow_gru_update': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
+    'bflow_bezier_eval': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
+    'bflow_cvx_upsample': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        path = _build.LIB
+        if not os.path.isfile(path):
+            path = _build.build()          # raises when nvcc is unavailable: there is no other path
+        handle = C.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)     # AttributeError = ABI mismatch, also loud
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = '') -> None:
+    if rc != 0:
+        msg = lib().bflow_last_error().decode(errors='replace')
+        if rc == 1:
+            raise AssertionError(f'bflow_b200 {what}: {msg}')     # the reference's convention for contract violations
+        raise RuntimeError(f'bflow_b200 {what}: CUDA failure: {msg}')

@@ -1,0 +1,194 @@
+"""Tensor-level wrappers over the C ABI: argument checks (dtype/device/contiguity → AssertionError, the
+reference's error convention), output allocation, current-stream plumbing.  Used by the public mirrors
+(:mod:`bflow_b200.corr`, :class:`BezierCurves`) and by the parity tests; the engine calls the ABI directly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACT, ConvDesc, LookupDesc, check
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    assert isinstance(t, torch.Tensor), f'{name}: tensor expected'
+    assert t.is_cuda, f'{name}: CUDA tensor expected (bflow_b200 has no CPU path)'
+    assert t.dtype == torch.float32, f'{name}: float32 expected'
+    return t.contiguous()
+
+
+# ---- layout ------------------------------------------------------------------------------------------
+def nchw_to_nhwc(x: torch.Tensor, c_off: int = 0, c_cnt: Optional[int] = None, out: Optional[torch.Tensor] = None,
+                 out_ld: Optional[int] = None, scale: float = 1.0, shift: float = 0.0) -> torch.Tensor:
+    x = _f32c(x, 'x')
+    N, Ct, H, W = x.shape
+    c_cnt = Ct - c_off if c_cnt is None else c_cnt
+    ld = c_cnt if out_ld is None else out_ld
+    if out is None:
+        out = torch.zeros(N, H, W, ld, device=x.device, dtype=torch.float32)
+    check(_lib.lib().bflow_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), N, Ct, H, W, c_off, c_cnt, ld, scale, shift, _stream()),
+          'nchw_to_nhwc')
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, C_: Optional[int] = None) -> torch.Tensor:
+    x = _f32c(x, 'x')
+    N, H, W, ld = x.shape
+    C_ = ld if C_ is None else C_
+    out = torch.empty(N, C_, H, W, device=x.device, dtype=torch.float32)
+    check(_lib.lib().bflow_nhwc_to_nchw(x.data_ptr(), out.data_ptr(), N, C_, H, W, ld, _stream()), 'nhwc_to_nchw')
+    return out
+
+
+# ---- convolution ----------------------------------------------------------------------------------------
+def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None) -> Tuple[torch.Tensor, int]:
+    """OIHW → K-major [(kh*KW+kw)*Cin + c][ldw] with Cout zero-padded to a multiple of 4 (and Cin to cin_pad)."""
+    O, I, KH, KW = w.shape
+    ldw = (O + 3) // 4 * 4
+    ci = I if cin_pad is None else cin_pad
+    p = torch.zeros(KH, KW, ci, ldw, device=w.device, dtype=torch.float32)
+    p[:, :, :I, :O] = w.detach().float().permute(2, 3, 1, 0)
+    return p.reshape(KH * KW * ci, ldw).contiguous(), ldw
+
+
+def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, stride: int = 1,
+           padding=(0, 0), act: str = 'none', scale: float = 1.0) -> torch.Tensor:
+    """NCHW in / NCHW out convenience form of bflow_conv2d_nhwc (used by tests and the operator mirror)."""
+    x = _f32c(x, 'x')
+    N, Cin, H, W = x.shape
+    O, I, KH, KW = weight.shape
+    assert I == Cin
+    ph, pw = (padding, padding) if isinstance(padding, int) else padding
+    Ho, Wo = (H + 2 * ph - KH) // stride + 1, (W + 2 * pw - KW) // stride + 1
+    xh = nchw_to_nhwc(x)
+    wp, ldw = pack_conv_weight(_f32c(weight, 'weight'))
+    y = torch.empty(N, Ho, Wo, O, device=x.device, dtype=torch.float32)
+    d = ConvDesc()
+    d.x0, d.c0, d.ld0 = xh.data_ptr(), Cin, Cin
+    d.x1, d.c1, d.ld1 = None, 0, 0
+    d.w, d.ldw = wp.data_ptr(), ldw
+    b = _f32c(bias, 'bias') if bias is not None else None
+    d.bias = b.data_ptr() if b is not None else None
+    d.res, d.ldr = None, 0
+    d.y, d.ldy = y.data_ptr(), O
+    d.N, d.H, d.W, d.Ho, d.Wo, d.Cout = N, H, W, Ho, Wo, O
+    d.KH, d.KW, d.stride, d.pad_h, d.pad_w = KH, KW, stride, ph, pw
+    d.act1, d.act2, d.scale = ACT[act], 0, scale
+    check(_lib.lib().bflow_conv2d_nhwc(C.byref(d), _stream()), 'conv2d')
+    return nhwc_to_nchw(y)
+
+
+def instance_norm_relu(x: torch.Tensor, residual: Optional[torch.Tensor] = None, residual_norm: bool = False,
+                       eps: float = 1e-5) -> torch.Tensor:
+    """NCHW convenience form: relu(IN(x)) or relu(relu(IN(x)) + R)."""
+    L = _lib.lib()
+    xh = nchw_to_nhwc(x)
+    N, H, W, Cc = xh.shape
+    sums = torch.zeros(N, Cc, 2, device=x.device, dtype=torch.float64)
+    check(L.bflow_plane_sums(xh.data_ptr(), Cc, sums.data_ptr(), N, H * W, Cc, _stream()), 'plane_sums')
+    rh = rs = None
+    if residual is not None:
+        rh = nchw_to_nhwc(residual)
+        if residual_norm:
+            rs = torch.zeros(N, Cc, 2, device=x.device, dtype=torch.float64)
+            check(L.bflow_plane_sums(rh.data_ptr(), Cc, rs.data_ptr(), N, H * W, Cc, _stream()), 'plane_sums')
+    out = torch.empty_like(xh)
+    check(L.bflow_instnorm_relu(xh.data_ptr(), Cc, sums.data_ptr(), rh.data_ptr() if rh is not None else None, Cc,
+                                rs.data_ptr() if rs is not None else None, out.data_ptr(), Cc, N, H * W, Cc, eps, _stream()),
+          'instnorm_relu')
+    return nhwc_to_nchw(out)
+
+
+# ---- correlation -------------------------------------------------------------------------------------------
+def corr_volume(fmap1: torch.Tensor, fmap2: torch.Tensor) -> torch.Tensor:
+    """fmap1 (B,D,h,w) or (T,B,D,h,w); fmap2 (T,B,D,h,w), reference layout → (T, B*h*w, 1, h, w)
+    (models/raft_utils/corr.py:264-272)."""
+    fmap2 = _f32c(fmap2, 'fmap2')
+    T, B, D, h, w = fmap2.shape
+    fmap1 = _f32c(fmap1, 'fmap1')
+    per_target = fmap1.ndim == 5
+    Q = h * w
+    out = torch.empty(T, B * Q, 1, h, w, device=fmap2.device, dtype=torch.float32)
+    f1h = [nchw_to_nhwc(fmap1[t]) for t in range(T)] if per_target else [nchw_to_nhwc(fmap1)] * T
+    for t in range(T):
+        check(_lib.lib().bflow_corr_volume(f1h[t].data_ptr(), D, fmap2[t].data_ptr(), out[t].data_ptr(), B, D, Q, _stream()),
+              'corr_volume')
+    return out
+
+
+def corr_pool(vol: torch.Tensor) -> torch.Tensor:
+    """(..., H, W) → (..., H//2, W//2), avg_pool2d(2, 2) (corr.py:119)."""
+    vol = _f32c(vol, 'vol')
+    H, W = vol.shape[-2:]
+    planes = vol.numel() // (H * W)
+    out = torch.empty(*vol.shape[:-2], H // 2, W // 2, device=vol.device, dtype=torch.float32)
+    check(_lib.lib().bflow_corr_pool(vol.data_ptr(), out.data_ptr(), planes, H, W, _stream()), 'corr_pool')
+    return out
+
+
+def make_lookup_desc(slots: Sequence[Tuple[int, int, torch.Tensor]], n_targets: int, B: int, h: int, w: int) -> LookupDesc:
+    """slots: (level, base target, planes tensor (B*Q, hl, wl)) in output order."""
+    d = LookupDesc()
+    d.n_slots, d.n_targets, d.B, d.h, d.w, d.radius = len(slots), n_targets, B, h, w, 4
+    for s, (lvl, t, planes) in enumerate(slots):
+        assert planes.is_cuda and planes.dtype == torch.float32 and planes.is_contiguous()
+        assert planes.shape[0] == B * h * w
+        d.vol[s] = planes.data_ptr()
+        d.hl[s], d.wl[s] = planes.shape[-2], planes.shape[-1]
+        d.target[s] = t
+        d.inv_scale[s] = 1.0 / (2 ** lvl)
+    return d
+
+
+def corr_lookup(slots: Sequence[Tuple[int, int, torch.Tensor]], coords: torch.Tensor, nhwc: bool = False) -> torch.Tensor:
+    """coords (T,B,2,h,w) → (B, S*81, h, w) [reference layout] or (B,h,w,S*81) when nhwc (corr.py:307-350)."""
+    coords = _f32c(coords, 'coords')
+    T, B, two, h, w = coords.shape
+    assert two == 2
+    d = make_lookup_desc(slots, T, B, h, w)
+    S = len(slots)
+    d.coords = coords.data_ptr()
+    d.params, d.params_ld, d.degree = None, 0, 0
+    if nhwc:
+        out = torch.empty(B, h, w, S * 81, device=coords.device, dtype=torch.float32)
+    else:
+        out = torch.empty(B, S * 81, h, w, device=coords.device, dtype=torch.float32)
+    d.out, d.out_nhwc, d.out_ld = out.data_ptr(), int(nhwc), S * 81
+    check(_lib.lib().bflow_corr_lookup(C.byref(d), _stream()), 'corr_lookup')
+    return out
+
+
+# ---- Bezier ------------------------------------------------------------------------------------------------
+def bezier_eval(params: torch.Tensor, coef: np.ndarray) -> torch.Tensor:
+    params = _f32c(params, 'params')
+    B, c2, H, W = params.shape
+    deg = c2 // 2
+    coef = np.ascontiguousarray(coef, dtype=np.float32)
+    T = coef.shape[0]
+    assert coef.shape == (T, deg)
+    out = torch.empty(T, B, 2, H, W, device=params.device, dtype=torch.float32)
+    for t0 in range(0, T, 32):
+        t1 = min(T, t0 + 32)
+        chunk = np.ascontiguousarray(coef[t0:t1])
+        check(_lib.lib().bflow_bezier_eval(params.data_ptr(), chunk.ctypes.data, out[t0:t1].data_ptr(), t1 - t0, B, deg, H, W, _stream()),
+              'bezier_eval')
+    return out
+
+
+def cvx_upsample(data: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """data (N,C,h,w), mask (N,576,h,w) in the reference layout → (N,C,8h,8w) (utils.py:33-48)."""
+    data, mask = _f32c(data, 'data'), _f32c(mask, 'mask')
+    N, Cc, h, w = data.shape
+    assert mask.shape == (N, 576, h, w)
+    out = torch.empty(N, Cc, 8 * h, 8 * w, device=data.device, dtype=torch.float32)
+    check(_lib.lib().bflow_cvx_upsample(data.data_ptr(), 0, 1, mask.data_ptr(), 0, 1, out.data_ptr(), N, Cc, h, w, _stream()),
+          'cvx_upsample')
+    return out

@@ -1,0 +1,152 @@
+/* bflow_b200 — C ABI of the B200-native (sm_100a) RAFT-spline inference hot path.
+ *
+ * The reference (uzh-rpg/bflow) is 100 % Python and has NO native interface: every entry point
+ * below replaces a group of PyTorch/ATen calls at the cited reference location
+ * (paths relative to the reference root).  A maintainer binds them with ctypes;
+ * bflow_b200/ops.py is that binding.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers to fp32 unless stated otherwise; inputs are borrowed and never
+ *     written; nothing is allocated or freed inside the library;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); no entry point
+ *     synchronises the host;
+ *   - every function returns 0 on success, BFLOW_ERR_INVALID for a contract violation detected on the
+ *     host (the reference's convention is `assert`), BFLOW_ERR_CUDA when the launch failed
+ *     (bflow_last_error() then holds cudaGetErrorString);
+ *   - "NHWC" activations are addressed as  base[pixel * ld + channel]  with pixel = (n*H + y)*W + x,
+ *     so a tensor may be a channel slice of a wider buffer (ld >= channels).  "NCHW" is the
+ *     reference's layout.
+ */
+#ifndef BFLOW_B200_H
+#define BFLOW_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFLOW_OK 0
+#define BFLOW_ERR_INVALID 1
+#define BFLOW_ERR_CUDA 2
+
+#define BFLOW_ACT_NONE 0
+#define BFLOW_ACT_RELU 1
+#define BFLOW_ACT_SIGMOID 2
+#define BFLOW_ACT_TANH 3
+
+#define BFLOW_MAX_SLOTS 16
+#define BFLOW_MAX_TARGETS 8
+#define BFLOW_MAX_DEGREE 16
+
+int bflow_abi_version(void);
+const char* bflow_last_error(void);
+/* compute capability the library was built for (100 for sm_100a) */
+int bflow_built_for_sm(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Layout plumbing.  Replaces torch slicing/cat of the voxel grid windows (models/raft_spline/raft.py:88-99),
+ * the image normalisation 2*(x/255)-1 (raft.py:134) and the NCHW views the reference API exposes.
+ * dst[pix*dst_ld + c] = src[n, c_off + c, y, x] * scale + shift     for c in [0, c_cnt)
+ * ------------------------------------------------------------------------------------------- */
+int bflow_nchw_to_nhwc(const float* src, float* dst, int N, int C_total, int H, int W,
+                       int c_off, int c_cnt, int dst_ld, float scale, float shift, void* stream);
+/* dst[n, c, y, x] = src[pix*src_ld + c]   for c in [0, C) */
+int bflow_nhwc_to_nchw(const float* src, float* dst, int N, int C, int H, int W, int src_ld, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 2-D convolution as implicit GEMM on NHWC activations.  Replaces every nn.Conv2d call on the path:
+ * models/raft_utils/extractor.py:49-53,112,120 and models/raft_spline/update.py:17-18,36-45,89-96,112-114.
+ *   out = act2( res + act1( scale * (conv(x, w) + bias) ) )
+ * The input is the channel concatenation of up to two sources (torch.cat at update.py:35,38,42,45,94,120).
+ * Weights are pre-packed K-major: w[((kh*KW + kw)*Cin + c) * ldw + o], zero padded to ldw (ldw % 4 == 0).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct bflow_conv_desc {
+    const float* x0; int c0; int ld0;
+    const float* x1; int c1; int ld1;      /* x1 == NULL / c1 == 0: single source */
+    const float* w;  int ldw;
+    const float* bias;                     /* [Cout] or NULL */
+    const float* res; int ldr;             /* optional residual, NHWC with pixel stride ldr */
+    float* y; int ldy;
+    int N, H, W, Ho, Wo, Cout;
+    int KH, KW, stride, pad_h, pad_w;
+    int act1, act2;
+    float scale;
+} bflow_conv_desc;
+int bflow_conv2d_nhwc(const bflow_conv_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * InstanceNorm2d (biased variance, eps, no affine; extractor.py:27-31) in two passes:
+ * per-(n,c) sums, then  out = relu( (a-mu_a)*rstd_a )                      if r == NULL
+ *                       out = relu( relu((a-mu_a)*rstd_a) + R )            otherwise,
+ *                       R = r (identity skip) or (r-mu_r)*rstd_r (norm3 of the 1x1 downsample;
+ *                       extractor.py:43-44,47-55).
+ * sums: double[N][C][2] = (sum x, sum x^2), must be zeroed by the caller (bflow_zero).
+ * ------------------------------------------------------------------------------------------- */
+int bflow_plane_sums(const float* x, int ld, double* sums, int N, int HW, int C, void* stream);
+int bflow_instnorm_relu(const float* a, int lda, const double* sums_a,
+                        const float* r, int ldr, const double* sums_r,
+                        float* out, int ldo, int N, int HW, int C, float eps, void* stream);
+int bflow_zero(void* ptr, unsigned long long bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Correlation volume (models/raft_utils/corr.py:264-272):
+ *   corr[bq, p] = sum_d f1[bq, d] * f2[b, d, p] / sqrt(D)       for one target
+ * f1: NHWC rows (B*Q, D) with pixel stride ld1;  f2: NCHW (B, D, Q);  corr: (B*Q, Q) row-major, i.e. the
+ * reference's (B*h*w, 1, h, w) plane stack of that target.
+ * ------------------------------------------------------------------------------------------- */
+int bflow_corr_volume(const float* f1, int ld1, const float* f2_nchw, float* corr,
+                      int B, int D, int Q, void* stream);
+/* avg_pool2d(2, stride 2) with floor on a stack of planes (corr.py:119): (P,H,W) -> (P,H/2,W/2) */
+int bflow_corr_pool(const float* in, float* out, long long planes, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pyramid lookup (corr.py:307-350 + models/raft_utils/utils.py:5-21).  One unit = (query pixel, slot):
+ * a (2r+1)^2 window sampled bilinearly (pixel units, align_corners=True, per-corner zero padding) around
+ * coords/2^level in the query's private plane.  Output channel = slot*81 + iy*9 + ix (dy = iy-4 major).
+ * Centre coordinates come either from `coords` (T,B,2,h,w — the reference's argument) or, when
+ * coords == NULL, are formed in-kernel as pixel grid + Bezier flow (raft.py:180-181, bezier.py:165-186)
+ * from `params` (NHWC rows (B*Q) x 2*degree at pixel stride params_ld; channel = dim*degree + i-1).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct bflow_lookup_desc {
+    int n_slots, n_targets, B, h, w, radius;
+    const float* vol[BFLOW_MAX_SLOTS];     /* (B*Q, hl, wl) planes of this slot's (level, target) */
+    int hl[BFLOW_MAX_SLOTS], wl[BFLOW_MAX_SLOTS];
+    int target[BFLOW_MAX_SLOTS];
+    float inv_scale[BFLOW_MAX_SLOTS];      /* 1 / 2^level */
+    const float* coords;                   /* (T,B,2,h,w) or NULL */
+    const float* params; int params_ld; int degree;
+    float coef[BFLOW_MAX_TARGETS][BFLOW_MAX_DEGREE];   /* Bernstein weights per target timestamp */
+    float* out;
+    int out_nhwc;                          /* 0: (B, S*81, h, w) like the reference; 1: rows (B*Q) x out_ld */
+    int out_ld;
+} bflow_lookup_desc;
+int bflow_corr_lookup(const bflow_lookup_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SepConvGRU gate arithmetic (update.py:37-40,44-47) on NHWC rows:
+ *   bflow_gru_rh:      rh = r * h            (r = zr[:, C:2C])
+ *   bflow_gru_update:  h  = (1-z)*h + z*q    (z = zr[:, 0:C]), in place
+ * ------------------------------------------------------------------------------------------- */
+int bflow_gru_rh(const float* zr, int ldzr, const float* h, int ldh, float* rh, int ldrh,
+                 long long rows, int C, void* stream);
+int bflow_gru_update(const float* zr, int ldzr, const float* q, int ldq, float* h, int ldh,
+                     long long rows, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Bezier evaluation (bezier.py:165-186): flows[t,b,d,y,x] = sum_i coef[t][i] * P_i,  params NCHW
+ * (B, 2*degree, H, W), coef host array [T][degree] (fp32), T <= 32.
+ * ------------------------------------------------------------------------------------------- */
+int bflow_bezier_eval(const float* params_nchw, const float* coef_host, float* flows,
+                      int T, int B, int degree, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convex 8x upsampling (utils.py:33-48 via bezier.py:81-84).  data: NHWC rows (N*h*w) x C at pixel stride
+ * ldd (or NCHW when data_nchw != 0); mask: NHWC rows x 576 at stride ldm (or NCHW (N,576,h,w) when
+ * mask_nchw != 0), channel = k*64 + i*8 + j.  out: NCHW (N, C, 8h, 8w).
+ * ------------------------------------------------------------------------------------------- */
+int bflow_cvx_upsample(const float* data, int ldd, int data_nchw, const float* mask, int ldm, int mask_nchw,
+                       float* out, int N, int C, int h, int w, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFLOW_B200_H */

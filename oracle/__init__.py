@@ -1,0 +1,6 @@
+"""TEST INFRASTRUCTURE ONLY — CPU oracle for the RAFT-spline inference hot path.
+
+Nothing under ``oracle/`` is part of the product.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import it, and only as the checker.  ``bflow_b200`` never imports it.
+"""

@@ -1,0 +1,138 @@
+"""GPU parity of every C-ABI kernel against the CPU oracle / torch CPU fp32 on seeded inputs."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden
+from oracle import raft_spline_oracle as O
+from bflow_b200 import ops, synthetic, BezierCurves
+from bflow_b200.bezier import bernstein_coeffs
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def g(seed=0):
+    return torch.Generator().manual_seed(seed)
+
+
+@pytest.mark.parametrize('N,Cin,H,W,Cout,k,s,p,act', [
+    (2, 5, 20, 28, 64, (7, 7), 2, (3, 3), 'relu'),        # encoder stem, odd Cin → generic path
+    (2, 64, 12, 20, 96, (3, 3), 2, (1, 1), 'none'),       # vector path, stride 2, Cout not multiple of 64
+    (1, 96, 9, 11, 128, (1, 1), 2, (0, 0), 'none'),       # 1x1 downsample
+    (1, 384, 8, 12, 256, (1, 5), 1, (0, 2), 'sigmoid'),   # GRU horizontal
+    (1, 384, 8, 12, 128, (5, 1), 1, (2, 0), 'tanh'),      # GRU vertical
+    (1, 256, 8, 12, 4, (3, 3), 1, (1, 1), 'none'),        # Bezier head: tiny Cout
+    (3, 20, 8, 12, 128, (7, 7), 1, (3, 3), 'relu'),       # convf1 at degree 10
+    (4, 128, 40, 60, 64, (3, 3), 1, (1, 1), 'relu'),      # big enough for the 128-row tile
+    (1, 576, 6, 10, 124, (1, 1), 1, (0, 0), 'relu'),      # convc1-like, Cout 124
+])
+def test_conv2d_matches_torch(N, Cin, H, W, Cout, k, s, p, act):
+    x = torch.randn(N, Cin, H, W, generator=g(1))
+    w = torch.randn(Cout, Cin, *k, generator=g(2)) / (Cin * k[0] * k[1]) ** 0.5
+    b = torch.randn(Cout, generator=g(3))
+    ref = F.conv2d(x, w, b, stride=s, padding=p)
+    ref = {'none': lambda t: t, 'relu': torch.relu, 'sigmoid': torch.sigmoid, 'tanh': torch.tanh}[act](ref)
+    out = ops.conv2d(x.to(DEV), w.to(DEV), b.to(DEV), stride=s, padding=p, act=act).cpu()
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max() < 2e-5
+
+
+def test_instance_norm_relu_variants():
+    x = torch.randn(3, 96, 17, 23, generator=g(1)) * 3 + 1
+    r = torch.randn(3, 96, 17, 23, generator=g(2))
+    inorm = lambda t: F.instance_norm(t, eps=1e-5)
+    for res, rn, want in ((None, False, torch.relu(inorm(x))),
+                          (r, False, torch.relu(torch.relu(inorm(x)) + r)),
+                          (r, True, torch.relu(torch.relu(inorm(x)) + inorm(r)))):
+        out = ops.instance_norm_relu(x.to(DEV), None if res is None else res.to(DEV), rn).cpu()
+        assert (out - want).abs().max() < 1e-5
+
+
+def test_layout_round_trip_and_window():
+    x = torch.randn(2, 9, 16, 24, generator=g(1))
+    y = ops.nchw_to_nhwc(x.to(DEV), c_off=2, c_cnt=5)
+    assert torch.equal(y.cpu(), x[:, 2:7].permute(0, 2, 3, 1))
+    z = ops.nchw_to_nhwc(x.to(DEV), scale=2.0 / 255.0, shift=-1.0)
+    assert torch.allclose(z.cpu(), (2 * (x / 255) - 1).permute(0, 2, 3, 1), atol=1e-6)
+    assert torch.equal(ops.nhwc_to_nchw(ops.nchw_to_nhwc(x.to(DEV))).cpu(), x)
+
+
+def _pyramid_slots(vol, levels):
+    """GPU pyramid in engine form from a level-0 volume (T, BQ, 1, h, w)."""
+    T = vol.shape[0]
+    lv = [vol[:, :, 0].contiguous()]
+    idx = [list(range(T))]
+    for lvl in range(1, max(levels)):
+        keep = [t for t in range(T) if levels[t] > lvl]
+        prev = torch.stack([lv[-1][idx[-1].index(t)] for t in keep], 0)
+        lv.append(ops.corr_pool(prev))
+        idx.append(keep)
+    return [(l, t, lv[l][idx[l].index(t)].contiguous()) for (l, t) in O.slot_table(levels)], lv
+
+
+def test_corr_volume_pool_lookup_match_reference_fixture():
+    gd = load_golden('lookup_16x24')
+    B, h, w, D = int(gd['B']), int(gd['h']), int(gd['w']), int(gd['D'])
+    levels = [int(v) for v in gd['levels']]
+    f1, f2, coords = synthetic.lookup_case(B, h, w, dim=D, targets=len(levels), seed=7)
+    vol = ops.corr_volume(f1.to(DEV), f2.to(DEV))
+    assert vol.shape == (4, B * h * w, 1, h, w)
+    assert np.abs(vol.cpu().reshape(-1).numpy()[gd['lvl0_index']] - gd['lvl0_samples']).max() < 2e-5
+    slots, lv = _pyramid_slots(vol, levels)
+    for lvl in (1, 2, 3):
+        assert np.abs(lv[lvl].cpu().numpy() - gd[f'lvl{lvl}']).max() < 2e-5
+    out = ops.corr_lookup(slots, coords.to(DEV))
+    assert np.abs(out.cpu().numpy() - gd['out']).max() < 3e-5
+    out2 = ops.corr_lookup(slots, coords.to(DEV), nhwc=True)
+    assert torch.equal(out2.permute(0, 3, 1, 2), out)
+
+
+@pytest.mark.parametrize('B,h,w,levels', [(1, 60, 80, [4]), (3, 24, 40, [1, 1, 1, 1, 4, 4]), (2, 9, 13, [2, 1])])
+def test_lookup_matches_oracle(B, h, w, levels):
+    T = len(levels)
+    f1, f2, coords = synthetic.lookup_case(B, h, w, dim=32, targets=T, seed=11)
+    coords[0, 0, :, 0, 0] = torch.tensor([-30.0, 1e9])            # far outside: all taps zero-padded
+    coords[0, 0, :, 0, 1] = torch.tensor([float(w - 1), float(h - 1)])   # exact integer corner
+    vol = O.corr_volume(f1, f2)
+    pyr = O.corr_pyramid(vol, levels)
+    want = O.corr_lookup(pyr, coords)
+    slots = [(l, t, pyr[l][1][pyr[l][0].index(t)].contiguous().to(DEV)) for (l, t) in O.slot_table(levels)]
+    out = ops.corr_lookup(slots, coords.to(DEV)).cpu()
+    assert out.shape == want.shape
+    assert (out - want).abs().max() < 3e-5
+    assert out[0, :81, 0, 0].abs().max() == 0
+
+
+def test_lookup_known_answer_centre_tap():
+    h, w = 12, 20
+    vol = torch.randn(1, h * w, 1, h, w, generator=g(5))
+    co = O.coords_grid(1, h, w)[None]
+    out = ops.corr_lookup([(0, 0, vol[0, :, 0].contiguous().to(DEV))], co.to(DEV)).cpu()
+    assert torch.equal(out[0, 40].reshape(-1), vol[0, :, 0].reshape(h * w, h * w).diagonal())
+
+
+@pytest.mark.parametrize('deg', [1, 2, 10])
+def test_bezier_and_upsample_match_reference_fixture(deg):
+    gd = load_golden('bezier')
+    p = torch.from_numpy(gd[f'deg{deg}_params']).to(DEV)
+    b = BezierCurves(p)
+    ts = [float(t) for t in gd['ts']]
+    assert np.abs(b.get_flow_from_reference(ts).cpu().numpy() - gd[f'deg{deg}_flows']).max() < 1e-6
+    assert np.abs(b.get_flow_from_reference(0.5).cpu().numpy() - gd[f'deg{deg}_scalar_half']).max() < 1e-6
+    assert np.abs(b.get_flow_from_reference(1.0).cpu().numpy() - gd[f'deg{deg}_scalar_one']).max() == 0
+    up = b.create_upsampled(torch.from_numpy(gd[f'deg{deg}_mask']).to(DEV))
+    assert np.abs(up.get_params().cpu().numpy() - gd[f'deg{deg}_up']).max() < 1e-5
+
+
+def test_upsample_of_constant_is_eight_times_constant():
+    up = ops.cvx_upsample(torch.full((2, 4, 7, 9), 0.25, device=DEV), torch.randn(2, 576, 7, 9, device=DEV))
+    assert torch.allclose(up[:, :, 8:-8, 8:-8], torch.full((2, 4, 40, 56), 2.0, device=DEV), atol=1e-6)
+
+
+def test_contract_errors_are_assertions():
+    with pytest.raises(AssertionError):
+        ops.conv2d(torch.zeros(1, 3, 8, 8), torch.zeros(4, 3, 3, 3, device=DEV))       # CPU tensor
+    with pytest.raises(AssertionError):
+        ops.corr_lookup([(0, 0, torch.zeros(5, 4, 4, device=DEV))], torch.zeros(1, 1, 2, 4, 4, device=DEV))
