@@ -39,7 +39,7 @@ def test_forward_matches_reference_fixture(name):
 
 
 @pytest.mark.parametrize('preset,B,H,W,iters,kind', [
-    ('E_LU4_BD2', 2, 96, 160, 3, 'randn'),
+    ('E_LU4_BD2', 2, 128, 160, 3, 'randn'),
     ('E_I_LU5_BD10', 1, 128, 128, 2, 'sparse_norm'),
 ])
 def test_forward_matches_oracle_all_modes(preset, B, H, W, iters, kind):
