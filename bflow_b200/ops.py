@@ -59,8 +59,33 @@ def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None) -> Tuple[to
     return p.reshape(KH * KW * ci, ldw).contiguous(), ldw
 
 
+def pack_conv_weight_tc(w: torch.Tensor, bn: int, cin_pad: Optional[int] = None) -> torch.Tensor:
+    """OIHW fp32 → the tensor-core weight image of bflow_conv2d_nhwc_tc:
+    [ceil(O/bn)][ceil(K/64)][hi|lo][bn][64] bf16 with K = (kh*KW+kw)*Cin + c flattened and the 16-byte chunks of
+    every 128-byte row XOR-swizzled by (row % 8) — byte for byte the SWIZZLE_128B shared-memory tile."""
+    O, I, KH, KW = w.shape
+    ci = I if cin_pad is None else cin_pad
+    K = KH * KW * ci
+    nkb, nt = (K + 63) // 64, (O + bn - 1) // bn
+    wk = torch.zeros(nt * bn, nkb * 64, device=w.device, dtype=torch.float32)
+    wp = torch.zeros(O, KH, KW, ci, device=w.device, dtype=torch.float32)
+    wp[..., :I] = w.detach().float().permute(0, 2, 3, 1)
+    wk[:O, :K] = wp.reshape(O, K)
+    hi = wk.to(torch.bfloat16)
+    lo = (wk - hi.float()).to(torch.bfloat16)
+    r = torch.arange(bn, device=w.device) % 8
+    src_chunk = (torch.arange(8, device=w.device)[None, :] ^ r[:, None])          # dst chunk j <- source chunk j ^ (row % 8)
+    idx = src_chunk[None, None, :, :, None].expand(nt, nkb, bn, 8, 8)
+
+    def tile(x):
+        x = x.view(nt, bn, nkb, 8, 8).permute(0, 2, 1, 3, 4)                       # tile, k-block, row, chunk, element
+        return torch.gather(x, 3, idx)
+    img = torch.stack([tile(hi), tile(lo)], dim=2).contiguous()                    # tile, k-block, hi|lo, row, chunk, element
+    return img.view(-1)
+
+
 def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, stride: int = 1,
-           padding=(0, 0), act: str = 'none', scale: float = 1.0) -> torch.Tensor:
+           padding=(0, 0), act: str = 'none', scale: float = 1.0, backend: str = 'simt', bn: int = 128) -> torch.Tensor:
     """NCHW in / NCHW out convenience form of bflow_conv2d_nhwc (used by tests and the operator mirror)."""
     x = _f32c(x, 'x')
     N, Cin, H, W = x.shape
@@ -82,7 +107,14 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     d.N, d.H, d.W, d.Ho, d.Wo, d.Cout = N, H, W, Ho, Wo, O
     d.KH, d.KW, d.stride, d.pad_h, d.pad_w = KH, KW, stride, ph, pw
     d.act1, d.act2, d.scale = ACT[act], 0, scale
-    check(_lib.lib().bflow_conv2d_nhwc(C.byref(d), _stream()), 'conv2d')
+    if backend == 'tc':
+        wtc = pack_conv_weight_tc(weight, bn)
+        err = torch.zeros(1, device=x.device, dtype=torch.int32)
+        check(_lib.lib().bflow_conv2d_nhwc_tc(C.byref(d), wtc.data_ptr(), bn, err.data_ptr(), _stream()), 'conv2d_tc')
+        if int(err.item()) != 0:
+            raise RuntimeError('bflow_conv2d_nhwc_tc: pipeline wait timed out inside the kernel')
+    else:
+        check(_lib.lib().bflow_conv2d_nhwc(C.byref(d), _stream()), 'conv2d')
     return nhwc_to_nchw(y)
 
 

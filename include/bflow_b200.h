@@ -73,6 +73,16 @@ typedef struct bflow_conv_desc {
 } bflow_conv_desc;
 int bflow_conv2d_nhwc(const bflow_conv_desc* d, void* stream);
 
+/* Tensor-core form of the same operator (tcgen05.mma, TMEM accumulators, split-bf16 operands: every fp32
+ * operand x = hi + lo in bf16, products hi*hi + hi*lo + lo*hi accumulated in fp32).  `d->w/ldw` are ignored;
+ * `w_tc` is the host-packed weight image  [ceil(Cout/bn)][ceil(K/64)][hi|lo][bn rows][64 bf16]  whose 16-byte
+ * chunks are XOR-swizzled by (row % 8), i.e. the exact SWIZZLE_128B shared-memory tile (bflow_b200/ops.py
+ * pack_conv_weight_tc).  Needs c0 % 8 == 0, c1 % 8 == 0, ld % 4 == 0 and 16-byte aligned sources
+ * (bflow_conv2d_tc_supported returns 1).  bn in {64,128,256}.  `err`: optional device int, set to 1 if an
+ * in-kernel pipeline wait timed out (never expected; the waits are bounded so that a bug cannot hang the GPU). */
+int bflow_conv2d_tc_supported(const bflow_conv_desc* d);
+int bflow_conv2d_nhwc_tc(const bflow_conv_desc* d, const void* w_tc, int bn, int* err, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * InstanceNorm2d (biased variance, eps, no affine; extractor.py:27-31) in two passes:
  * per-(n,c) sums, then  out = relu( (a-mu_a)*rstd_a )                      if r == NULL
