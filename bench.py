@@ -275,11 +275,14 @@ def main():
     line = {
         'metric': METRIC, 'value': frames / (ms * 1e-3), 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
         'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic',
+        'dtype': 'bf16x3' if eng.use_tc else 'f32', 'data': 'synthetic',
         'config': {'workload': f'{PRESET} {W}x{H} synthetic DSEC events (sparse_norm voxel grid 9 bins), {ITERS} iters, batch {Bp}/GPU, '
                                f'random-init weights seed 0', 'global_batch': Bp * world, 'parallelism': f'batch-sharded x{world}',
                    'l2': 'no explicit flush: one step streams a 369 MB correlation volume and ~0.5 GB of encoder activations (> 126 MB L2)',
-                   'cuda_graph': eng.use_graph, 'arithmetic': 'fp32 FFMA (CUDA cores), fp32 storage'},
+                   'cuda_graph': eng.use_graph,
+                   'arithmetic': ('split-bf16 operands (x = hi + lo; hi*hi + hi*lo + lo*hi) on tcgen05 with fp32 TMEM accumulation, fp32 storage; '
+                                  f'{plan.n_tc} of {sum(1 for f, _ in plan.launches if "conv2d" in f.__name__)} convolution launches on tensor cores, '
+                                  '7x7 stems and convf1 on fp32 CUDA cores') if eng.use_tc else 'fp32 FFMA (CUDA cores), fp32 storage'},
         'e2e': {'value': frames / (e2e_ms * 1e-3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': e2e_ms / K, 'api': 'RAFTSpline.forward(voxel_grid=pinned host tensor .to(cuda)) -> BezierCurves.cpu()'},
         'gpu_launches': plan.n_launches * K,

@@ -12,6 +12,7 @@ from . import build as _build
 
 MAX_SLOTS, MAX_TARGETS, MAX_DEGREE = 16, 8, 16
 ACT = {'none': 0, 'relu': 1, 'sigmoid': 2, 'tanh': 3}
+EPI = {'std': 0, 'gru_zr': 1, 'gru_q': 2}
 
 c_float_p = C.c_void_p   # device pointers travel as integers
 
@@ -26,7 +27,10 @@ class ConvDesc(C.Structure):
                 ('N', C.c_int), ('H', C.c_int), ('W', C.c_int), ('Ho', C.c_int), ('Wo', C.c_int), ('Cout', C.c_int),
                 ('KH', C.c_int), ('KW', C.c_int), ('stride', C.c_int), ('pad_h', C.c_int), ('pad_w', C.c_int),
                 ('act1', C.c_int), ('act2', C.c_int),
-                ('scale', C.c_float)]
+                ('scale', C.c_float),
+                ('epi', C.c_int),
+                ('aux0', C.c_void_p), ('ld_aux0', C.c_int),
+                ('aux1', C.c_void_p), ('ld_aux1', C.c_int)]
 
 
 class LookupDesc(C.Structure):
@@ -52,7 +56,10 @@ _SIGNATURES = {
     'bflow_nhwc_to_nchw': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     'bflow_conv2d_nhwc': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     'bflow_conv2d_tc_supported': (C.c_int, [C.POINTER(ConvDesc)]),
-    'bflow_conv2d_nhwc_tc': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    'bflow_conv2d_nhwc_tc': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    'bflow_pack_b_tc': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
+    'bflow_corr_volume_tc': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
+    'bflow_conv2d_small_n': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     'bflow_plane_sums': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'bflow_instnorm_relu': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),

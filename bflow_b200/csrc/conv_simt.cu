@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_simt_kernel(const bflow_conv_de
         __syncthreads();
     }
 
-    // ---- epilogue: out = act2(res + act1(scale * (acc + bias))) ----
+    // ---- epilogue ----
     const int nbase = n0 + tx * 4;
     float bias[4];
 #pragma unroll
@@ -196,25 +196,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_simt_kernel(const bflow_conv_de
         if (m >= M) continue;
         float v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = apply_act(d.scale * (acc[i][j] + bias[j]), d.act1);
-        if (vec_store) {
-            if (d.res != nullptr) {
-                float4 r = *reinterpret_cast<const float4*>(d.res + (size_t)m * d.ldr + nbase);
-                v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], d.act2);
-            *reinterpret_cast<float4*>(d.y + (size_t)m * d.ldy + nbase) = make_float4(v[0], v[1], v[2], v[3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (nbase + j < d.Cout) {
-                    float o = v[j];
-                    if (d.res != nullptr) o += d.res[(size_t)m * d.ldr + nbase + j];
-                    d.y[(size_t)m * d.ldy + nbase + j] = apply_act(o, d.act2);
-                }
-            }
-        }
+        for (int j = 0; j < 4; ++j) v[j] = d.scale * (acc[i][j] + bias[j]);
+        conv_epilogue4(d, m, nbase, v, vec_store);
     }
 }
 
@@ -257,8 +240,105 @@ extern "C" int bflow_conv2d_nhwc(const bflow_conv_desc* dp, void* stream) {
     BFLOW_REQUIRE(d.ldy >= d.Cout, "conv: ldy < Cout");
     BFLOW_REQUIRE(d.res == nullptr || d.ldr >= d.Cout, "conv: ldr < Cout");
     BFLOW_REQUIRE(d.act1 >= 0 && d.act1 <= 3 && d.act2 >= 0 && d.act2 <= 3, "conv: bad activation");
+    if (const char* msg = bflow::check_epilogue(d)) { bflow::set_error(msg); return BFLOW_ERR_INVALID; }
     BFLOW_REQUIRE((long long)d.N * d.Ho * d.Wo < (1ll << 31) && (long long)d.KH * d.KW * (d.c0 + d.c1) < (1ll << 31), "conv: too large");
     return bflow::launch_conv(d, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Direct convolution for tiny Cout: one warp per output pixel, lanes split the (tap, channel) axis in float4 steps,
+// shuffle reduction at the end.  Bezier head conv2 (256 -> 2*degree, update.py:18) fused with the delta update.
+// ---------------------------------------------------------------------------------------------
+namespace bflow {
+template <int NV>   // NV = ceil(Cout/4) float4 accumulators per lane
+__global__ void __launch_bounds__(256) conv_small_n_kernel(const bflow_conv_desc d, const int M) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = blockIdx.x * 8 + warp;
+    if (m >= M) return;
+    const int ow = m % d.Wo;
+    const int t = m / d.Wo;
+    const int oh = t % d.Ho;
+    const int n = t / d.Ho;
+    const int Cin = d.c0;
+    float4 acc[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kh = 0; kh < d.KH; ++kh) {
+        const int ih = oh * d.stride - d.pad_h + kh;
+        if (ih < 0 || ih >= d.H) continue;
+        for (int kw = 0; kw < d.KW; ++kw) {
+            const int iw = ow * d.stride - d.pad_w + kw;
+            if (iw < 0 || iw >= d.W) continue;
+            const float* xp = d.x0 + (((size_t)n * d.H + ih) * d.W + iw) * d.ld0;
+            const float* wp = d.w + (size_t)((kh * d.KW + kw) * Cin) * d.ldw;
+            for (int c = lane * 4; c < Cin; c += 128) {
+                const float4 xv = __ldg(reinterpret_cast<const float4*>(xp + c));
+                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) {
+                        const float4 wv = __ldg(reinterpret_cast<const float4*>(wp + (size_t)(c + e) * d.ldw + 4 * j));
+                        acc[j].x = fmaf(xs[e], wv.x, acc[j].x);
+                        acc[j].y = fmaf(xs[e], wv.y, acc[j].y);
+                        acc[j].z = fmaf(xs[e], wv.z, acc[j].z);
+                        acc[j].w = fmaf(xs[e], wv.w, acc[j].w);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc[j].x += __shfl_xor_sync(0xffffffffu, acc[j].x, o);
+            acc[j].y += __shfl_xor_sync(0xffffffffu, acc[j].y, o);
+            acc[j].z += __shfl_xor_sync(0xffffffffu, acc[j].z, o);
+            acc[j].w += __shfl_xor_sync(0xffffffffu, acc[j].w, o);
+        }
+    }
+    if (lane < NV) {
+        float4 a = acc[0];
+#pragma unroll
+        for (int j = 1; j < NV; ++j) if (lane == j) a = acc[j];
+        const int nb = lane * 4;
+        float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = d.scale * (v[j] + ((d.bias != nullptr && nb + j < d.Cout) ? __ldg(d.bias + nb + j) : 0.f));
+        const bool vec = ((d.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15) == 0) && (nb + 3 < d.Cout) &&
+                         (d.res == nullptr || (((d.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.res) & 15) == 0)));
+        conv_epilogue4(d, m, nb, v, vec);
+    }
+}
+}  // namespace bflow
+
+extern "C" int bflow_conv2d_small_n(const bflow_conv_desc* dp, void* stream) {
+    BFLOW_REQUIRE(dp != nullptr, "conv_small_n: null descriptor");
+    const bflow_conv_desc& d = *dp;
+    BFLOW_REQUIRE(d.x0 != nullptr && d.w != nullptr && d.y != nullptr, "conv_small_n: null tensor");
+    BFLOW_REQUIRE(d.c1 == 0 && d.c0 > 0 && d.c0 % 4 == 0 && d.ld0 % 4 == 0 && bflow::aligned16(d.x0), "conv_small_n: one aligned source, Cin % 4 == 0");
+    BFLOW_REQUIRE(d.Cout > 0 && d.Cout <= 32 && d.ldw % 4 == 0 && d.ldw >= d.Cout && bflow::aligned16(d.w), "conv_small_n: Cout <= 32, packed weights");
+    BFLOW_REQUIRE(d.epi == BFLOW_EPI_STD, "conv_small_n: standard epilogue only");
+    BFLOW_REQUIRE(d.Ho == (d.H + 2 * d.pad_h - d.KH) / d.stride + 1 && d.Wo == (d.W + 2 * d.pad_w - d.KW) / d.stride + 1, "conv_small_n: Ho/Wo mismatch");
+    BFLOW_REQUIRE(d.ldy >= d.Cout && (d.res == nullptr || d.ldr >= d.Cout), "conv_small_n: bad output stride");
+    const long long Mll = (long long)d.N * d.Ho * d.Wo;
+    BFLOW_REQUIRE(Mll > 0 && Mll < (1ll << 31), "conv_small_n: bad shape");
+    const int M = (int)Mll;
+    const int nv = (d.Cout + 3) / 4;
+    dim3 grid((unsigned)bflow::ceil_div(M, 8));
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (nv) {
+        case 1: bflow::conv_small_n_kernel<1><<<grid, 256, 0, st>>>(d, M); break;
+        case 2: bflow::conv_small_n_kernel<2><<<grid, 256, 0, st>>>(d, M); break;
+        case 3: bflow::conv_small_n_kernel<3><<<grid, 256, 0, st>>>(d, M); break;
+        case 4: bflow::conv_small_n_kernel<4><<<grid, 256, 0, st>>>(d, M); break;
+        case 5: bflow::conv_small_n_kernel<5><<<grid, 256, 0, st>>>(d, M); break;
+        case 6: bflow::conv_small_n_kernel<6><<<grid, 256, 0, st>>>(d, M); break;
+        case 7: bflow::conv_small_n_kernel<7><<<grid, 256, 0, st>>>(d, M); break;
+        default: bflow::conv_small_n_kernel<8><<<grid, 256, 0, st>>>(d, M); break;
+    }
+    return bflow::check_launch("bflow_conv2d_small_n");
 }
 
 // corr[bq, p] = sum_d f1[bq, d] * f2[b, d, p] / sqrt(D)   (models/raft_utils/corr.py:264-272)
@@ -277,6 +357,7 @@ extern "C" int bflow_corr_volume(const float* f1, int ld1, const float* f2_nchw,
         d.N = 1; d.H = 1; d.W = Q; d.Ho = 1; d.Wo = Q; d.Cout = Q;
         d.KH = 1; d.KW = 1; d.stride = 1; d.pad_h = 0; d.pad_w = 0;
         d.act1 = BFLOW_ACT_NONE; d.act2 = BFLOW_ACT_NONE;
+        d.epi = BFLOW_EPI_STD;
         d.scale = 1.0f / sqrtf((float)D);
         BFLOW_REQUIRE(bflow::aligned16(d.w), "corr_volume: f2 must be 16B aligned per sample");
         int rc = bflow::launch_conv(d, (cudaStream_t)stream);

@@ -1,35 +1,42 @@
-// Tensor-core implicit-GEMM convolution for sm_100a: tcgen05.mma with TMEM accumulators, split-bf16 operands.
+// Tensor-core implicit-GEMM convolution for sm_100a: tcgen05.mma with TMEM accumulators, split 16-bit operands.
 //
 // Same contract as bflow_conv2d_nhwc (conv_simt.cu):  out = act2(res + act1(scale * (conv(x, w) + bias)))
 // on NHWC fp32 activations, up to two channel-concatenated sources.  Replaces the nn.Conv2d calls of
 // models/raft_utils/extractor.py:49-53,112,120 and models/raft_spline/update.py:17-18,36-45,89-96,112-114.
 //
 // Precision: the parity bar is 1e-3 px against an fp32 reference and single-pass bf16/TF32 operands miss it
-// (SURVEY.md §7.1), so every operand is split x = hi + lo (two bf16) and each product is issued as
-// hi*hi + hi*lo + lo*hi into one fp32 TMEM accumulator (~16 mantissa bits per operand).
+// (SURVEY.md §7.1), so every operand is split x = hi + lo with hi = fp16(x) and lo = fp16(x - hi) (11 + 11 mantissa
+// bits; saturating, |x| < 1.3e5; weights are pre-scaled by a power of two) and each product is issued as
+// hi*hi + hi*lo + lo*hi into one fp32 TMEM accumulator.
 //
-// One CTA = one 128 x BN output tile (BN in {64,128,256} TMEM columns), 5 warps:
-//   warps 0-3  A producers, then epilogue.  Thread t owns 16-byte swizzle chunk (t % 8) of rows t/8 + 16 i:
-//              it gathers 8 fp32 channels of the input pixel that row/tap maps to (zero outside the image),
-//              splits them into bf16 hi/lo and stores them straight into the SWIZZLE_128B K-major layout the
-//              UMMA descriptor expects; fence.proxy.async, then mbarrier arrive on full[stage].
-//              Thread 0 also streams the stage's weight tile (host-packed image of the swizzled smem
-//              tile, hi then lo) with one cp.async.bulk (UBLKCP) that completes on the same barrier.
-//   warp 4     allocates TMEM; one elected lane issues 4 k-steps x 3 tcgen05.mma per stage and
-//              tcgen05.commit's the stage's empty barrier (and the accumulator barrier after the last).
+// One CTA = one 128 x BN output tile (BN in {64,128,256} TMEM columns), 9 warps:
+//   warps 0-7  A producers, then epilogue.  Thread t owns 16-byte swizzle chunk (t & 7) of rows (t >> 3) + 32 i:
+//              it gathers 8 fp32 channels of the input pixel that row/tap maps to (zero outside the image), splits
+//              them into hi/lo and stores them straight into the SWIZZLE_128B K-major layout the UMMA descriptor
+//              expects; fence.proxy.async, then mbarrier arrive on full[stage].  The global loads of k-block kb+1
+//              are issued before k-block kb is stored (register double buffering).  Row invariants (pixel index of
+//              tap (0,0), bit mask of in-image taps) live in registers.
+//              Thread 0 also streams the stage's weight tile (pre-packed image of the swizzled smem tile, hi then
+//              lo) with one cp.async.bulk (UBLKCP) that completes on the same barrier.
+//   warp 8     allocates TMEM; one elected lane issues 4 k-steps x 3 tcgen05.mma per stage and tcgen05.commit's
+//              the stage's empty barrier (and the accumulator barrier after the last).
 //   epilogue   tcgen05.ld 32 lanes x 16 columns -> bias / scale / activation / residual -> float4 stores.
 //
 // K is the flattened (tap, channel) axis k = (kh*KW + kw)*Cin + c in blocks of 64; a block may straddle taps
 // (each 8-channel chunk resolves its own tap), so Cin only has to be a multiple of 8.
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace bflow {
 
 constexpr int TC_BM = 128;
-constexpr int TC_BK = 64;                 // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int TC_THREADS = 160;           // 4 producer/epilogue warps + 1 MMA warp
-constexpr int TC_A_BYTES = TC_BM * 128;   // one bf16 A tile (hi or lo)
+constexpr int TC_BK = 64;                 // 16-bit elements per k-block = one 128-byte swizzle row
+constexpr int TC_A_BYTES = TC_BM * 128;   // one 16-bit A tile (hi or lo)
+constexpr int TC_PRODUCERS = 256;         // 8 producer / epilogue warps
+constexpr int TC_THREADS = TC_PRODUCERS + 32;
+constexpr int TC_UNITS = TC_BM * 8 / TC_PRODUCERS;   // 16-byte chunks per producer thread per k-block (4)
+constexpr int TC_BAR_BYTES = 128;         // full[4], empty[4], accum, tmem slot
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -81,7 +88,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return d;
 }
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -105,33 +112,33 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// split two floats into packed bf16 hi and lo words (element 0 in the low half)
+// split two floats into packed fp16 "hi" and "lo" words (element 0 in the low half): x = hi + lo with hi = fp16(x) and
+// lo = fp16(x - hi): 11 + 11 mantissa bits.  Conversions saturate (no inf): |x| up to 1.3e5 is represented, beyond that it
+// clamps; residuals below 6e-5 are fp16-subnormal with 6e-8 absolute spacing.  (tcgen05 kind::f16 rejects mixed bf16 x fp16
+// operands with an illegal-instruction fault, so a bf16 hi / fp16 lo split is not available.)
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float e0, float e1) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
+    return r;
+}
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    float ra = a - __low2float(h), rb = b - __high2float(h);
-    __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
-    hi = *reinterpret_cast<uint32_t*>(&h);
-    lo = *reinterpret_cast<uint32_t*>(&l);
+    hi = pack_f16x2_sat(a, b);
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    lo = pack_f16x2_sat(a - hf.x, b - hf.y);
 }
 
-struct TcSmemTail {
-    uint64_t full[4];
-    uint64_t empty[4];
-    uint64_t accum;
-    uint32_t tmem_base;
-    int row_n[TC_BM];
-    int row_ih0[TC_BM];
-    int row_iw0[TC_BM];
-};
-
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const bflow_conv_desc d, const uint8_t* __restrict__ wtc, const int M, const int K, const int nkb, int* err) {
-    constexpr int B_BYTES = BN * 128;                          // one bf16 B tile (hi or lo)
+template <int BN, int STAGES, int MINB>
+__global__ void __launch_bounds__(TC_THREADS, MINB)
+conv_tc_kernel(const bflow_conv_desc d, const uint8_t* __restrict__ wtc, const int M, const int nkb, const float acc_scale, int* err) {
+    constexpr int B_BYTES = BN * 128;                          // one 16-bit B tile (hi or lo)
     constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    TcSmemTail* tail = reinterpret_cast<TcSmemTail*>(smem + STAGES * STAGE_BYTES);
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t bars = smem_base + STAGES * STAGE_BYTES;                 // barriers live behind the stages
+    auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
+    auto empty_bar = [&](int s) { return bars + 32u + 8u * (uint32_t)s; };
+    const uint32_t accum_bar = bars + 64u;
+    const uint32_t tmem_slot = bars + 72u;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -139,72 +146,64 @@ conv_tc_kernel(const bflow_conv_desc d, const uint8_t* __restrict__ wtc, const i
     const int n_tile = blockIdx.y;
     const int n0 = n_tile * BN;
     const int Cin = d.c0 + d.c1;
+    const int ntaps = d.KH * d.KW;
 
-    if (tid < TC_BM) {
-        int m = m0 + tid;
-        if (m < M) {
-            int ow = m % d.Wo;
-            int t = m / d.Wo;
-            int oh = t % d.Ho;
-            tail->row_n[tid] = t / d.Ho;
-            tail->row_ih0[tid] = oh * d.stride - d.pad_h;
-            tail->row_iw0[tid] = ow * d.stride - d.pad_w;
-        } else {
-            tail->row_n[tid] = -1;
-            tail->row_ih0[tid] = 0;
-            tail->row_iw0[tid] = 0;
-        }
-    }
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(smem_u32(&tail->full[s]), TC_BM);     // 128 producer arrivals (+ weight bytes via complete_tx)
-            mbar_init(smem_u32(&tail->empty[s]), 1);        // one tcgen05.commit
+            mbar_init(full_bar(s), TC_PRODUCERS);   // every producer thread arrives (+ weight bytes via complete_tx)
+            mbar_init(empty_bar(s), 1);             // one tcgen05.commit
         }
-        mbar_init(smem_u32(&tail->accum), 1);
+        mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tail->tmem_base)), "r"(BN) : "memory");
+    if (warp == TC_PRODUCERS / 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = tail->tmem_base;
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    if (warp < 4) {
+    if (warp < TC_PRODUCERS / 32) {
         // ------------------------------------------------ A producers ------------------------------------------------
-        const int chunk = tid & 7;                 // 16-byte chunk (8 bf16 = 8 source floats) within the 128-byte row
-        const int rbase = tid >> 3;                // rows rbase + 16 i
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-            mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u, err);
-            uint8_t* stage = smem + s * STAGE_BYTES;
-            if (tid == 0) {
-                const uint32_t bar = smem_u32(&tail->full[s]);
-                mbar_expect_tx(bar, 2 * B_BYTES);
-                bulk_g2s(smem_u32(stage + 2 * TC_A_BYTES), wtc + ((size_t)n_tile * nkb + kb) * (2 * B_BYTES), 2 * B_BYTES, bar);
-            }
-            // which tap / channel does this thread's chunk of the k-block fall on?
-            const int kflat = kb * TC_BK + chunk * 8;
-            const bool k_ok = kflat < K;
-            const int tap = k_ok ? kflat / Cin : 0;
-            int c = kflat - tap * Cin;
-            const int kh = tap / d.KW;
-            const int kw = tap - kh * d.KW;
-            const float* src;
-            int ld;
-            if (c < d.c0) { src = d.x0; ld = d.ld0; } else { src = d.x1; ld = d.ld1; c -= d.c0; }
-            float4 va[8], vb[8];
+        const int chunk = tid & 7;
+        int pix0[TC_UNITS];
+        uint32_t tapmask[TC_UNITS];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = rbase + 16 * i;
-                const int n = tail->row_n[r];
-                const int ih = tail->row_ih0[r] + kh;
-                const int iw = tail->row_iw0[r] + kw;
-                if (k_ok && n >= 0 && ih >= 0 && ih < d.H && iw >= 0 && iw < d.W) {
-                    const float4* p = reinterpret_cast<const float4*>(src + (((size_t)n * d.H + ih) * d.W + iw) * ld + c);
+        for (int i = 0; i < TC_UNITS; ++i) {
+            const int m = m0 + (tid >> 3) + 32 * i;
+            pix0[i] = 0;
+            tapmask[i] = 0;
+            if (m < M) {
+                const int ow = m % d.Wo;
+                const int t = m / d.Wo;
+                const int oh = t % d.Ho;
+                const int n = t / d.Ho;
+                const int ih0 = oh * d.stride - d.pad_h, iw0 = ow * d.stride - d.pad_w;
+                pix0[i] = (n * d.H + ih0) * d.W + iw0;
+                for (int kh = 0; kh < d.KH; ++kh)
+                    for (int kw = 0; kw < d.KW; ++kw)
+                        if (ih0 + kh >= 0 && ih0 + kh < d.H && iw0 + kw >= 0 && iw0 + kw < d.W) tapmask[i] |= 1u << (kh * d.KW + kw);
+            }
+        }
+        const uint32_t sts_off = (uint32_t)(tid >> 6) * 1024u + (uint32_t)((tid >> 3) & 7) * 128u + (uint32_t)((chunk ^ ((tid >> 3) & 7)) << 4);
+        // running position of this thread's chunk on the flattened (tap, channel) axis
+        int c = chunk * 8, tap = 0, kh = 0, kw = 0;
+        while (c >= Cin) { c -= Cin; ++tap; if (++kw == d.KW) { kw = 0; ++kh; } }
+        float4 va[TC_UNITS], vb[TC_UNITS];
+
+        auto gather = [&]() {
+            const bool k_ok = tap < ntaps;
+            const float* src = d.x0;
+            int ld = d.ld0, cc = c;
+            if (cc >= d.c0) { src = d.x1; ld = d.ld1; cc -= d.c0; }
+            const int tapoff = kh * d.W + kw;
+#pragma unroll
+            for (int i = 0; i < TC_UNITS; ++i) {
+                if (k_ok && ((tapmask[i] >> tap) & 1u)) {
+                    const float4* p = reinterpret_cast<const float4*>(src + (long long)(pix0[i] + tapoff) * ld + cc);
                     va[i] = __ldg(p);
                     vb[i] = __ldg(p + 1);
                 } else {
@@ -212,31 +211,51 @@ conv_tc_kernel(const bflow_conv_desc d, const uint8_t* __restrict__ wtc, const i
                     vb[i] = va[i];
                 }
             }
+            c += TC_BK;                                  // advance to the next k-block
+            while (c >= Cin) { c -= Cin; ++tap; if (++kw == d.KW) { kw = 0; ++kh; } }
+        };
+
+        gather();
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+            uint4 hi[TC_UNITS], lo[TC_UNITS];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = rbase + 16 * i;
-                uint4 hi, lo;
-                split2(va[i].x, va[i].y, hi.x, lo.x);
-                split2(va[i].z, va[i].w, hi.y, lo.y);
-                split2(vb[i].x, vb[i].y, hi.z, lo.z);
-                split2(vb[i].z, vb[i].w, hi.w, lo.w);
-                const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
-                *reinterpret_cast<uint4*>(stage + off) = hi;
-                *reinterpret_cast<uint4*>(stage + TC_A_BYTES + off) = lo;
+            for (int i = 0; i < TC_UNITS; ++i) {
+                split2(va[i].x, va[i].y, hi[i].x, lo[i].x);
+                split2(va[i].z, va[i].w, hi[i].y, lo[i].y);
+                split2(vb[i].x, vb[i].y, hi[i].z, lo[i].z);
+                split2(vb[i].z, vb[i].w, hi[i].w, lo[i].w);
+            }
+            if (kb + 1 < nkb) gather();              // next k-block's global loads fly while this one is stored and multiplied
+            mbar_wait(empty_bar(s), ph ^ 1u, err);
+            const uint32_t stage = smem_base + (uint32_t)s * STAGE_BYTES;
+            if (tid == 0) {
+                mbar_expect_tx(full_bar(s), 2 * B_BYTES);
+                bulk_g2s(stage + 2 * TC_A_BYTES, wtc + ((size_t)n_tile * nkb + kb) * (2 * B_BYTES), 2 * B_BYTES, full_bar(s));
+            }
+#pragma unroll
+            for (int i = 0; i < TC_UNITS; ++i) {
+                const uint32_t a = stage + sts_off + (uint32_t)i * 4096u;
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hi[i].x), "r"(hi[i].y), "r"(hi[i].z), "r"(hi[i].w) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + TC_A_BYTES), "r"(lo[i].x), "r"(lo[i].y), "r"(lo[i].z), "r"(lo[i].w)
+                             : "memory");
             }
             fence_proxy_async();                    // generic-proxy stores -> visible to the tensor core (async proxy)
-            mbar_arrive(smem_u32(&tail->full[s]));
+            mbar_arrive(full_bar(s));
         }
         // ------------------------------------------------ epilogue ------------------------------------------------
-        mbar_wait(smem_u32(&tail->accum), 0, err);
+        // TMEM lane == tile row; warp w may only touch lanes 32 (w & 3) .. +31; warps w and w + 4 split the columns.
+        mbar_wait(accum_bar, 0, err);
         tc_fence_after();
-        const int row = tid;                        // TMEM lane == tile row; warp w may only touch lanes 32w..32w+31
-        const int m = m0 + row;
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int quad = warp & 3;
+        const int m = m0 + quad * 32 + (tid & 31);
+        const int cbeg = (warp >> 2) * (BN / 2);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
         const bool vec_ok = ((d.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15) == 0) &&
                             (d.res == nullptr || (((d.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.res) & 15) == 0)));
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 16) {
             if (n0 + c0 >= d.Cout) break;           // warp-uniform
             float v[16];
             tmem_ld16(taddr + (uint32_t)c0, v);
@@ -245,79 +264,58 @@ conv_tc_kernel(const bflow_conv_desc d, const uint8_t* __restrict__ wtc, const i
                 for (int j = 0; j < 16; ++j) {
                     const int n = n0 + c0 + j;
                     const float b = (d.bias != nullptr && n < d.Cout) ? __ldg(d.bias + n) : 0.f;
-                    v[j] = apply_act(d.scale * (v[j] + b), d.act1);
+                    v[j] = d.scale * fmaf(v[j], acc_scale, b);
                 }
-                float* yrow = d.y + (size_t)m * d.ldy + n0 + c0;
-                const float* rrow = d.res != nullptr ? d.res + (size_t)m * d.ldr + n0 + c0 : nullptr;
-                if (vec_ok && n0 + c0 + 15 < d.Cout) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        if (rrow != nullptr) {
-                            float4 r4 = *reinterpret_cast<const float4*>(rrow + j);
-                            o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-                        }
-                        o.x = apply_act(o.x, d.act2); o.y = apply_act(o.y, d.act2);
-                        o.z = apply_act(o.z, d.act2); o.w = apply_act(o.w, d.act2);
-                        *reinterpret_cast<float4*>(yrow + j) = o;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (n0 + c0 + j < d.Cout) {
-                            float o = v[j];
-                            if (rrow != nullptr) o += rrow[j];
-                            yrow[j] = apply_act(o, d.act2);
-                        }
-                    }
-                }
+                for (int j = 0; j < 16; j += 4) conv_epilogue4(d, m, n0 + c0 + j, v + j, vec_ok && (n0 + c0 + j + 3 < d.Cout));
             }
         }
         tc_fence_before();
     } else {
         // ------------------------------------------------ MMA issuer ------------------------------------------------
-        // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        // instruction descriptor: D fp32, K-major fp16 A and B, N = BN, M = 128
+        const uint32_t ibase = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        const uint32_t idesc = ibase;                                   // a_format = b_format = 0 (fp16)
         const bool leader = (tid & 31) == 0;
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % STAGES;
             const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-            mbar_wait(smem_u32(&tail->full[s]), ph, err);
+            mbar_wait(full_bar(s), ph, err);
             tc_fence_after();
             if (leader) {
-                const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
+                const uint32_t a_hi = smem_base + (uint32_t)s * STAGE_BYTES;
                 const uint32_t a_lo = a_hi + TC_A_BYTES;
                 const uint32_t b_hi = a_hi + 2 * TC_A_BYTES;
                 const uint32_t b_lo = b_hi + B_BYTES;
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k) {
-                    const uint32_t ko = (uint32_t)k * 32u;      // 16 bf16 = 32 bytes along K inside the swizzle atom
+                    const uint32_t ko = (uint32_t)k * 32u;      // 16 elements = 32 bytes along K inside the swizzle atom
                     const uint64_t dah = umma_desc(a_hi + ko), dal = umma_desc(a_lo + ko);
                     const uint64_t dbh = umma_desc(b_hi + ko), dbl = umma_desc(b_lo + ko);
-                    umma_bf16(tmem_base, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-                    umma_bf16(tmem_base, dal, dbh, idesc, 1u);
+                    umma_f16(tmem_base, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_f16(tmem_base, dah, dbl, idesc, 1u);
+                    umma_f16(tmem_base, dal, dbh, idesc, 1u);
                 }
-                umma_commit(smem_u32(&tail->empty[s]));         // frees the stage when these MMAs have read it
-                if (kb == nkb - 1) umma_commit(smem_u32(&tail->accum));
+                umma_commit(empty_bar(s));                      // frees the stage when these MMAs have read it
+                if (kb == nkb - 1) umma_commit(accum_bar);
             }
             __syncwarp();
         }
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == TC_PRODUCERS / 32) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
     }
 }
 
-template <int BN, int STAGES>
-static int launch_tc(const bflow_conv_desc& d, const void* wtc, int M, int K, int nkb, int* err, cudaStream_t stream) {
-    constexpr int smem = STAGES * (2 * TC_A_BYTES + 2 * BN * 128) + (int)sizeof(TcSmemTail) + 1024;
+template <int BN, int STAGES, int MINB>
+static int launch_tc(const bflow_conv_desc& d, const void* wtc, int M, int nkb, float acc_scale, int* err, cudaStream_t stream) {
+    constexpr int smem = STAGES * (2 * TC_A_BYTES + 2 * BN * 128) + TC_BAR_BYTES + 1024;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) {
             set_error(cudaGetErrorString(e));
             return BFLOW_ERR_CUDA;
@@ -325,11 +323,76 @@ static int launch_tc(const bflow_conv_desc& d, const void* wtc, int M, int K, in
         configured = true;
     }
     dim3 grid((unsigned)ceil_div(M, TC_BM), (unsigned)ceil_div(d.Cout, BN));
-    conv_tc_kernel<BN, STAGES><<<grid, TC_THREADS, smem, stream>>>(d, reinterpret_cast<const uint8_t*>(wtc), M, K, nkb, err);
+    conv_tc_kernel<BN, STAGES, MINB><<<grid, TC_THREADS, smem, stream>>>(d, reinterpret_cast<const uint8_t*>(wtc), M, nkb, acc_scale, err);
     return check_launch("bflow_conv2d_nhwc_tc");
 }
 
 }  // namespace bflow
+
+namespace bflow {
+// fp32 NHWC rows -> tensor-core B-operand image (see bflow_pack_b_tc in the header)
+__global__ void pack_b_tc_kernel(const float* __restrict__ src, int ld, uint8_t* __restrict__ dst, int rows, int K, int bn, int nkb,
+                                 int plane_h, int plane_w) {
+    const int chunks = (K + 7) / 8;
+    const long long total = (long long)rows * chunks;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / chunks);
+        const int ck = (int)(idx - (long long)r * chunks);
+        const int k = ck * 8;
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = (k + e < K) ? __ldg(src + (size_t)r * ld + k + e) : 0.f;
+        uint4 hi, lo;
+        split2(x[0], x[1], hi.x, lo.x);
+        split2(x[2], x[3], hi.y, lo.y);
+        split2(x[4], x[5], hi.z, lo.z);
+        split2(x[6], x[7], hi.w, lo.w);
+        int n = r;
+        if (plane_w > 0) {               // source rows are pixels (y, x): land in 4x4-tiled order
+            const int y = r / plane_w, xx = r - y * plane_w;
+            const int wp4 = (plane_w + 3) >> 2;
+            n = (((y >> 2) * wp4 + (xx >> 2)) << 4) + ((y & 3) << 2) + (xx & 3);
+        }
+        const int tile = n / bn, rr = n - tile * bn;
+        const int kb = ck >> 3, c = ck & 7;
+        uint8_t* base = dst + ((size_t)tile * nkb + kb) * (size_t)(2 * bn * 128) + (size_t)rr * 128 + (size_t)((c ^ (rr & 7)) << 4);
+        *reinterpret_cast<uint4*>(base) = hi;
+        *reinterpret_cast<uint4*>(base + (size_t)bn * 128) = lo;
+    }
+}
+}  // namespace bflow
+
+extern "C" int bflow_pack_b_tc(const float* src, int ld, void* dst, int rows, int K, int bn, int plane_h, int plane_w, void* stream) {
+    BFLOW_REQUIRE(src != nullptr && dst != nullptr, "pack_b_tc: null tensor");
+    BFLOW_REQUIRE(rows > 0 && K > 0 && ld >= K && (bn == 64 || bn == 128 || bn == 256), "pack_b_tc: bad shape");
+    BFLOW_REQUIRE(plane_w == 0 || (plane_h > 0 && plane_h * plane_w == rows), "pack_b_tc: plane does not match rows");
+    BFLOW_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "pack_b_tc: dst must be 16-byte aligned");
+    const int nkb = (K + 63) / 64;
+    const long long total = (long long)rows * ((K + 7) / 8);
+    const unsigned grid = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    bflow::pack_b_tc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld, reinterpret_cast<uint8_t*>(dst), rows, K, bn, nkb, plane_h, plane_w);
+    return bflow::check_launch("bflow_pack_b_tc");
+}
+
+extern "C" int bflow_conv2d_nhwc_tc(const bflow_conv_desc* dp, const void* w_tc, int bn, float acc_scale, int* err, void* stream);
+
+extern "C" int bflow_corr_volume_tc(const float* f1, int ld1, const void* f2_img, long long img_stride, float* corr, int B, int D, int Q, int Np,
+                                    int bn, int* err, void* stream) {
+    BFLOW_REQUIRE(f1 != nullptr && f2_img != nullptr && corr != nullptr, "corr_volume_tc: null tensor");
+    BFLOW_REQUIRE(B > 0 && D > 0 && D % 8 == 0 && Q > 0 && Np >= Q && Np % 4 == 0 && ld1 >= D, "corr_volume_tc: bad shape");
+    for (int b = 0; b < B; ++b) {
+        bflow_conv_desc d{};
+        d.x0 = f1 + (size_t)b * Q * ld1; d.c0 = D; d.ld0 = ld1;
+        d.y = corr + (size_t)b * Q * Np; d.ldy = Np;
+        d.N = 1; d.H = 1; d.W = Q; d.Ho = 1; d.Wo = Q; d.Cout = Np;
+        d.KH = 1; d.KW = 1; d.stride = 1;
+        d.act1 = BFLOW_ACT_NONE; d.act2 = BFLOW_ACT_NONE; d.epi = BFLOW_EPI_STD;
+        d.scale = 1.0f / sqrtf((float)D);
+        int rc = bflow_conv2d_nhwc_tc(&d, reinterpret_cast<const uint8_t*>(f2_img) + (size_t)b * img_stride, bn, 1.0f, err, stream);
+        if (rc != BFLOW_OK) return rc;
+    }
+    return BFLOW_OK;
+}
 
 extern "C" int bflow_conv2d_tc_supported(const bflow_conv_desc* dp) {
     if (dp == nullptr) return 0;
@@ -337,30 +400,34 @@ extern "C" int bflow_conv2d_tc_supported(const bflow_conv_desc* dp) {
     if (d.c0 <= 0 || d.c0 % 8 != 0 || d.c1 % 8 != 0) return 0;
     if (d.ld0 % 4 != 0 || !bflow::aligned16(d.x0)) return 0;
     if (d.c1 > 0 && (d.ld1 % 4 != 0 || !bflow::aligned16(d.x1))) return 0;
+    if (d.KH * d.KW > 32) return 0;                                   // per-row tap validity is a 32-bit mask
+    if ((long long)d.N * d.H * d.W >= (1ll << 31)) return 0;          // pixel indices are 32-bit
     return 1;
 }
 
-// w_tc: host-packed weight image [ceil(Cout/bn)][nkb][hi|lo][bn rows][64 bf16, 16-byte chunks XOR-swizzled by row%8]
-// (bflow_b200/ops.py: pack_conv_weight_tc).  err: optional device int set to 1 if a pipeline wait timed out.
-extern "C" int bflow_conv2d_nhwc_tc(const bflow_conv_desc* dp, const void* w_tc, int bn, int* err, void* stream) {
+// w_tc: packed weight image [ceil(Cout/bn)][nkb][hi | lo (fp16)][bn rows][64 elements, 16-byte chunks XOR-swizzled by row%8]
+// of W / acc_scale (bflow_b200/ops.py: pack_conv_weight_tc; acc_scale is a power of two that keeps the fp16 residuals normal).
+// err: optional device int set to 1 if a pipeline wait timed out.
+extern "C" int bflow_conv2d_nhwc_tc(const bflow_conv_desc* dp, const void* w_tc, int bn, float acc_scale, int* err, void* stream) {
     BFLOW_REQUIRE(dp != nullptr && w_tc != nullptr, "conv_tc: null argument");
     const bflow_conv_desc& d = *dp;
     BFLOW_REQUIRE(d.x0 != nullptr && d.y != nullptr, "conv_tc: null tensor");
-    BFLOW_REQUIRE(bflow_conv2d_tc_supported(dp) == 1, "conv_tc: needs channels % 8 == 0 and 16-byte aligned rows");
+    BFLOW_REQUIRE(bflow_conv2d_tc_supported(dp) == 1, "conv_tc: needs channels % 8 == 0, 16-byte aligned rows, <= 32 taps");
     BFLOW_REQUIRE(d.c1 == 0 || d.x1 != nullptr, "conv_tc: bad source 1");
     BFLOW_REQUIRE(d.N > 0 && d.H > 0 && d.W > 0 && d.Cout > 0, "conv_tc: bad shape");
     BFLOW_REQUIRE(d.Ho == (d.H + 2 * d.pad_h - d.KH) / d.stride + 1 && d.Wo == (d.W + 2 * d.pad_w - d.KW) / d.stride + 1, "conv_tc: Ho/Wo mismatch");
     BFLOW_REQUIRE(d.ldy >= d.Cout && (d.res == nullptr || d.ldr >= d.Cout), "conv_tc: bad output stride");
     BFLOW_REQUIRE((reinterpret_cast<uintptr_t>(w_tc) & 15) == 0, "conv_tc: packed weights must be 16-byte aligned");
+    if (const char* msg = bflow::check_epilogue(d)) { bflow::set_error(msg); return BFLOW_ERR_INVALID; }
     const long long Mll = (long long)d.N * d.Ho * d.Wo;
     const long long Kll = (long long)d.KH * d.KW * (d.c0 + d.c1);
     BFLOW_REQUIRE(Mll < (1ll << 31) && Kll < (1ll << 31), "conv_tc: too large");
-    const int M = (int)Mll, K = (int)Kll, nkb = (K + bflow::TC_BK - 1) / bflow::TC_BK;
+    const int M = (int)Mll, nkb = (int)((Kll + bflow::TC_BK - 1) / bflow::TC_BK);
     cudaStream_t st = (cudaStream_t)stream;
     switch (bn) {
-        case 64: return bflow::launch_tc<64, 4>(d, w_tc, M, K, nkb, err, st);
-        case 128: return bflow::launch_tc<128, 3>(d, w_tc, M, K, nkb, err, st);
-        case 256: return bflow::launch_tc<256, 2>(d, w_tc, M, K, nkb, err, st);
+        case 64: return bflow::launch_tc<64, 2, 2>(d, w_tc, M, nkb, acc_scale, err, st);    // 2 CTAs/SM: epilogue of one overlaps the main loop of the other
+        case 128: return bflow::launch_tc<128, 3, 1>(d, w_tc, M, nkb, acc_scale, err, st);
+        case 256: return bflow::launch_tc<256, 2, 1>(d, w_tc, M, nkb, acc_scale, err, st);
         default: bflow::set_error("conv_tc: bn must be 64, 128 or 256"); return BFLOW_ERR_INVALID;
     }
 }

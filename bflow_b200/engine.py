@@ -20,9 +20,9 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib, config as _cfg
-from ._lib import ACT, ConvDesc, LookupDesc, check
+from ._lib import ACT, EPI, ConvDesc, LookupDesc, check
 from .bezier import bernstein_coeffs
-from .ops import pack_conv_weight, make_lookup_desc
+from .ops import pack_conv_weight, pack_conv_weight_tc, make_lookup_desc
 
 
 def _ceil(a: int, b: int) -> int:
@@ -30,11 +30,18 @@ def _ceil(a: int, b: int) -> int:
 
 
 class _Weight:
-    __slots__ = ('w', 'ldw', 'b', 'cout', 'cin', 'kh', 'kw', 'stride', 'pad')
+    __slots__ = ('w', 'ldw', 'b', 'cout', 'cin', 'kh', 'kw', 'stride', 'pad', 'oihw', 'cin_pad', 'tc')
 
-    def __init__(self, w, ldw, b, cout, cin, kh, kw, stride, pad):
+    def __init__(self, w, ldw, b, cout, cin, kh, kw, stride, pad, oihw, cin_pad):
         self.w, self.ldw, self.b, self.cout, self.cin = w, ldw, b, cout, cin
         self.kh, self.kw, self.stride, self.pad = kh, kw, stride, pad
+        self.oihw, self.cin_pad = oihw, cin_pad
+        self.tc = {}                       # bn -> tensor-core weight image (packed on first use)
+
+    def tc_image(self, bn: int):
+        if bn not in self.tc:
+            self.tc[bn] = pack_conv_weight_tc(self.oihw, bn, self.cin_pad)
+        return self.tc[bn]
 
 
 class Engine:
@@ -43,6 +50,8 @@ class Engine:
         self.device = device
         self.lib = _lib.lib()
         self.use_graph = os.environ.get('BFLOW_GRAPH', '1') != '0'
+        self.use_tc = os.environ.get('BFLOW_TC', '1') != '0'      # tcgen05 convolutions (0: fp32 CUDA-core kernels only)
+        self.err = torch.zeros(1, device=device, dtype=torch.int32)
         self._plans: Dict[tuple, '_Plan'] = {}
         self._pack(model)
 
@@ -56,7 +65,7 @@ class Engine:
         b = b.detach().to(self.device, torch.float32).contiguous()
         O, I, KH, KW = w.shape
         wp, ldw = pack_conv_weight(w, cin_pad)
-        return _Weight(wp, ldw, b, O, I if cin_pad is None else cin_pad, KH, KW, conv.stride, conv.pad)
+        return _Weight(wp, ldw, b, O, I if cin_pad is None else cin_pad, KH, KW, conv.stride, conv.pad, w, cin_pad)
 
     def _mk_folded(self, conv, bn, rows: Optional[slice] = None) -> _Weight:
         """Conv followed by eval-mode BatchNorm (extractor.py:21-25) folded into weight and bias."""
@@ -114,10 +123,18 @@ class Engine:
         U['convc1'] = self._mk(ub.encoder.convc1, cin_pad=self.ldc)
         for n in ('convc2', 'convf1', 'convf2', 'conv'):
             U[n] = self._mk(getattr(ub.encoder, n))
+        hd, cd = self.hdim, self.cdim
         for sfx in '12':
+            # [z | r] share one GEMM (N = 2*hdim).  The K axis of every GRU conv is [h | inp | motion] (update.py:35,38): the `inp`
+            # slice is the same in every iteration, so its contribution (+ bias) is computed once per forward ("*_inp") and the
+            # per-iteration convs only see [h | motion] ("*_dyn").
             z, r, q = getattr(g, 'convz' + sfx), getattr(g, 'convr' + sfx), getattr(g, 'convq' + sfx)
-            U['zr' + sfx] = self._mk(z, torch.cat([z.weight, r.weight], 0), torch.cat([z.bias, r.bias], 0))
-            U['q' + sfx] = self._mk(q)
+            wzr, bzr = torch.cat([z.weight, r.weight], 0), torch.cat([z.bias, r.bias], 0)
+            dyn = lambda w: torch.cat([w[:, :hd], w[:, hd + cd:]], 1).contiguous()
+            U['zr' + sfx + '_inp'] = self._mk(z, wzr[:, hd:hd + cd].contiguous(), bzr)
+            U['zr' + sfx + '_dyn'] = self._mk(z, dyn(wzr), bzr)
+            U['q' + sfx + '_inp'] = self._mk(q, q.weight[:, hd:hd + cd].contiguous(), q.bias)
+            U['q' + sfx + '_dyn'] = self._mk(q, dyn(q.weight), q.bias)
         U['head1'], U['head2'] = self._mk(ub.bezier_head.conv1), self._mk(ub.bezier_head.conv2)
         U['mask0'], U['mask2'] = self._mk(ub.mask[0]), self._mk(ub.mask[2])
         self.upd = U
@@ -154,9 +171,11 @@ class _Plan:
         self.Q = self.h * self.w
         self.R = B * self.Q
         self.launches: List[Tuple] = []
+        self.labels: List[Tuple[str, float]] = []
         self.keep: List = []           # descriptors / tensors referenced by raw pointer
         self.graph = None
         self.n_launches = 0
+        self.n_tc = 0
         f32 = dict(device=dev, dtype=torch.float32)
         self.use_ev, self.use_img = cfg['use_events'], cfg['use_boundary_images']
         nctx, ncorr = cfg['num_bins']['context'], cfg['num_bins']['correlation']
@@ -172,15 +191,17 @@ class _Plan:
         self._record()
 
     # ---- recording helpers -------------------------------------------------------------------------------
-    def _add(self, fn, *args):
+    def _add(self, fn, *args, label: Optional[str] = None, flops: float = 0.0):
         self.launches.append((fn, args))
+        self.labels.append((label or fn.__name__.replace('bflow_', ''), flops))
 
     def _conv(self, wt, x0, c0, ld0, N, H, W, y, ldy, act1='none', act2='none', res=None, ldr=0,
-              x1=None, c1=0, ld1=0, scale=1.0):
+              x1=None, c1=0, ld1=0, scale=1.0, bias=True, epi='std', aux0=None, ld_aux0=0, aux1=None, ld_aux1=0, kernel='auto'):
         d = ConvDesc()
         d.x0, d.c0, d.ld0 = x0, c0, ld0
         d.x1, d.c1, d.ld1 = x1, c1, ld1
-        d.w, d.ldw, d.bias = wt.w.data_ptr(), wt.ldw, wt.b.data_ptr()
+        d.w, d.ldw, d.bias = wt.w.data_ptr(), wt.ldw, (wt.b.data_ptr() if bias else None)
+        d.epi, d.aux0, d.ld_aux0, d.aux1, d.ld_aux1 = EPI[epi], aux0, ld_aux0, aux1, ld_aux1
         d.res, d.ldr = res, ldr
         d.y, d.ldy = y, ldy
         ph, pw = wt.pad
@@ -190,7 +211,19 @@ class _Plan:
         d.act1, d.act2, d.scale = ACT[act1], ACT[act2], scale
         assert c0 + c1 == wt.cin, (c0, c1, wt.cin)
         self.keep.append(d)
-        self._add(self.eng.lib.bflow_conv2d_nhwc, C.byref(d))
+        lib = self.eng.lib
+        flops = 2.0 * N * Ho * Wo * wt.cout * wt.kh * wt.kw * (c0 + c1)
+        if kernel == 'small_n':
+            self._add(lib.bflow_conv2d_small_n, C.byref(d), label=f'conv_small_n {c0 + c1}->{wt.cout} {wt.kh}x{wt.kw}/{wt.stride} M={N * Ho * Wo}', flops=flops)
+        elif self.eng.use_tc and lib.bflow_conv2d_tc_supported(C.byref(d)) == 1:
+            mtiles = (N * Ho * Wo + 127) // 128
+            bn = 64 if (wt.cout <= 64 or mtiles * ((wt.cout + 127) // 128) < 148) else 128
+            img, acc_scale = wt.tc_image(bn)
+            self._add(lib.bflow_conv2d_nhwc_tc, C.byref(d), img.data_ptr(), bn, acc_scale, self.eng.err.data_ptr(),
+                      label=f'conv_tc{bn} {c0 + c1}->{wt.cout} {wt.kh}x{wt.kw}/{wt.stride} M={N * Ho * Wo}', flops=flops)
+            self.n_tc += 1
+        else:
+            self._add(lib.bflow_conv2d_nhwc, C.byref(d), label=f'conv_simt {c0 + c1}->{wt.cout} {wt.kh}x{wt.kw}/{wt.stride} M={N * Ho * Wo}', flops=flops)
         return Ho, Wo
 
     def _sums(self, N, Cc):
@@ -333,15 +366,27 @@ class _Plan:
 
         # ---- correlation volume + pyramid (corr.py:264-272, 293-305) ----
         self.vol0 = torch.empty(T, R, h, w, **f32)
-        if self.use_ev:
-            self.f2_ev = torch.empty(T_ev * B, fd, Q, **f32)
-            self._add(L.bflow_nhwc_to_nchw, fm_ev.data_ptr() + B * Q * fd * 4, self.f2_ev.data_ptr(), T_ev * B, fd, h, w, fd)
-            for t in range(T_ev):
-                self._add(L.bflow_corr_volume, fm_ev.data_ptr(), fd, self.f2_ev.data_ptr() + t * B * fd * Q * 4, self.vol0[t].data_ptr(), B, fd, Q)
-        if self.use_img:
-            self.f2_img = torch.empty(B, fd, Q, **f32)
-            self._add(L.bflow_nhwc_to_nchw, fm_img.data_ptr() + B * Q * fd * 4, self.f2_img.data_ptr(), B, fd, h, w, fd)
-            self._add(L.bflow_corr_volume, fm_img.data_ptr(), fd, self.f2_img.data_ptr(), self.vol0[T_ev].data_ptr(), B, fd, Q)
+        if eng.use_tc and fd % 8 == 0 and Q % 4 == 0:
+            # tensor-core GEMM: the target feature map is packed once into the B-operand image (hi/lo fp16, swizzled)
+            bn = 128
+            img_bytes = ((Q + bn - 1) // bn) * ((fd + 63) // 64) * 2 * bn * 128
+            self.f2img = torch.zeros(T, B, img_bytes, device=dev, dtype=torch.uint8)
+            srcs = [(fm_ev, (t + 1) * B, fm_ev) for t in range(T_ev)] + ([(fm_img, B, fm_img)] if self.use_img else [])
+            for t, (fm2, n0, fm1) in enumerate(srcs):
+                for b in range(B):
+                    self._add(L.bflow_pack_b_tc, fm2.data_ptr() + (n0 + b) * Q * fd * 4, fd, self.f2img[t, b].data_ptr(), Q, fd, bn, 0, 0)
+                self._add(L.bflow_corr_volume_tc, fm1.data_ptr(), fd, self.f2img[t].data_ptr(), img_bytes, self.vol0[t].data_ptr(), B, fd, Q, Q, bn,
+                          eng.err.data_ptr(), label=f'corr_volume_tc Q={Q} D={fd}', flops=2.0 * B * Q * Q * fd)
+        else:
+            if self.use_ev:
+                self.f2_ev = torch.empty(T_ev * B, fd, Q, **f32)
+                self._add(L.bflow_nhwc_to_nchw, fm_ev.data_ptr() + B * Q * fd * 4, self.f2_ev.data_ptr(), T_ev * B, fd, h, w, fd)
+                for t in range(T_ev):
+                    self._add(L.bflow_corr_volume, fm_ev.data_ptr(), fd, self.f2_ev.data_ptr() + t * B * fd * Q * 4, self.vol0[t].data_ptr(), B, fd, Q)
+            if self.use_img:
+                self.f2_img = torch.empty(B, fd, Q, **f32)
+                self._add(L.bflow_nhwc_to_nchw, fm_img.data_ptr() + B * Q * fd * 4, self.f2_img.data_ptr(), B, fd, h, w, fd)
+                self._add(L.bflow_corr_volume, fm_img.data_ptr(), fd, self.f2_img.data_ptr(), self.vol0[T_ev].data_ptr(), B, fd, Q)
         pyr: List[Tuple[List[int], torch.Tensor]] = [(list(range(T)), self.vol0)]
         for lvl in range(1, max(eng.levels)):
             prev_idx, prev = pyr[-1]
@@ -374,16 +419,21 @@ class _Plan:
         self.f1 = torch.empty(R, 128, **f32)
         self.zr = torch.empty(R, 2 * hd, **f32)
         self.rh = torch.empty(R, hd, **f32)
-        self.qb = torch.empty(R, hd, **f32)
         self.hh = torch.empty(R, 256, **f32)
         self.mask = torch.empty(R, 576, **f32)
-        c1, cb, f1, zr, rh, qb, hh, mk = (t.data_ptr() for t in (self.c1, self.cb, self.f1, self.zr, self.rh, self.qb, self.hh, self.mask))
+        c1, cb, f1, zr, rh, hh, mk = (t.data_ptr() for t in (self.c1, self.cb, self.f1, self.zr, self.rh, self.hh, self.mask))
         xw = cd + md                                   # x = [inp | motion features]
 
         def upsample(out_t):
             self._conv(U['mask0'], hx, hd, gw, B, h, w, hh, 256, act1='relu')
             self._conv(U['mask2'], hh, 256, 256, B, h, w, mk, 576, scale=0.25)
             self._add(L.bflow_cvx_upsample, hx + poff * 4, gw, 0, mk, 576, 0, out_t.data_ptr(), B, 2 * deg, h, w)
+
+        # iteration-invariant part of the GRU convolutions: conv(inp) + bias for z|r and q of both passes
+        self.pre = {k: torch.empty(R, (2 * hd if k.startswith('zr') else hd), **f32) for k in ('zr1', 'q1', 'zr2', 'q2')}
+        pre = {k: v.data_ptr() for k, v in self.pre.items()}
+        for k in ('zr1', 'q1', 'zr2', 'q2'):
+            self._conv(U[k + '_inp'], hx + hd * 4, cd, gw, B, h, w, pre[k], self.pre[k].shape[1])
 
         self.iter_start = len(self.launches)
         for itr in range(self.iters):
@@ -399,13 +449,16 @@ class _Plan:
             self._conv(U['conv'], cb, 256, 256, B, h, w, hx + (hd + cd) * 4, gw, act1='relu')
             # SepConvGRU (update.py:33-48): horizontal then vertical pass
             for sfx in '12':
-                self._conv(U['zr' + sfx], hx, gw, gw, B, h, w, zr, 2 * hd, act1='sigmoid')
-                self._add(L.bflow_gru_rh, zr, 2 * hd, hx, gw, rh, hd, R, hd)
-                self._conv(U['q' + sfx], rh, hd, hd, B, h, w, qb, hd, act1='tanh', x1=hx + hd * 4, c1=xw, ld1=gw)
-                self._add(L.bflow_gru_update, zr, 2 * hd, qb, hd, hx, gw, R, hd)
+                # z|r = sigmoid(conv([h | motion]) + inp part); epilogue also emits r*h.   q = tanh(conv([r*h | motion]) + inp part);
+                # epilogue applies h = (1-z) h + z q in place.
+                self._conv(U['zr' + sfx + '_dyn'], hx, hd, gw, B, h, w, zr, 2 * hd, x1=hx + (hd + cd) * 4, c1=md, ld1=gw, bias=False,
+                           res=pre['zr' + sfx], ldr=2 * hd, epi='gru_zr', aux0=hx, ld_aux0=gw, aux1=rh, ld_aux1=hd)
+                self._conv(U['q' + sfx + '_dyn'], rh, hd, hd, B, h, w, hx, gw, x1=hx + (hd + cd) * 4, c1=md, ld1=gw, bias=False,
+                           res=pre['q' + sfx], ldr=hd, epi='gru_q', aux0=zr, ld_aux0=2 * hd)
             # Bezier head + delta update in place (update.py:17-18, bezier.py:137-139)
             self._conv(U['head1'], hx, hd, gw, B, h, w, hh, 256, act1='relu')
-            self._conv(U['head2'], hh, 256, 256, B, h, w, hx + poff * 4, gw, res=hx + poff * 4, ldr=gw)
+            self._conv(U['head2'], hh, 256, 256, B, h, w, hx + poff * 4, gw, res=hx + poff * 4, ldr=gw,
+                       kernel='small_n' if 2 * deg <= 32 else 'auto')
             if not self.test_mode:
                 upsample(self.ups[itr])
         if self.iters == 1:
@@ -439,6 +492,11 @@ class _Plan:
             if rc != 0:
                 check(rc, fn.__name__)
 
+    def check(self):
+        """Synchronises and raises if a tensor-core pipeline wait timed out (never expected)."""
+        if int(self.eng.err.item()) != 0:
+            raise RuntimeError('bflow_b200: a tcgen05 pipeline wait timed out inside a kernel')
+
     def execute(self):
         if not self.eng.use_graph:
             self.launch_all()
@@ -446,6 +504,7 @@ class _Plan:
         if self.graph is None:
             self.launch_all()                         # eager warm-up (also surfaces contract errors outside capture)
             torch.cuda.current_stream().synchronize()
+            self.check()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self.launch_all()

@@ -5,6 +5,7 @@ reference's error convention), output allocation, current-stream plumbing.  Used
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -59,29 +60,36 @@ def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None) -> Tuple[to
     return p.reshape(KH * KW * ci, ldw).contiguous(), ldw
 
 
-def pack_conv_weight_tc(w: torch.Tensor, bn: int, cin_pad: Optional[int] = None) -> torch.Tensor:
-    """OIHW fp32 → the tensor-core weight image of bflow_conv2d_nhwc_tc:
-    [ceil(O/bn)][ceil(K/64)][hi|lo][bn][64] bf16 with K = (kh*KW+kw)*Cin + c flattened and the 16-byte chunks of
-    every 128-byte row XOR-swizzled by (row % 8) — byte for byte the SWIZZLE_128B shared-memory tile."""
+def pack_conv_weight_tc(w: torch.Tensor, bn: int, cin_pad: Optional[int] = None, prescale: bool = True) -> Tuple[torch.Tensor, float]:
+    """OIHW fp32 → (tensor-core weight image of bflow_conv2d_nhwc_tc, acc_scale).
+    Image: [ceil(O/bn)][ceil(K/64)][hi | lo (fp16)][bn][64] with K = (kh*KW+kw)*Cin + c flattened and the 16-byte
+    chunks of every 128-byte row XOR-swizzled by (row % 8) — byte for byte the SWIZZLE_128B shared-memory tile.
+    The weights are multiplied by 2^k (largest magnitude in [0.5, 1)) so that the fp16 residuals stay normal;
+    acc_scale = 2^-k is applied to the fp32 accumulator (exact)."""
     O, I, KH, KW = w.shape
     ci = I if cin_pad is None else cin_pad
     K = KH * KW * ci
     nkb, nt = (K + 63) // 64, (O + bn - 1) // bn
+    w = w.detach().float()
+    k = 0
+    amax = float(w.abs().max())
+    if prescale and amax > 0:
+        k = max(-16, min(16, int(math.floor(-math.log2(amax)))))
     wk = torch.zeros(nt * bn, nkb * 64, device=w.device, dtype=torch.float32)
     wp = torch.zeros(O, KH, KW, ci, device=w.device, dtype=torch.float32)
-    wp[..., :I] = w.detach().float().permute(0, 2, 3, 1)
+    wp[..., :I] = (w * (2.0 ** k)).permute(0, 2, 3, 1)
     wk[:O, :K] = wp.reshape(O, K)
-    hi = wk.to(torch.bfloat16)
-    lo = (wk - hi.float()).to(torch.bfloat16)
+    hi = wk.clamp(-65504.0, 65504.0).to(torch.float16)
+    lo = (wk - hi.float()).clamp(-65504.0, 65504.0).to(torch.float16)
     r = torch.arange(bn, device=w.device) % 8
     src_chunk = (torch.arange(8, device=w.device)[None, :] ^ r[:, None])          # dst chunk j <- source chunk j ^ (row % 8)
     idx = src_chunk[None, None, :, :, None].expand(nt, nkb, bn, 8, 8)
 
     def tile(x):
-        x = x.view(nt, bn, nkb, 8, 8).permute(0, 2, 1, 3, 4)                       # tile, k-block, row, chunk, element
+        x = x.view(torch.int16).view(nt, bn, nkb, 8, 8).permute(0, 2, 1, 3, 4)     # tile, k-block, row, chunk, element
         return torch.gather(x, 3, idx)
     img = torch.stack([tile(hi), tile(lo)], dim=2).contiguous()                    # tile, k-block, hi|lo, row, chunk, element
-    return img.view(-1)
+    return img.view(-1), 2.0 ** (-k)
 
 
 def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, stride: int = 1,
@@ -108,9 +116,9 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     d.KH, d.KW, d.stride, d.pad_h, d.pad_w = KH, KW, stride, ph, pw
     d.act1, d.act2, d.scale = ACT[act], 0, scale
     if backend == 'tc':
-        wtc = pack_conv_weight_tc(weight, bn)
+        wtc, acc_scale = pack_conv_weight_tc(weight, bn)
         err = torch.zeros(1, device=x.device, dtype=torch.int32)
-        check(_lib.lib().bflow_conv2d_nhwc_tc(C.byref(d), wtc.data_ptr(), bn, err.data_ptr(), _stream()), 'conv2d_tc')
+        check(_lib.lib().bflow_conv2d_nhwc_tc(C.byref(d), wtc.data_ptr(), bn, acc_scale, err.data_ptr(), _stream()), 'conv2d_tc')
         if int(err.item()) != 0:
             raise RuntimeError('bflow_conv2d_nhwc_tc: pipeline wait timed out inside the kernel')
     else:

@@ -33,6 +33,15 @@ extern "C" {
 #define BFLOW_ACT_SIGMOID 2
 #define BFLOW_ACT_TANH 3
 
+/* epilogue modes of bflow_conv_desc.epi
+ *   STD     out = act2(res + act1(scale*(conv + bias)))
+ *   GRU_ZR  Cout = 2C, columns [z | r]:  g = sigmoid(conv + bias + res);  y = g;  for the r half also
+ *           aux1[m, n-C] = g * aux0[m, n-C]            (aux0 = h, aux1 = r*h : update.py:37-39)
+ *   GRU_Q   q = tanh(conv + bias + res);  z = aux0[m, n];  y[m, n] = (1-z)*y[m, n] + z*q   (y = h in place, update.py:39-40) */
+#define BFLOW_EPI_STD 0
+#define BFLOW_EPI_GRU_ZR 1
+#define BFLOW_EPI_GRU_Q 2
+
 #define BFLOW_MAX_SLOTS 16
 #define BFLOW_MAX_TARGETS 8
 #define BFLOW_MAX_DEGREE 16
@@ -70,18 +79,38 @@ typedef struct bflow_conv_desc {
     int KH, KW, stride, pad_h, pad_w;
     int act1, act2;
     float scale;
+    /* fused SepConvGRU epilogues (update.py:36-40); epi = BFLOW_EPI_STD ignores aux0/aux1 */
+    int epi;
+    const float* aux0; int ld_aux0;
+    float* aux1; int ld_aux1;
 } bflow_conv_desc;
 int bflow_conv2d_nhwc(const bflow_conv_desc* d, void* stream);
 
-/* Tensor-core form of the same operator (tcgen05.mma, TMEM accumulators, split-bf16 operands: every fp32
- * operand x = hi + lo in bf16, products hi*hi + hi*lo + lo*hi accumulated in fp32).  `d->w/ldw` are ignored;
- * `w_tc` is the host-packed weight image  [ceil(Cout/bn)][ceil(K/64)][hi|lo][bn rows][64 bf16]  whose 16-byte
- * chunks are XOR-swizzled by (row % 8), i.e. the exact SWIZZLE_128B shared-memory tile (bflow_b200/ops.py
- * pack_conv_weight_tc).  Needs c0 % 8 == 0, c1 % 8 == 0, ld % 4 == 0 and 16-byte aligned sources
+/* Tensor-core form of the same operator (tcgen05.mma, TMEM accumulators, split 16-bit operands: every fp32
+ * operand x = hi + lo with hi = fp16(x), lo = fp16(x - hi), saturating at |x| = 1.3e5; products hi*hi + hi*lo + lo*hi
+ * accumulated in fp32).
+ * `d->w/ldw` are ignored; `w_tc` is the packed image of W / acc_scale
+ *   [ceil(Cout/bn)][ceil(K/64)][hi | lo (fp16)][bn rows][64 elements]
+ * whose 16-byte chunks are XOR-swizzled by (row % 8), i.e. byte for byte the SWIZZLE_128B shared-memory tile
+ * (bflow_b200/ops.py pack_conv_weight_tc); acc_scale (a power of two) is multiplied back onto the accumulator.
+ * Needs c0 % 8 == 0, c1 % 8 == 0, ld % 4 == 0, 16-byte aligned sources and KH*KW <= 32
  * (bflow_conv2d_tc_supported returns 1).  bn in {64,128,256}.  `err`: optional device int, set to 1 if an
  * in-kernel pipeline wait timed out (never expected; the waits are bounded so that a bug cannot hang the GPU). */
 int bflow_conv2d_tc_supported(const bflow_conv_desc* d);
-int bflow_conv2d_nhwc_tc(const bflow_conv_desc* d, const void* w_tc, int bn, int* err, void* stream);
+/* Packs NHWC fp32 rows (rows x K at stride ld) into the tensor-core B-operand image above (rows play the role of
+ * output channels): used for the correlation volume, whose "weights" are the target feature map.  dst must be
+ * zero-initialised once (rows beyond `rows` in the last tile stay zero).  Row r of the source lands at image row
+ * perm(r): identity when tile_w == 0; otherwise the source rows are pixels (y, x) of a tile_h x tile_w plane and
+ * land in 4x4-pixel-tiled order (the layout bflow_corr_lookup reads with tiled = 1). */
+int bflow_pack_b_tc(const float* src, int ld, void* dst, int rows, int K, int bn, int plane_h, int plane_w, void* stream);
+/* Correlation volume on tensor cores (corr.py:264-272): corr[bq, n] = sum_d f1[bq, d] * f2[n, d] / sqrt(D), n in [0, Np).
+ * f2_img: per-sample images from bflow_pack_b_tc (img_stride bytes apart). */
+int bflow_corr_volume_tc(const float* f1, int ld1, const void* f2_img, long long img_stride, float* corr,
+                         int B, int D, int Q, int Np, int bn, int* err, void* stream);
+/* Direct convolution for tiny Cout (<= 32): one warp per output pixel, K split over lanes, shuffle reduction.
+ * Same descriptor and packed weights as bflow_conv2d_nhwc (Bezier head conv2: 256 -> 2*degree, update.py:18). */
+int bflow_conv2d_small_n(const bflow_conv_desc* d, void* stream);
+int bflow_conv2d_nhwc_tc(const bflow_conv_desc* d, const void* w_tc, int bn, float acc_scale, int* err, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * InstanceNorm2d (biased variance, eps, no affine; extractor.py:27-31) in two passes:

@@ -65,6 +65,26 @@ def test_forward_matches_oracle_all_modes(preset, B, H, W, iters, kind):
     assert (up2.get_params().cpu() - want_list[-1]).abs().max() <= EPE_BAR
 
 
+def test_forward_cuda_core_fp32_path(monkeypatch):
+    """BFLOW_TC=0: every convolution on the exact-fp32 CUDA-core kernel (the numerical anchor of the tcgen05 path)."""
+    monkeypatch.setenv('BFLOW_TC', '0')
+    g = load_golden('d_128_i4_bn')
+    cfg, net, sd, vg, im = build_case(g)
+    low, up = run_cuda(net, vg, im, iters=int(g['iters']), test_mode=True)
+    assert net.engine().plan(int(g['B']), int(g['H']), int(g['W']), int(g['iters']), True).n_tc == 0
+    assert np.abs(up.get_params().cpu().numpy() - g['up']).max() <= 1e-4
+
+
+def test_tensor_core_path_is_the_default():
+    cfg = config.preset('E_LU4_BD2')
+    net = RAFTSpline(cfg, seed=1).to(DEV)
+    vg, _ = synthetic.inputs(cfg, 1, 64, 96, seed=3)
+    net(voxel_grid=vg.to(DEV), iters=1, test_mode=True)
+    plan = net.engine().plan(1, 64, 96, 1, True)
+    assert plan.n_tc >= 40, plan.n_tc           # all but the 7x7 stems and convf1 run on tcgen05
+    plan.check()
+
+
 def test_graph_replay_equals_eager_and_is_repeatable(monkeypatch):
     cfg = config.preset('E_LU4_BD2')
     vg, _ = synthetic.inputs(cfg, 1, 128, 160, seed=3)

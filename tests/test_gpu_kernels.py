@@ -39,6 +39,28 @@ def test_conv2d_matches_torch(N, Cin, H, W, Cout, k, s, p, act):
     assert (out - ref).abs().max() < 2e-5
 
 
+@pytest.mark.parametrize('N,Cin,H,W,Cout,k,s,p,act,bn', [
+    (1, 64, 8, 16, 64, (1, 1), 1, (0, 0), 'none', 64),
+    (1, 576, 10, 13, 256, (1, 1), 1, (0, 0), 'relu', 128),     # ring wraps, ragged M, 2 n-tiles
+    (1, 64, 8, 16, 256, (1, 1), 1, (0, 0), 'none', 256),
+    (2, 64, 12, 20, 96, (3, 3), 2, (1, 1), 'none', 128),
+    (1, 96, 16, 24, 128, (3, 3), 1, (1, 1), 'relu', 64),       # k-blocks straddle taps
+    (1, 384, 8, 12, 256, (1, 5), 1, (0, 2), 'sigmoid', 64),
+    (1, 384, 8, 12, 128, (5, 1), 1, (2, 0), 'tanh', 128),
+    (1, 256, 8, 12, 4, (3, 3), 1, (1, 1), 'none', 64),
+    (4, 128, 40, 60, 64, (3, 3), 1, (1, 1), 'relu', 64),
+])
+def test_conv2d_tensor_core_matches_torch(N, Cin, H, W, Cout, k, s, p, act, bn):
+    """tcgen05 path with split-bf16 operands: ~16 mantissa bits per operand, fp32 accumulate."""
+    x = torch.randn(N, Cin, H, W, generator=g(1))
+    w = torch.randn(Cout, Cin, *k, generator=g(2)) / (Cin * k[0] * k[1]) ** 0.5
+    b = torch.randn(Cout, generator=g(3))
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride=s, padding=p).float()
+    ref = {'none': lambda t: t, 'relu': torch.relu, 'sigmoid': torch.sigmoid, 'tanh': torch.tanh}[act](ref)
+    out = ops.conv2d(x.to(DEV), w.to(DEV), b.to(DEV), stride=s, padding=p, act=act, backend='tc', bn=bn).cpu()
+    assert (out - ref).abs().max() < 1e-4
+
+
 def test_instance_norm_relu_variants():
     x = torch.randn(3, 96, 17, 23, generator=g(1)) * 3 + 1
     r = torch.randn(3, 96, 17, 23, generator=g(2))

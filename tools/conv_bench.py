@@ -1,0 +1,63 @@
+"""Single-convolution microbench / ncu target.
+    python tools/conv_bench.py --n 1 --cin 384 --h 60 --w 80 --cout 128 --kh 1 --kw 5 --backend tc --bn 64"""
+import argparse
+import ctypes as C
+import os
+import statistics
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bflow_b200 import ops, _lib  # noqa: E402
+from bflow_b200._lib import ConvDesc  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    for k, v in dict(n=1, cin=384, h=60, w=80, cout=128, kh=1, kw=5, stride=1, bn=64, reps=10).items():
+        ap.add_argument('--' + k, type=int, default=v)
+    ap.add_argument('--backend', default='tc')
+    a = ap.parse_args()
+    dev = torch.device('cuda:0')
+    lib = _lib.lib()
+    ph, pw = a.kh // 2, a.kw // 2
+    Ho, Wo = (a.h + 2 * ph - a.kh) // a.stride + 1, (a.w + 2 * pw - a.kw) // a.stride + 1
+    x = torch.randn(a.n, a.h, a.w, a.cin, device=dev)
+    w = torch.randn(a.cout, a.cin, a.kh, a.kw, device=dev) / (a.cin * a.kh * a.kw) ** 0.5
+    b = torch.randn(a.cout, device=dev)
+    y = torch.empty(a.n, Ho, Wo, a.cout, device=dev)
+    wp, ldw = ops.pack_conv_weight(w)
+    wtc, acc_scale = ops.pack_conv_weight_tc(w, a.bn)
+    err = torch.zeros(1, device=dev, dtype=torch.int32)
+    d = ConvDesc()
+    d.x0, d.c0, d.ld0 = x.data_ptr(), a.cin, a.cin
+    d.x1, d.c1, d.ld1 = None, 0, 0
+    d.w, d.ldw, d.bias = wp.data_ptr(), ldw, b.data_ptr()
+    d.res, d.ldr = None, 0
+    d.y, d.ldy = y.data_ptr(), a.cout
+    d.N, d.H, d.W, d.Ho, d.Wo, d.Cout = a.n, a.h, a.w, Ho, Wo, a.cout
+    d.KH, d.KW, d.stride, d.pad_h, d.pad_w = a.kh, a.kw, a.stride, ph, pw
+    d.act1, d.act2, d.scale = 1, 0, 1.0
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        if a.backend == 'tc':
+            _lib.check(lib.bflow_conv2d_nhwc_tc(C.byref(d), wtc.data_ptr(), a.bn, acc_scale, err.data_ptr(), st), 'tc')
+        else:
+            _lib.check(lib.bflow_conv2d_nhwc(C.byref(d), st), 'simt')
+    for _ in range(3):
+        run()
+    ts = []
+    for _ in range(a.reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    t = statistics.median(ts)
+    fl = 2.0 * a.n * Ho * Wo * a.cout * a.kh * a.kw * a.cin
+    print(f'{a.backend} bn={a.bn} {a.cin}->{a.cout} {a.kh}x{a.kw}/{a.stride} M={a.n * Ho * Wo}: {t * 1e3:.1f} us  {fl / (t * 1e-3) / 1e12:.1f} TF/s useful; err flag {int(err.item())}')
+
+
+if __name__ == '__main__':
+    main()
