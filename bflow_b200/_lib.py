@@ -44,7 +44,8 @@ class LookupDesc(C.Structure):
                 ('coef', (C.c_float * MAX_DEGREE) * MAX_TARGETS),
                 ('out', C.c_void_p),
                 ('out_nhwc', C.c_int),
-                ('out_ld', C.c_int)]
+                ('out_ld', C.c_int),
+                ('tiled', C.c_int)]
 
 
 _SIGNATURES = {
@@ -65,6 +66,7 @@ _SIGNATURES = {
                                       C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     'bflow_corr_volume': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'bflow_corr_pool': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    'bflow_corr_pool_tiled': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     'bflow_corr_lookup': (C.c_int, [C.POINTER(LookupDesc), C.c_void_p]),
     'bflow_gru_rh': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
     'bflow_gru_update': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),

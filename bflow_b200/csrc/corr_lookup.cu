@@ -19,6 +19,12 @@
 
 namespace bflow {
 
+// 4x4-pixel-tiled plane layout: tile (y>>2, x>>2) row-major over ceil(w/4) tiles, 16 floats per tile
+__host__ __device__ __forceinline__ int tiled_index(int y, int x, int w) {
+    return ((((y >> 2) * ((w + 3) >> 2)) + (x >> 2)) << 4) + ((y & 3) << 2) + (x & 3);
+}
+__host__ __device__ __forceinline__ int tiled_plane_size(int h, int w) { return ((h + 3) >> 2) * ((w + 3) >> 2) * 16; }
+
 constexpr int LK_QPB = 32;        // queries per CTA
 constexpr int LK_WARPS = 8;
 constexpr int LK_QPW = LK_QPB / LK_WARPS;   // 4 queries per warp
@@ -40,7 +46,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) corr_lookup_kernel(const bflow_
     const int hl = d.hl[slot], wl = d.wl[slot];
     const int t = d.target[slot];
     const float inv_scale = d.inv_scale[slot];
-    const int plane = hl * wl;
+    const int plane = d.tiled ? tiled_plane_size(hl, wl) : hl * wl;
 
     float v[LK_QPW][4];
 #pragma unroll
@@ -88,7 +94,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) corr_lookup_kernel(const bflow_
             if (e < 100) {
                 const int r = e / 10, c = e - r * 10;
                 const int yy = y0 + r, xx = x0 + c;
-                if (yy >= 0 && yy < hl && xx >= 0 && xx < wl) v[i][j] = __ldg(pl + yy * wl + xx);
+                if (yy >= 0 && yy < hl && xx >= 0 && xx < wl) v[i][j] = __ldg(pl + (d.tiled ? tiled_index(yy, xx, wl) : yy * wl + xx));
             }
         }
     }
@@ -141,6 +147,103 @@ __global__ void __launch_bounds__(LK_WARPS * 32) corr_lookup_kernel(const bflow_
     }
 }
 
+// -------------------------------------------------------------------------------------------------------------------
+// v2: granule-tiled volume.  Every plane is stored as 4x4-pixel tiles (64 B = one DRAM access granule, one float4 per tile
+// row, zero padded to multiples of 4), so a 10x10 window touches a 3x3 .. 4x4 block of tiles (10.6 on average, ~680 B)
+// instead of ten 40-byte row segments that each cost one or two 64-byte granules (~1100 B measured with ncu).
+// One warp per unit: 64 lane-slots = 16 tile rows x 4 tile columns, two LDG.128 per lane, the 16x16 patch goes through
+// shared memory, then lane k computes taps k, k+32, k+64 with tap offsets precomputed once per warp.
+// -------------------------------------------------------------------------------------------------------------------
+constexpr int LK2_WARPS = 8;
+constexpr int LK2_PITCH = 20;      // floats per patch row in shared memory (16 used; 20 spreads the tap reads over banks)
+
+__global__ void __launch_bounds__(LK2_WARPS * 32) corr_lookup_tiled_kernel(const bflow_lookup_desc d, const long long n_units, const int slots_per_group) {
+    __shared__ __align__(16) float patch[LK2_WARPS][16 * LK2_PITCH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = d.n_slots;
+    const int Q = d.h * d.w;
+    float* ps = patch[warp];
+
+    // lane-constant geometry: slot A = lane, slot B = lane + 32 of the 64 (tile row, tile column) float4 slots
+    const int tcA = lane & 3, rgA = lane >> 2;            // tile column, patch row 0..7   (slot B: patch row + 8)
+    const int trA = rgA >> 2, rrA = rgA & 3;              // tile row 0..1 (+2 for slot B), row inside the tile
+    int soff[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int k = lane + 32 * j;
+        const int iy = k / 9, ix = k - iy * 9;
+        soff[j] = iy * LK2_PITCH + ix;
+    }
+
+    // a warp walks query pixels (stride = warps in the grid) and, per pixel, all S slots: no division in the inner loop
+    const unsigned n_bq = (unsigned)(n_units / S);
+    for (unsigned bq = blockIdx.x * LK2_WARPS + warp; bq < n_bq; bq += gridDim.x * LK2_WARPS) {
+        const unsigned b = bq / (unsigned)Q;
+        const unsigned q = bq - b * (unsigned)Q;
+        const unsigned qy = q / (unsigned)d.w;
+        const float gx = (float)(q - qy * (unsigned)d.w), gy = (float)qy;
+        const float* prm = d.params + (size_t)bq * d.params_ld;
+        float* o = d.out + (size_t)bq * d.out_ld;
+        const int s_beg = (int)blockIdx.y * slots_per_group, s_end = min(S, s_beg + slots_per_group);
+        o += s_beg * 81;
+
+#pragma unroll 1
+        for (int slot = s_beg; slot < s_end; ++slot, o += 81) {
+            const int hl = d.hl[slot], wl = d.wl[slot];
+            const int t = d.target[slot];
+            float cx, cy;
+            if (d.coords != nullptr) {
+                const float* c = d.coords + (((size_t)t * d.B + b) * 2) * Q + q;
+                cx = __ldg(c);
+                cy = __ldg(c + Q);
+            } else {
+                float fxv = 0.f, fyv = 0.f;
+                for (int k = 0; k < d.degree; ++k) {
+                    const float ck = d.coef[t][k];
+                    fxv = fmaf(ck, __ldg(prm + k), fxv);
+                    fyv = fmaf(ck, __ldg(prm + d.degree + k), fyv);
+                }
+                cx = gx + fxv;
+                cy = gy + fyv;
+            }
+            const float inv_scale = d.inv_scale[slot];
+            cx = fminf(fmaxf(cx * inv_scale, -16.f), (float)wl + 16.f);
+            cy = fminf(fmaxf(cy * inv_scale, -16.f), (float)hl + 16.f);
+            const float flx = floorf(cx), fly = floorf(cy);
+            const float fx = cx - flx, fy = cy - fly;
+            const int x0 = (int)flx - 4, y0 = (int)fly - 4;
+            const int tx0 = x0 >> 2, ty0 = y0 >> 2, ox = x0 & 3, oy = y0 & 3;
+            const int ntx = ((ox + 9) >> 2) + 1, nty = ((oy + 9) >> 2) + 1;   // 3 or 4 tiles per axis
+            const int tw = (wl + 3) >> 2, th = (hl + 3) >> 2;
+            const float* pl = d.vol[slot] + (size_t)bq * (size_t)(tw * th * 16);
+
+            // (a two-deep software pipeline over the slots was measured 10 % slower: 60 registers cost more occupancy than the
+            //  extra loads in flight gain)
+            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+            {
+                const int txx = tx0 + tcA;
+                const bool colok = tcA < ntx && txx >= 0 && txx < tw;
+                const int tya = ty0 + trA, tyb = ty0 + trA + 2;
+                if (colok && tya >= 0 && tya < th) va = __ldg(reinterpret_cast<const float4*>(pl + ((tya * tw + txx) << 4) + (rrA << 2)));
+                if (colok && (trA + 2) < nty && tyb >= 0 && tyb < th) vb = __ldg(reinterpret_cast<const float4*>(pl + ((tyb * tw + txx) << 4) + (rrA << 2)));
+            }
+            __syncwarp();                                     // previous unit's tap reads are done
+            *reinterpret_cast<float4*>(ps + rgA * LK2_PITCH + tcA * 4) = va;
+            *reinterpret_cast<float4*>(ps + (rgA + 8) * LK2_PITCH + tcA * 4) = vb;
+            __syncwarp();
+            const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+            const float* f0 = ps + oy * LK2_PITCH + ox;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                if (lane + 32 * j < 81) {
+                    const float* f = f0 + soff[j];
+                    o[lane + 32 * j] = w00 * f[0] + w01 * f[1] + w10 * f[LK2_PITCH] + w11 * f[LK2_PITCH + 1];
+                }
+            }
+        }
+    }
+}
+
 }  // namespace bflow
 
 extern "C" int bflow_corr_lookup(const bflow_lookup_desc* dp, void* stream) {
@@ -160,6 +263,21 @@ extern "C" int bflow_corr_lookup(const bflow_lookup_desc* dp, void* stream) {
         BFLOW_REQUIRE(d.target[s] >= 0 && d.target[s] < d.n_targets, "lookup: bad slot target");
     }
     const long long BQ = (long long)d.B * d.h * d.w;
+    if (d.tiled && d.out_nhwc) {
+        BFLOW_REQUIRE(BQ * d.n_slots < (1ll << 31), "lookup: too many units");
+        const long long n_units = BQ * d.n_slots;
+        long long g = bflow::ceil_div_ll(BQ, bflow::LK2_WARPS);
+        const long long cap = 148ll * 8 * 8;
+        if (g > cap) g = cap;
+        // few query pixels (batch 1): split the slots over blockIdx.y so that every SM still holds a full set of warps
+        long long groups = bflow::ceil_div_ll(148ll * 48, BQ);
+        if (groups < 1) groups = 1;
+        if (groups > d.n_slots) groups = d.n_slots;
+        const int spg = (int)bflow::ceil_div_ll(d.n_slots, groups);
+        dim3 grid2((unsigned)g, (unsigned)bflow::ceil_div(d.n_slots, spg));
+        bflow::corr_lookup_tiled_kernel<<<grid2, bflow::LK2_WARPS * 32, 0, (cudaStream_t)stream>>>(d, n_units, spg);
+        return bflow::check_launch("bflow_corr_lookup(tiled)");
+    }
     dim3 grid((unsigned)bflow::ceil_div_ll(BQ, bflow::LK_QPB), (unsigned)d.n_slots);
     bflow::corr_lookup_kernel<<<grid, bflow::LK_WARPS * 32, 0, (cudaStream_t)stream>>>(d);
     return bflow::check_launch("bflow_corr_lookup");

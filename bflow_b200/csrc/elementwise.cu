@@ -171,6 +171,41 @@ __global__ void corr_pool_kernel(const float* __restrict__ in, float* __restrict
     }
 }
 
+// the same on 4x4-tiled planes: one thread per output tile row (float4 = 4 pixels of one row); its 8x2 input pixels are the
+// same row pair of two horizontally adjacent input tiles
+__global__ void corr_pool_tiled_kernel(const float* __restrict__ in, float* __restrict__ out, long long planes, int H, int W) {
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int twi = (W + 3) >> 2, thi = (H + 3) >> 2, two = (Wo + 3) >> 2, tho = (Ho + 3) >> 2;
+    const long long per_plane = (long long)two * tho * 4;
+    const long long total = planes * per_plane;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long p = idx / per_plane;
+        const int rem = (int)(idx - p * per_plane);
+        const int tile = rem >> 2, rr = rem & 3;
+        const int tyo = tile / two, txo = tile - tyo * two;
+        const int yo = tyo * 4 + rr;
+        const float* ip = in + (size_t)p * ((size_t)twi * thi * 16);
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        if (yo < Ho) {
+            const int yi = 2 * yo;                       // rows yi, yi+1 share an input tile (yi is even)
+            const int tyi = yi >> 2, ri = yi & 3;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int txi = 2 * txo + half;
+                if (txi < twi) {
+                    const float4 a = *reinterpret_cast<const float4*>(ip + ((size_t)(tyi * twi + txi) << 4) + (ri << 2));
+                    const float4 b = *reinterpret_cast<const float4*>(ip + ((size_t)(tyi * twi + txi) << 4) + ((ri + 1) << 2));
+                    o[2 * half + 0] = (((a.x + a.y) + b.x) + b.y) * 0.25f;
+                    o[2 * half + 1] = (((a.z + a.w) + b.z) + b.w) * 0.25f;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (txo * 4 + j >= Wo) o[j] = 0.f;
+        }
+        *reinterpret_cast<float4*>(out + (size_t)p * ((size_t)two * tho * 16) + ((size_t)tile << 4) + (rr << 2)) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Bezier evaluation at T timestamps (models/raft_spline/bezier.py:165-186)
 // ---------------------------------------------------------------------------------------------
@@ -303,6 +338,14 @@ extern "C" int bflow_corr_pool(const float* in, float* out, long long planes, in
     BFLOW_REQUIRE(planes > 0 && H >= 2 && W >= 2, "corr_pool: bad shape");
     corr_pool_kernel<<<grid_1d(planes * (H / 2) * (W / 2), 256), 256, 0, (cudaStream_t)stream>>>(in, out, planes, H, W);
     return check_launch("bflow_corr_pool");
+}
+
+extern "C" int bflow_corr_pool_tiled(const float* in, float* out, long long planes, int H, int W, void* stream) {
+    BFLOW_REQUIRE(in != nullptr && out != nullptr, "corr_pool_tiled: null tensor");
+    BFLOW_REQUIRE(planes > 0 && H >= 2 && W >= 2 && aligned16(in) && aligned16(out), "corr_pool_tiled: bad shape");
+    const long long total = planes * (((H / 2 + 3) / 4) * ((W / 2 + 3) / 4)) * 4;
+    corr_pool_tiled_kernel<<<grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, planes, H, W);
+    return check_launch("bflow_corr_pool_tiled");
 }
 
 extern "C" int bflow_bezier_eval(const float* params_nchw, const float* coef_host, float* flows, int T, int B, int degree, int H, int W,

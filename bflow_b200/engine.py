@@ -22,7 +22,7 @@ import torch
 from . import _lib, config as _cfg
 from ._lib import ACT, EPI, ConvDesc, LookupDesc, check
 from .bezier import bernstein_coeffs
-from .ops import pack_conv_weight, pack_conv_weight_tc, make_lookup_desc
+from .ops import pack_conv_weight, pack_conv_weight_tc, make_lookup_desc, tiled_plane_size
 
 
 def _ceil(a: int, b: int) -> int:
@@ -365,19 +365,24 @@ class _Plan:
         self._add(L.bflow_nchw_to_nhwc, self.init_in.data_ptr(), hx + poff * 4, B, 2 * deg, h, w, 0, 2 * deg, gw, 1.0, 0.0)
 
         # ---- correlation volume + pyramid (corr.py:264-272, 293-305) ----
-        self.vol0 = torch.empty(T, R, h, w, **f32)
-        if eng.use_tc and fd % 8 == 0 and Q % 4 == 0:
-            # tensor-core GEMM: the target feature map is packed once into the B-operand image (hi/lo fp16, swizzled)
+        tiled = eng.use_tc and fd % 8 == 0
+        self.tiled = tiled
+        if tiled:
+            # tensor-core GEMM; the target feature map is packed once into the B-operand image (hi/lo fp16, swizzled) with its
+            # pixels in 4x4-tiled order, so the GEMM's row-major output IS the granule-tiled plane layout the lookup reads.
             bn = 128
-            img_bytes = ((Q + bn - 1) // bn) * ((fd + 63) // 64) * 2 * bn * 128
+            Np0 = tiled_plane_size(h, w)
+            self.vol0 = torch.empty(T, R, Np0, **f32)
+            img_bytes = ((Np0 + bn - 1) // bn) * ((fd + 63) // 64) * 2 * bn * 128
             self.f2img = torch.zeros(T, B, img_bytes, device=dev, dtype=torch.uint8)
             srcs = [(fm_ev, (t + 1) * B, fm_ev) for t in range(T_ev)] + ([(fm_img, B, fm_img)] if self.use_img else [])
             for t, (fm2, n0, fm1) in enumerate(srcs):
                 for b in range(B):
-                    self._add(L.bflow_pack_b_tc, fm2.data_ptr() + (n0 + b) * Q * fd * 4, fd, self.f2img[t, b].data_ptr(), Q, fd, bn, 0, 0)
-                self._add(L.bflow_corr_volume_tc, fm1.data_ptr(), fd, self.f2img[t].data_ptr(), img_bytes, self.vol0[t].data_ptr(), B, fd, Q, Q, bn,
+                    self._add(L.bflow_pack_b_tc, fm2.data_ptr() + (n0 + b) * Q * fd * 4, fd, self.f2img[t, b].data_ptr(), Q, fd, bn, h, w)
+                self._add(L.bflow_corr_volume_tc, fm1.data_ptr(), fd, self.f2img[t].data_ptr(), img_bytes, self.vol0[t].data_ptr(), B, fd, Q, Np0, bn,
                           eng.err.data_ptr(), label=f'corr_volume_tc Q={Q} D={fd}', flops=2.0 * B * Q * Q * fd)
         else:
+            self.vol0 = torch.empty(T, R, h, w, **f32)
             if self.use_ev:
                 self.f2_ev = torch.empty(T_ev * B, fd, Q, **f32)
                 self._add(L.bflow_nhwc_to_nchw, fm_ev.data_ptr() + B * Q * fd * 4, self.f2_ev.data_ptr(), T_ev * B, fd, h, w, fd)
@@ -387,22 +392,26 @@ class _Plan:
                 self.f2_img = torch.empty(B, fd, Q, **f32)
                 self._add(L.bflow_nhwc_to_nchw, fm_img.data_ptr() + B * Q * fd * 4, self.f2_img.data_ptr(), B, fd, h, w, fd)
                 self._add(L.bflow_corr_volume, fm_img.data_ptr(), fd, self.f2_img.data_ptr(), self.vol0[T_ev].data_ptr(), B, fd, Q)
-        pyr: List[Tuple[List[int], torch.Tensor]] = [(list(range(T)), self.vol0)]
+        # pyramid: level l holds the targets with more than l levels; (indices, tensor, hl, wl)
+        pyr = [(list(range(T)), self.vol0, h, w)]
         for lvl in range(1, max(eng.levels)):
-            prev_idx, prev = pyr[-1]
+            prev_idx, prev, hp_, wp_ = pyr[-1]
             keep = [t for t in range(T) if eng.levels[t] > lvl]
-            hl, wl = prev.shape[-2] // 2, prev.shape[-1] // 2
-            cur = torch.empty(len(keep), R, hl, wl, **f32)
+            hl, wl = hp_ // 2, wp_ // 2
+            cur = torch.empty(len(keep), R, tiled_plane_size(hl, wl), **f32) if tiled else torch.empty(len(keep), R, hl, wl, **f32)
             for j, t in enumerate(keep):
                 src = prev[prev_idx.index(t)]
-                self._add(L.bflow_corr_pool, src.data_ptr(), cur[j].data_ptr(), R, prev.shape[-2], prev.shape[-1])
-            pyr.append((keep, cur))
+                self._add(L.bflow_corr_pool_tiled if tiled else L.bflow_corr_pool, src.data_ptr(), cur[j].data_ptr(), R, hp_, wp_)
+            pyr.append((keep, cur, hl, wl))
         self.pyr = pyr
 
         # ---- lookup descriptor (corr.py:307-350); centres come from the Bezier params in hx ----
-        slots = [(lvl, t, pyr[lvl][1][pyr[lvl][0].index(t)]) for (lvl, t) in eng.slots]
+        if tiled:
+            slots = [(lvl, t, pyr[lvl][1][pyr[lvl][0].index(t)], pyr[lvl][2], pyr[lvl][3]) for (lvl, t) in eng.slots]
+        else:
+            slots = [(lvl, t, pyr[lvl][1][pyr[lvl][0].index(t)]) for (lvl, t) in eng.slots]
         self.corr = torch.zeros(R, eng.ldc, **f32)
-        ld = make_lookup_desc(slots, T, B, h, w)
+        ld = make_lookup_desc(slots, T, B, h, w, tiled)
         ld.coords = None
         ld.params, ld.params_ld, ld.degree = hx + poff * 4, gw, deg
         for t in range(T):

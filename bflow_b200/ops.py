@@ -174,26 +174,64 @@ def corr_pool(vol: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def make_lookup_desc(slots: Sequence[Tuple[int, int, torch.Tensor]], n_targets: int, B: int, h: int, w: int) -> LookupDesc:
-    """slots: (level, base target, planes tensor (B*Q, hl, wl)) in output order."""
+def tiled_plane_size(h: int, w: int) -> int:
+    return ((h + 3) // 4) * ((w + 3) // 4) * 16
+
+
+def to_tiled(planes: torch.Tensor) -> torch.Tensor:
+    """(..., h, w) row-major planes → (..., ceil4(h)*ceil4(w)) in the 4x4-pixel-tiled layout of bflow_corr_lookup(tiled=1)."""
+    h, w = planes.shape[-2:]
+    hp, wp = (h + 3) // 4 * 4, (w + 3) // 4 * 4
+    p = torch.nn.functional.pad(planes, (0, wp - w, 0, hp - h))
+    lead = p.shape[:-2]
+    p = p.reshape(*lead, hp // 4, 4, wp // 4, 4).transpose(-3, -2)
+    return p.reshape(*lead, hp * wp).contiguous()
+
+
+def from_tiled(flat: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    hp, wp = (h + 3) // 4 * 4, (w + 3) // 4 * 4
+    lead = flat.shape[:-1]
+    p = flat.reshape(*lead, hp // 4, wp // 4, 4, 4).transpose(-3, -2).reshape(*lead, hp, wp)
+    return p[..., :h, :w].contiguous()
+
+
+def corr_pool_tiled(flat: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """avg_pool2d(2,2) on tiled planes (..., tiled(h, w)) → (..., tiled(h//2, w//2))."""
+    flat = _f32c(flat, 'vol')
+    planes = flat.numel() // tiled_plane_size(h, w)
+    out = torch.empty(*flat.shape[:-1], tiled_plane_size(h // 2, w // 2), device=flat.device, dtype=torch.float32)
+    check(_lib.lib().bflow_corr_pool_tiled(flat.data_ptr(), out.data_ptr(), planes, h, w, _stream()), 'corr_pool_tiled')
+    return out
+
+
+def make_lookup_desc(slots: Sequence[tuple], n_targets: int, B: int, h: int, w: int, tiled: bool = False) -> LookupDesc:
+    """slots: (level, base target, planes) in output order; planes is (B*Q, hl, wl) row-major, or — when ``tiled`` —
+    (level, base target, planes (B*Q, tiled size), hl, wl)."""
     d = LookupDesc()
     d.n_slots, d.n_targets, d.B, d.h, d.w, d.radius = len(slots), n_targets, B, h, w, 4
-    for s, (lvl, t, planes) in enumerate(slots):
+    d.tiled = int(tiled)
+    for s, entry in enumerate(slots):
+        lvl, t, planes = entry[:3]
         assert planes.is_cuda and planes.dtype == torch.float32 and planes.is_contiguous()
         assert planes.shape[0] == B * h * w
+        if tiled:
+            hl, wl = entry[3], entry[4]
+            assert planes.shape[1] == tiled_plane_size(hl, wl)
+        else:
+            hl, wl = planes.shape[-2], planes.shape[-1]
         d.vol[s] = planes.data_ptr()
-        d.hl[s], d.wl[s] = planes.shape[-2], planes.shape[-1]
+        d.hl[s], d.wl[s] = hl, wl
         d.target[s] = t
         d.inv_scale[s] = 1.0 / (2 ** lvl)
     return d
 
 
-def corr_lookup(slots: Sequence[Tuple[int, int, torch.Tensor]], coords: torch.Tensor, nhwc: bool = False) -> torch.Tensor:
+def corr_lookup(slots: Sequence[tuple], coords: torch.Tensor, nhwc: bool = False, tiled: bool = False) -> torch.Tensor:
     """coords (T,B,2,h,w) → (B, S*81, h, w) [reference layout] or (B,h,w,S*81) when nhwc (corr.py:307-350)."""
     coords = _f32c(coords, 'coords')
     T, B, two, h, w = coords.shape
     assert two == 2
-    d = make_lookup_desc(slots, T, B, h, w)
+    d = make_lookup_desc(slots, T, B, h, w, tiled)
     S = len(slots)
     d.coords = coords.data_ptr()
     d.params, d.params_ld, d.degree = None, 0, 0

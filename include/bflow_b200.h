@@ -136,6 +136,8 @@ int bflow_corr_volume(const float* f1, int ld1, const float* f2_nchw, float* cor
                       int B, int D, int Q, void* stream);
 /* avg_pool2d(2, stride 2) with floor on a stack of planes (corr.py:119): (P,H,W) -> (P,H/2,W/2) */
 int bflow_corr_pool(const float* in, float* out, long long planes, int H, int W, void* stream);
+/* the same pooling on 4x4-tiled planes (in: ceil4(H) x ceil4(W) tiled, out: ceil4(H/2) x ceil4(W/2) tiled, pad = 0) */
+int bflow_corr_pool_tiled(const float* in, float* out, long long planes, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Pyramid lookup (corr.py:307-350 + models/raft_utils/utils.py:5-21).  One unit = (query pixel, slot):
@@ -157,6 +159,8 @@ typedef struct bflow_lookup_desc {
     float* out;
     int out_nhwc;                          /* 0: (B, S*81, h, w) like the reference; 1: rows (B*Q) x out_ld */
     int out_ld;
+    int tiled;                             /* 0: planes row-major (hl x wl) like the reference; 1: planes stored as 4x4-pixel
+                                              tiles (64-byte DRAM granules), ceil(hl/4) x ceil(wl/4) tiles of 16 floats, zero padded */
 } bflow_lookup_desc;
 int bflow_corr_lookup(const bflow_lookup_desc* d, void* stream);
 

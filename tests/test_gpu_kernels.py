@@ -127,6 +127,38 @@ def test_lookup_matches_oracle(B, h, w, levels):
     assert out[0, :81, 0, 0].abs().max() == 0
 
 
+@pytest.mark.parametrize('B,h,w,levels', [(1, 60, 80, [4]), (2, 24, 40, [1, 1, 1, 1, 4, 4]), (2, 9, 13, [2, 1]), (1, 15, 22, [3])])
+def test_tiled_lookup_and_pool_match_oracle(B, h, w, levels):
+    """Granule-tiled volume layout (4x4-pixel tiles): pooling and lookup against the row-major oracle."""
+    T = len(levels)
+    f1, f2, coords = synthetic.lookup_case(B, h, w, dim=32, targets=T, seed=13)
+    coords[0, 0, :, 0, 0] = torch.tensor([-30.0, 1e9])
+    coords[0, 0, :, 0, 1] = torch.tensor([float(w - 1), float(h - 1)])
+    coords[0, 0, :, 0, 2] = torch.tensor([-3.25, -2.5])                   # window straddles the top-left corner
+    vol = O.corr_volume(f1, f2)
+    pyr = O.corr_pyramid(vol, levels)
+    want = O.corr_lookup(pyr, coords)
+    # tiled pyramid built on the GPU from the tiled level 0
+    lv = {0: ops.to_tiled(vol.to(DEV))}
+    dims = {0: (h, w)}
+    idx = {0: list(range(T))}
+    for lvl in range(1, max(levels)):
+        keep = [t for t in range(T) if levels[t] > lvl]
+        prev = torch.stack([lv[lvl - 1][idx[lvl - 1].index(t)] for t in keep], 0)
+        lv[lvl] = ops.corr_pool_tiled(prev, *dims[lvl - 1])
+        dims[lvl] = (dims[lvl - 1][0] // 2, dims[lvl - 1][1] // 2)
+        idx[lvl] = keep
+        got = ops.from_tiled(lv[lvl], *dims[lvl]).cpu()
+        assert (got - pyr[lvl][1]).abs().max() < 1e-6
+        assert torch.equal(ops.to_tiled(got.to(DEV)), lv[lvl])          # padding of the tiled planes is exactly zero
+    slots = [(l, t, lv[l][idx[l].index(t)].contiguous(), dims[l][0], dims[l][1]) for (l, t) in O.slot_table(levels)]
+    out = ops.corr_lookup(slots, coords.to(DEV), nhwc=True, tiled=True).cpu().permute(0, 3, 1, 2)
+    assert out.shape == want.shape
+    assert (out - want).abs().max() < 3e-5
+    out2 = ops.corr_lookup(slots, coords.to(DEV), nhwc=False, tiled=True).cpu()      # reference layout out of tiled planes
+    assert (out2 - want).abs().max() < 3e-5
+
+
 def test_lookup_known_answer_centre_tap():
     h, w = 12, 20
     vol = torch.randn(1, h * w, 1, h, w, generator=g(5))

@@ -23,6 +23,7 @@ def main():
     ap.add_argument('--h', type=int, default=60)
     ap.add_argument('--w', type=int, default=80)
     ap.add_argument('--noflush', action='store_true')
+    ap.add_argument('--tiled', action='store_true')
     a = ap.parse_args()
     dev = torch.device('cuda:0')
     lib = _lib.lib()
@@ -33,12 +34,13 @@ def main():
     g = torch.Generator().manual_seed(7)
     planes = {}
     for (l, t) in table:
-        planes[(l, t)] = torch.randn(R, h >> l, w >> l, device=dev)
-    slots = [(l, t, planes[(l, t)]) for (l, t) in table]
+        p = torch.randn(R, h >> l, w >> l, device=dev)
+        planes[(l, t)] = ops.to_tiled(p) if a.tiled else p
+    slots = [(l, t, planes[(l, t)], h >> l, w >> l) for (l, t) in table] if a.tiled else [(l, t, planes[(l, t)]) for (l, t) in table]
     ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing='ij')
     coords = (torch.stack([xs, ys], 0).float()[None, None] + 8 * torch.randn(T, B, 2, h, w, generator=g)).to(dev)
     out = torch.empty(B, S * 81, h, w, device=dev) if a.nchw else torch.empty(R, S * 81, device=dev)
-    d = ops.make_lookup_desc(slots, T, B, h, w)
+    d = ops.make_lookup_desc(slots, T, B, h, w, a.tiled)
     d.coords, d.params, d.params_ld, d.degree = coords.data_ptr(), None, 0, 0
     d.out, d.out_nhwc, d.out_ld = out.data_ptr(), int(not a.nchw), S * 81
     stream = torch.cuda.current_stream().cuda_stream
@@ -57,7 +59,7 @@ def main():
         ts.append(e0.elapsed_time(e1))
     t = statistics.median(ts)
     nbytes = R * (S * 724 + T * 8)
-    print(f'lookup B={B} {h}x{w} slots={S} targets={T} layout={"nchw" if a.nchw else "nhwc"}: median {t*1e3:.1f} us, min {min(ts)*1e3:.1f} us, '
+    print(f'lookup B={B} {h}x{w} slots={S} targets={T} layout={"nchw" if a.nchw else "nhwc"}{" tiled-volume" if a.tiled else ""}: median {t*1e3:.1f} us, min {min(ts)*1e3:.1f} us, '
           f'{nbytes/1e6:.2f} MB algorithmic -> {nbytes/(t*1e-3)/1e9:.0f} GB/s ({nbytes/(t*1e-3)/1e9/6552.6:.3f} of measured HBM peak)')
 
 
