@@ -30,7 +30,10 @@ class ConvDesc(C.Structure):
                 ('scale', C.c_float),
                 ('epi', C.c_int),
                 ('aux0', C.c_void_p), ('ld_aux0', C.c_int),
-                ('aux1', C.c_void_p), ('ld_aux1', C.c_int)]
+                ('aux1', C.c_void_p), ('ld_aux1', C.c_int),
+                ('y16_hi', C.c_void_p), ('y16_lo', C.c_void_p), ('ldy16', C.c_int),
+                ('res16_hi', C.c_void_p), ('res16_lo', C.c_void_p), ('ldr16', C.c_int),
+                ('aux1_16_hi', C.c_void_p), ('aux1_16_lo', C.c_void_p), ('ld_aux1_16', C.c_int)]
 
 
 class LookupDesc(C.Structure):
@@ -45,6 +48,7 @@ class LookupDesc(C.Structure):
                 ('out', C.c_void_p),
                 ('out_nhwc', C.c_int),
                 ('out_ld', C.c_int),
+                ('out16_hi', C.c_void_p), ('out16_lo', C.c_void_p), ('out16_ld', C.c_int),
                 ('tiled', C.c_int)]
 
 
@@ -58,12 +62,17 @@ _SIGNATURES = {
     'bflow_conv2d_nhwc': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     'bflow_conv2d_tc_supported': (C.c_int, [C.POINTER(ConvDesc)]),
     'bflow_conv2d_nhwc_tc': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    'bflow_tma_im2col_map': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 10),
+    'bflow_conv2d_nhwc_tc3': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    'bflow_split_f16': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
     'bflow_pack_b_tc': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     'bflow_corr_volume_tc': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     'bflow_conv2d_small_n': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     'bflow_plane_sums': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'bflow_instnorm_relu': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    'bflow_instnorm_relu16': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     'bflow_corr_volume': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'bflow_corr_pool': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     'bflow_corr_pool_tiled': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),

@@ -1,6 +1,7 @@
 // Shared helpers for the bflow_b200 kernels (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include "../../include/bflow_b200.h"
 
@@ -26,6 +27,44 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     }
 }
 
+// split two floats into packed fp16 "hi" and "lo" words (element 0 in the low half): x = hi + lo with hi = fp16(x) and
+// lo = fp16(x - hi): 11 + 11 mantissa bits.  Conversions saturate (no inf): |x| up to 1.3e5 is represented, beyond that it
+// clamps; residuals below 6e-5 are fp16-subnormal with 6e-8 absolute spacing.  (tcgen05 kind::f16 rejects mixed bf16 x fp16
+// operands with an illegal-instruction fault, so a bf16 hi / fp16 lo split is not available.)
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float e0, float e1) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
+    return r;
+}
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack_f16x2_sat(a, b);
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    lo = pack_f16x2_sat(a - hf.x, b - hf.y);
+}
+// 4 floats -> 8 bytes of hi and 8 bytes of lo
+__device__ __forceinline__ void store_split4(void* hi_base, void* lo_base, size_t elem, float a, float b, float c, float d) {
+    uint2 h, l;
+    split2(a, b, h.x, l.x);
+    split2(c, d, h.y, l.y);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(hi_base) + elem) = h;
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(lo_base) + elem) = l;
+}
+__device__ __forceinline__ void store_split1(void* hi_base, void* lo_base, size_t elem, float a) {
+    const __half h = __float2half_rn(fminf(fmaxf(a, -65504.f), 65504.f));
+    reinterpret_cast<__half*>(hi_base)[elem] = h;
+    reinterpret_cast<__half*>(lo_base)[elem] = __float2half_rn(a - __half2float(h));
+}
+__device__ __forceinline__ float4 load_split4(const void* hi_base, const void* lo_base, size_t elem) {
+    const uint2 h = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(hi_base) + elem);
+    const uint2 l = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(lo_base) + elem);
+    const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+    const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+    return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+}
+__device__ __forceinline__ float load_split1(const void* hi_base, const void* lo_base, size_t elem) {
+    return __half2float(reinterpret_cast<const __half*>(hi_base)[elem]) + __half2float(reinterpret_cast<const __half*>(lo_base)[elem]);
+}
+
 // Epilogue shared by the CUDA-core and tensor-core convolutions for 4 consecutive output channels n..n+3 of row m.
 // v[] = scale * (acc + bias).  `vec` = all four channels valid and every pointer involved is 16-byte aligned.
 __device__ __forceinline__ void conv_epilogue4(const bflow_conv_desc& d, int m, int n, float* v, bool vec) {
@@ -36,17 +75,24 @@ __device__ __forceinline__ void conv_epilogue4(const bflow_conv_desc& d, int m, 
             if (d.res != nullptr) {
                 const float4 r = *reinterpret_cast<const float4*>(d.res + (size_t)m * d.ldr + n);
                 v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+            } else if (d.res16_hi != nullptr) {
+                const float4 r = load_split4(d.res16_hi, d.res16_lo, (size_t)m * d.ldr16 + n);
+                v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], d.act2);
-            *reinterpret_cast<float4*>(d.y + (size_t)m * d.ldy + n) = make_float4(v[0], v[1], v[2], v[3]);
+            if (d.y != nullptr) *reinterpret_cast<float4*>(d.y + (size_t)m * d.ldy + n) = make_float4(v[0], v[1], v[2], v[3]);
+            if (d.y16_hi != nullptr) store_split4(d.y16_hi, d.y16_lo, (size_t)m * d.ldy16 + n, v[0], v[1], v[2], v[3]);
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (n + j < d.Cout) {
                     float o = v[j];
                     if (d.res != nullptr) o += d.res[(size_t)m * d.ldr + n + j];
-                    d.y[(size_t)m * d.ldy + n + j] = apply_act(o, d.act2);
+                    else if (d.res16_hi != nullptr) o += load_split1(d.res16_hi, d.res16_lo, (size_t)m * d.ldr16 + n + j);
+                    o = apply_act(o, d.act2);
+                    if (d.y != nullptr) d.y[(size_t)m * d.ldy + n + j] = o;
+                    if (d.y16_hi != nullptr) store_split1(d.y16_hi, d.y16_lo, (size_t)m * d.ldy16 + n + j, o);
                 }
             }
         }
@@ -64,7 +110,10 @@ __device__ __forceinline__ void conv_epilogue4(const bflow_conv_desc& d, int m, 
         *reinterpret_cast<float4*>(d.y + (size_t)m * d.ldy + n) = g;
         if (n >= C) {
             const float4 hv = *reinterpret_cast<const float4*>(d.aux0 + (size_t)m * d.ld_aux0 + (n - C));
-            *reinterpret_cast<float4*>(d.aux1 + (size_t)m * d.ld_aux1 + (n - C)) = make_float4(g.x * hv.x, g.y * hv.y, g.z * hv.z, g.w * hv.w);
+            if (d.aux1 != nullptr)
+                *reinterpret_cast<float4*>(d.aux1 + (size_t)m * d.ld_aux1 + (n - C)) = make_float4(g.x * hv.x, g.y * hv.y, g.z * hv.z, g.w * hv.w);
+            if (d.aux1_16_hi != nullptr)
+                store_split4(d.aux1_16_hi, d.aux1_16_lo, (size_t)m * d.ld_aux1_16 + (n - C), g.x * hv.x, g.y * hv.y, g.z * hv.z, g.w * hv.w);
         }
     } else {   // BFLOW_EPI_GRU_Q
         if (n + 3 >= d.Cout) return;
@@ -81,6 +130,7 @@ __device__ __forceinline__ void conv_epilogue4(const bflow_conv_desc& d, int m, 
         hv.z = (1.f - z.z) * hv.z + z.z * q.z;
         hv.w = (1.f - z.w) * hv.w + z.w * q.w;
         *reinterpret_cast<float4*>(d.y + (size_t)m * d.ldy + n) = hv;
+        if (d.y16_hi != nullptr) store_split4(d.y16_hi, d.y16_lo, (size_t)m * d.ldy16 + n, hv.x, hv.y, hv.z, hv.w);
     }
 }
 
@@ -91,12 +141,19 @@ __host__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr
 
 // host-side contract of the fused GRU epilogues; returns nullptr when fine
 __host__ inline const char* check_epilogue(const bflow_conv_desc& d) {
+    if (d.y == nullptr && d.y16_hi == nullptr) return "conv: no output (y and y16 both null)";
+    if (d.y16_hi != nullptr && (d.y16_lo == nullptr || d.ldy16 < d.Cout || d.ldy16 % 4 != 0 ||
+                                (reinterpret_cast<uintptr_t>(d.y16_hi) & 7) != 0 || (reinterpret_cast<uintptr_t>(d.y16_lo) & 7) != 0))
+        return "conv: split output needs both planes, ldy16 >= Cout, ldy16 % 4 == 0, 8-byte alignment";
+    if (d.res16_hi != nullptr && (d.res != nullptr || d.res16_lo == nullptr || d.ldr16 < d.Cout || d.ldr16 % 4 != 0)) return "conv: bad split residual";
     if (d.epi == BFLOW_EPI_STD) return nullptr;
     if (d.epi != BFLOW_EPI_GRU_ZR && d.epi != BFLOW_EPI_GRU_Q) return "conv: unknown epilogue mode";
     if (d.Cout % 8 != 0 || d.ldy % 4 != 0 || !aligned16(d.y)) return "conv: GRU epilogue needs Cout % 8 == 0 and aligned output";
     if (d.res != nullptr && (d.ldr % 4 != 0 || !aligned16(d.res))) return "conv: GRU epilogue needs aligned res";
     if (d.aux0 == nullptr || d.ld_aux0 % 4 != 0 || !aligned16(d.aux0)) return "conv: GRU epilogue needs aligned aux0";
-    if (d.epi == BFLOW_EPI_GRU_ZR && (d.aux1 == nullptr || d.ld_aux1 % 4 != 0 || !aligned16(d.aux1))) return "conv: GRU_ZR needs aligned aux1";
+    if (d.epi == BFLOW_EPI_GRU_ZR && d.aux1 == nullptr && d.aux1_16_hi == nullptr) return "conv: GRU_ZR needs aux1 (fp32 or split)";
+    if (d.epi == BFLOW_EPI_GRU_ZR && d.aux1 != nullptr && (d.ld_aux1 % 4 != 0 || !aligned16(d.aux1))) return "conv: GRU_ZR needs aligned aux1";
+    if (d.aux1_16_hi != nullptr && (d.aux1_16_lo == nullptr || d.ld_aux1_16 % 4 != 0)) return "conv: bad split aux1";
     return nullptr;
 }
 

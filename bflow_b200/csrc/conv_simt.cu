@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_simt_kernel(const bflow_conv_de
     float bias[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) bias[j] = (d.bias != nullptr && nbase + j < d.Cout) ? __ldg(d.bias + nbase + j) : 0.f;
-    const bool vec_store = ((d.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15) == 0) && (nbase + 3 < d.Cout) &&
+    const bool vec_store = (d.y == nullptr || (((d.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15) == 0))) && (nbase + 3 < d.Cout) &&
                            (d.res == nullptr || (((d.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.res) & 15) == 0)));
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
@@ -229,7 +229,7 @@ static int launch_conv(const bflow_conv_desc& d, cudaStream_t stream) {
 extern "C" int bflow_conv2d_nhwc(const bflow_conv_desc* dp, void* stream) {
     BFLOW_REQUIRE(dp != nullptr, "conv: null descriptor");
     const bflow_conv_desc& d = *dp;
-    BFLOW_REQUIRE(d.x0 != nullptr && d.w != nullptr && d.y != nullptr, "conv: null tensor");
+    BFLOW_REQUIRE(d.x0 != nullptr && d.w != nullptr, "conv: null tensor");
     BFLOW_REQUIRE(d.c0 > 0 && d.c1 >= 0 && d.ld0 >= d.c0, "conv: bad source 0");
     BFLOW_REQUIRE(d.c1 == 0 || (d.x1 != nullptr && d.ld1 >= d.c1), "conv: bad source 1");
     BFLOW_REQUIRE(d.N > 0 && d.H > 0 && d.W > 0 && d.Cout > 0, "conv: bad shape");
@@ -237,7 +237,7 @@ extern "C" int bflow_conv2d_nhwc(const bflow_conv_desc* dp, void* stream) {
     BFLOW_REQUIRE(d.Ho == (d.H + 2 * d.pad_h - d.KH) / d.stride + 1, "conv: Ho does not match");
     BFLOW_REQUIRE(d.Wo == (d.W + 2 * d.pad_w - d.KW) / d.stride + 1, "conv: Wo does not match");
     BFLOW_REQUIRE(d.ldw >= d.Cout && d.ldw % 4 == 0 && bflow::aligned16(d.w), "conv: packed weights need ldw%4==0, 16B aligned");
-    BFLOW_REQUIRE(d.ldy >= d.Cout, "conv: ldy < Cout");
+    BFLOW_REQUIRE(d.y == nullptr || d.ldy >= d.Cout, "conv: ldy < Cout");
     BFLOW_REQUIRE(d.res == nullptr || d.ldr >= d.Cout, "conv: ldr < Cout");
     BFLOW_REQUIRE(d.act1 >= 0 && d.act1 <= 3 && d.act2 >= 0 && d.act2 <= 3, "conv: bad activation");
     if (const char* msg = bflow::check_epilogue(d)) { bflow::set_error(msg); return BFLOW_ERR_INVALID; }
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(256) conv_small_n_kernel(const bflow_conv_desc
         float v[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = d.scale * (v[j] + ((d.bias != nullptr && nb + j < d.Cout) ? __ldg(d.bias + nb + j) : 0.f));
-        const bool vec = ((d.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15) == 0) && (nb + 3 < d.Cout) &&
+        const bool vec = (d.y == nullptr || (((d.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15) == 0))) && (nb + 3 < d.Cout) &&
                          (d.res == nullptr || (((d.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.res) & 15) == 0)));
         conv_epilogue4(d, m, nb, v, vec);
     }
@@ -316,12 +316,13 @@ __global__ void __launch_bounds__(256) conv_small_n_kernel(const bflow_conv_desc
 extern "C" int bflow_conv2d_small_n(const bflow_conv_desc* dp, void* stream) {
     BFLOW_REQUIRE(dp != nullptr, "conv_small_n: null descriptor");
     const bflow_conv_desc& d = *dp;
-    BFLOW_REQUIRE(d.x0 != nullptr && d.w != nullptr && d.y != nullptr, "conv_small_n: null tensor");
+    BFLOW_REQUIRE(d.x0 != nullptr && d.w != nullptr, "conv_small_n: null tensor");
     BFLOW_REQUIRE(d.c1 == 0 && d.c0 > 0 && d.c0 % 4 == 0 && d.ld0 % 4 == 0 && bflow::aligned16(d.x0), "conv_small_n: one aligned source, Cin % 4 == 0");
     BFLOW_REQUIRE(d.Cout > 0 && d.Cout <= 32 && d.ldw % 4 == 0 && d.ldw >= d.Cout && bflow::aligned16(d.w), "conv_small_n: Cout <= 32, packed weights");
     BFLOW_REQUIRE(d.epi == BFLOW_EPI_STD, "conv_small_n: standard epilogue only");
     BFLOW_REQUIRE(d.Ho == (d.H + 2 * d.pad_h - d.KH) / d.stride + 1 && d.Wo == (d.W + 2 * d.pad_w - d.KW) / d.stride + 1, "conv_small_n: Ho/Wo mismatch");
-    BFLOW_REQUIRE(d.ldy >= d.Cout && (d.res == nullptr || d.ldr >= d.Cout), "conv_small_n: bad output stride");
+    BFLOW_REQUIRE((d.y == nullptr || d.ldy >= d.Cout) && (d.res == nullptr || d.ldr >= d.Cout), "conv_small_n: bad output stride");
+    if (const char* msg = bflow::check_epilogue(d)) { bflow::set_error(msg); return BFLOW_ERR_INVALID; }
     const long long Mll = (long long)d.N * d.Ho * d.Wo;
     BFLOW_REQUIRE(Mll > 0 && Mll < (1ll << 31), "conv_small_n: bad shape");
     const int M = (int)Mll;

@@ -112,21 +112,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// split two floats into packed fp16 "hi" and "lo" words (element 0 in the low half): x = hi + lo with hi = fp16(x) and
-// lo = fp16(x - hi): 11 + 11 mantissa bits.  Conversions saturate (no inf): |x| up to 1.3e5 is represented, beyond that it
-// clamps; residuals below 6e-5 are fp16-subnormal with 6e-8 absolute spacing.  (tcgen05 kind::f16 rejects mixed bf16 x fp16
-// operands with an illegal-instruction fault, so a bf16 hi / fp16 lo split is not available.)
-__device__ __forceinline__ uint32_t pack_f16x2_sat(float e0, float e1) {
-    uint32_t r;
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
-    return r;
-}
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    hi = pack_f16x2_sat(a, b);
-    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-    lo = pack_f16x2_sat(a - hf.x, b - hf.y);
-}
-
 template <int BN, int STAGES, int MINB>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 conv_tc_kernel(const bflow_conv_desc d, const uint8_t* __restrict__ wtc, const int M, const int nkb, const float acc_scale, int* err) {
@@ -252,7 +237,7 @@ conv_tc_kernel(const bflow_conv_desc d, const uint8_t* __restrict__ wtc, const i
         const int m = m0 + quad * 32 + (tid & 31);
         const int cbeg = (warp >> 2) * (BN / 2);
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const bool vec_ok = ((d.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15) == 0) &&
+        const bool vec_ok = (d.y == nullptr || (((d.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15) == 0))) &&
                             (d.res == nullptr || (((d.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.res) & 15) == 0)));
 #pragma unroll 1
         for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 16) {
@@ -411,12 +396,12 @@ extern "C" int bflow_conv2d_tc_supported(const bflow_conv_desc* dp) {
 extern "C" int bflow_conv2d_nhwc_tc(const bflow_conv_desc* dp, const void* w_tc, int bn, float acc_scale, int* err, void* stream) {
     BFLOW_REQUIRE(dp != nullptr && w_tc != nullptr, "conv_tc: null argument");
     const bflow_conv_desc& d = *dp;
-    BFLOW_REQUIRE(d.x0 != nullptr && d.y != nullptr, "conv_tc: null tensor");
+    BFLOW_REQUIRE(d.x0 != nullptr, "conv_tc: null tensor");
     BFLOW_REQUIRE(bflow_conv2d_tc_supported(dp) == 1, "conv_tc: needs channels % 8 == 0, 16-byte aligned rows, <= 32 taps");
     BFLOW_REQUIRE(d.c1 == 0 || d.x1 != nullptr, "conv_tc: bad source 1");
     BFLOW_REQUIRE(d.N > 0 && d.H > 0 && d.W > 0 && d.Cout > 0, "conv_tc: bad shape");
     BFLOW_REQUIRE(d.Ho == (d.H + 2 * d.pad_h - d.KH) / d.stride + 1 && d.Wo == (d.W + 2 * d.pad_w - d.KW) / d.stride + 1, "conv_tc: Ho/Wo mismatch");
-    BFLOW_REQUIRE(d.ldy >= d.Cout && (d.res == nullptr || d.ldr >= d.Cout), "conv_tc: bad output stride");
+    BFLOW_REQUIRE((d.y == nullptr || d.ldy >= d.Cout) && (d.res == nullptr || d.ldr >= d.Cout), "conv_tc: bad output stride");
     BFLOW_REQUIRE((reinterpret_cast<uintptr_t>(w_tc) & 15) == 0, "conv_tc: packed weights must be 16-byte aligned");
     if (const char* msg = bflow::check_epilogue(d)) { bflow::set_error(msg); return BFLOW_ERR_INVALID; }
     const long long Mll = (long long)d.N * d.Ho * d.Wo;

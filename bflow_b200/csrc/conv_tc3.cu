@@ -1,0 +1,522 @@
+// TMA-fed, persistent tensor-core convolution for sm_100a (bflow_conv2d_nhwc_tc3).
+//
+// Same operator as conv_tc.cu / conv_simt.cu, but the A operand never touches registers: activations are stored as
+// split-fp16 planes (x = hi + lo) by whoever produced them, and the TMA unit gathers the implicit-GEMM tile
+// [128 output pixels] x [64 channels of one filter tap] straight into the SWIZZLE_128B shared-memory layout with
+// cp.async.bulk.tensor.4d...im2col (zero fill for the padding halo, for channels beyond Cin and for rows beyond M).
+//
+//   grid      one CTA per SM, looping over (m_tile, n_tile) output tiles (n fastest, so co-running CTAs share A in L2)
+//   warp 0    TMA producer: per k-block one arrive.expect_tx + two im2col loads (hi, lo) + one bulk copy of the weight tile
+//   warp 1    MMA issuer: 4 k-steps x 3 tcgen05.mma (hi*hi, hi*lo, lo*hi) per k-block into TMEM accumulator `acc`,
+//             tcgen05.commit -> empty[stage]; after the last k-block tcgen05.commit -> tmem_full[acc]
+//   warps 2-5 epilogue: tcgen05.ld of accumulator `acc` (two accumulators: the epilogue of tile i overlaps the MMAs of
+//             tile i+1), bias / scale / activation / residual / GRU gates, fp32 and/or split-fp16 stores
+//
+// K order: k-block = (tap, 64-channel block); the two concatenated sources are two tensor-map pairs.
+#include <cuda.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace bflow {
+
+constexpr int T3_BM = 128;
+constexpr int T3_A_BYTES = T3_BM * 128;   // one fp16 A tile (hi or lo): 128 rows x 64 channels
+constexpr int T3_EPI_WARPS = 8;            // two per TMEM lane quadrant, each takes half of the tile's columns
+constexpr int T3_THREADS = 64 + 32 * T3_EPI_WARPS;
+
+__device__ __forceinline__ uint32_t t3_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void t3_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void t3_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void t3_mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool t3_mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool t3_mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// development: per-role clock64 stamps of CTA 0 (bflow_tc3_trace); the pointer travels as a kernel parameter
+#ifdef BFLOW_T3_TRACE
+#define T3_TRACE(slot, idx) do { if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 256) p.trace[(slot) * 256 + (idx)] = clock64(); } while (0)
+#else
+#define T3_TRACE(slot, idx) do { } while (0)
+#endif
+// bounded: a protocol bug sets the error word instead of hanging the GPU
+__device__ __forceinline__ void t3_mbar_wait(uint32_t bar, uint32_t parity, int* err) {
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 24); ++it)
+        if (t3_mbar_try_wait(bar, parity)) return;
+    if (err != nullptr) atomicExch(err, 1);
+}
+__device__ __forceinline__ void t3_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void t3_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void t3_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+// im2col tile load: {c, w, h, n} = first channel and the input coordinates of the first output pixel's tap (0,0);
+// {off_w, off_h} = filter tap
+__device__ __forceinline__ void t3_tma_im2col(uint32_t dst, const CUtensorMap* map, int c, int w, int h, int n, uint16_t off_w, uint16_t off_h,
+                                              uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t t3_umma_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(1024 >> 4) << 32;     // 8-row groups are 1024 bytes apart
+    d |= (uint64_t)1 << 46;               // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;               // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void t3_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void t3_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void t3_tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void t3_tmem_ld16_nowait(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct T3Params {
+    int M, n_mtiles, n_ntiles, ntaps, ncb0, ncb1, nkb;
+    float acc_scale;
+    long long* trace;
+    int dbg;      // development switches (bflow_tc3_debug): 1 no TMA loads, 2 no MMA, 4 no epilogue stores, 8 one MMA per k-step
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(T3_THREADS, 1)
+conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant__ CUtensorMap map0l, const __grid_constant__ CUtensorMap map1h,
+                const __grid_constant__ CUtensorMap map1l, const bflow_conv_desc d, const uint8_t* __restrict__ wtc, const T3Params p, int* err) {
+    constexpr int B_BYTES = BN * 128;
+    constexpr int STAGE_BYTES = 2 * T3_A_BYTES + 2 * B_BYTES;
+    constexpr uint32_t TX_BYTES = 2 * T3_A_BYTES + 2 * B_BYTES;
+    // BN <= 128: the weight tile's hi and lo halves are contiguous in shared memory, so A_hi x [B_hi; B_lo] is ONE tcgen05.mma with
+    // N = 2 BN (columns [0,BN) = hi*hi, [BN,2BN) = hi*lo) and A_lo x B_hi a second one into [0,BN): 2 instructions per k-step
+    // instead of 3 (the single issuing thread, not the tensor pipe, is the limiter for small N).  The epilogue adds the two halves.
+    constexpr bool STACK = BN <= 128;
+    constexpr int ACC_COLS = STACK ? 2 * BN : BN;
+    constexpr int TMEM_COLS = 2 * ACC_COLS;                   // two accumulators
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (t3_smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
+    auto empty_bar = [&](int s) { return bars + 32u + 8u * (uint32_t)s; };
+    auto tfull_bar = [&](int a) { return bars + 64u + 8u * (uint32_t)a; };
+    auto tempty_bar = [&](int a) { return bars + 80u + 8u * (uint32_t)a; };
+    const uint32_t tmem_slot = bars + 96u;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int n_tiles = p.n_mtiles * p.n_ntiles;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            t3_mbar_init(full_bar(s), 1);      // the producer's arrive.expect_tx (+ TMA bytes)
+            t3_mbar_init(empty_bar(s), 1);     // one tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            t3_mbar_init(tfull_bar(a), 1);     // one tcgen05.commit
+            t3_mbar_init(tempty_bar(a), T3_EPI_WARPS);    // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    t3_fence_before();
+    __syncthreads();
+    t3_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer ------------------------------------------------
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m_tile = tile / p.n_ntiles, n_tile = tile - m_tile * p.n_ntiles;
+                const int m0 = m_tile * T3_BM;
+                const int ow = m0 % d.Wo;
+                const int t = m0 / d.Wo;
+                const int oh = t % d.Ho;
+                const int n = t / d.Ho;
+                const int cw = ow * d.stride - d.pad_w, ch = oh * d.stride - d.pad_h;
+                const uint8_t* wt = wtc + (size_t)n_tile * p.nkb * (2 * B_BYTES);
+                int kb = 0;
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    const int kh = tap / d.KW, kw = tap - kh * d.KW;
+                    for (int cb = 0; cb < p.ncb0 + p.ncb1; ++cb, ++kb, ++it) {
+                        const int s = (int)(it % STAGES);
+                        const uint32_t ph = (it / STAGES) & 1u;
+                        t3_mbar_wait(empty_bar(s), ph ^ 1u, err);
+                        T3_TRACE(0, it);
+                        const uint32_t stage = smem_base + (uint32_t)s * STAGE_BYTES;
+                        const uint32_t bar = full_bar(s);
+                        t3_mbar_arrive_expect_tx(bar, TX_BYTES);
+                        const bool src0 = cb < p.ncb0;
+                        const int cc = (src0 ? cb : cb - p.ncb0) * 64;
+                        t3_tma_im2col(stage, src0 ? &map0h : &map1h, cc, cw, ch, n, (uint16_t)kw, (uint16_t)kh, bar);
+                        t3_tma_im2col(stage + T3_A_BYTES, src0 ? &map0l : &map1l, cc, cw, ch, n, (uint16_t)kw, (uint16_t)kh, bar);
+                        t3_bulk_g2s(stage + 2 * T3_A_BYTES, wt + (size_t)kb * (2 * B_BYTES), 2 * B_BYTES, bar);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer ------------------------------------------------
+        // fp16 x fp16 -> fp32, K-major, M 128, N = BN (idesc) or 2 BN (idesc2)
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
+        const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
+        uint32_t it = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
+            t3_mbar_wait(tempty_bar(acc), aph ^ 1u, err);          // epilogue has drained this accumulator
+            t3_fence_after();
+            const uint32_t tacc = tmem_base + acc * ACC_COLS;
+            for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+                const int s = (int)(it % STAGES);
+                const uint32_t ph = (it / STAGES) & 1u;
+                t3_mbar_wait(full_bar(s), ph, err);
+                t3_fence_after();
+                if (lane == 0) T3_TRACE(1, it);
+                if (lane == 0) {
+                    const uint32_t a_hi = smem_base + (uint32_t)s * STAGE_BYTES;
+                    const uint32_t a_lo = a_hi + T3_A_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * T3_A_BYTES;
+                    const uint32_t b_lo = b_hi + B_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t ko = (uint32_t)k * 32u;
+                        const uint64_t dah = t3_umma_desc(a_hi + ko), dal = t3_umma_desc(a_lo + ko);
+                        const uint64_t dbh = t3_umma_desc(b_hi + ko);
+                        if (STACK) {
+                            t3_umma(tacc, dah, dbh, idesc2, (kb > 0 || k > 0) ? 1u : 0u);      // hi*hi | hi*lo
+                            t3_umma(tacc, dal, dbh, idesc, 1u);                               // lo*hi
+                        } else {
+                            const uint64_t dbl = t3_umma_desc(b_lo + ko);
+                            t3_umma(tacc, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            t3_umma(tacc, dah, dbl, idesc, 1u);
+                            t3_umma(tacc, dal, dbh, idesc, 1u);
+                        }
+                    }
+                    t3_commit(empty_bar(s));
+                    if (kb == p.nkb - 1) t3_commit(tfull_bar(acc));
+                    T3_TRACE(2, it);
+                }
+                __syncwarp();
+            }
+        }
+        t3_fence_before();
+    } else {
+        // ------------------------------------------------ epilogue ------------------------------------------------
+        // 8 warps: quadrant (warp & 3) of the TMEM lanes = 32 tile rows, column half ((warp - 2) >> 2).  The tile's bias slice is
+        // staged in shared memory once per n_tile; all tcgen05.ld of a thread's columns are issued before the single wait.
+        constexpr int HALF = BN / 2;                  // columns per thread
+        const int quad = warp & 3;
+        const int chalf = (warp - 2) >> 2;
+        const int etid = tid - 64;                   // 0 .. 255
+        float* s_bias = reinterpret_cast<float*>(smem_raw + (bars - t3_smem_u32(smem_raw)) + 128);   // BN floats behind the barriers
+        const float lo1 = d.act1 == BFLOW_ACT_RELU ? 0.f : -INFINITY, lo2 = d.act2 == BFLOW_ACT_RELU ? 0.f : -INFINITY;
+        const bool slow1 = d.act1 >= BFLOW_ACT_SIGMOID, slow2 = d.act2 >= BFLOW_ACT_SIGMOID;
+        const bool aligned = (d.y == nullptr || (((d.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15) == 0))) &&
+                             (d.res == nullptr || (((d.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.res) & 15) == 0)));
+        const float post = d.scale;
+        uint32_t lt = 0;
+        int bias_tile = -1;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            const int m_tile = tile / p.n_ntiles, n_tile = tile - m_tile * p.n_ntiles;
+            const int m = m_tile * T3_BM + quad * 32 + lane;
+            const int n0 = n_tile * BN;
+            if (n_tile != bias_tile) {               // uniform over the epilogue warps
+                asm volatile("bar.sync 1, 256;" ::: "memory");      // everyone is done with the previous slice
+                for (int j = etid; j < BN; j += 256) s_bias[j] = (d.bias != nullptr && n0 + j < d.Cout) ? __ldg(d.bias + n0 + j) : 0.f;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                bias_tile = n_tile;
+            }
+            const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
+            t3_mbar_wait(tfull_bar(acc), aph, err);
+            t3_fence_after();
+            if (warp == 2 && lane == 0) T3_TRACE(3, lt);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_COLS + (uint32_t)(chalf * HALF);
+            const int nb0 = n0 + chalf * HALF;
+            if (nb0 < d.Cout) {                      // warp-uniform
+                float v[HALF];
+#pragma unroll
+                for (int c = 0; c < HALF; c += 16) t3_tmem_ld16_nowait(taddr + (uint32_t)c, v + c);
+                if (STACK) {
+                    float u[HALF];
+#pragma unroll
+                    for (int c = 0; c < HALF; c += 16) t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c), u + c);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int c = 0; c < HALF; ++c) v[c] += u[c];
+                } else {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                }
+                // the accumulator is in registers: hand the TMEM buffer back before the (slow) global stores
+                t3_fence_before();
+                __syncwarp();
+                if (lane == 0) t3_mbar_arrive(tempty_bar(acc));
+                if (warp == 2 && lane == 0) T3_TRACE(4, lt);
+                if (m < p.M) {
+#pragma unroll
+                    for (int c = 0; c < HALF; c += 16) {
+                        const int nb = nb0 + c;
+                        if (nb >= d.Cout) break;
+                        float* w = v + c;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + chalf * HALF + c + j);
+                            w[j] = post * fmaf(w[j], p.acc_scale, b4.x); w[j + 1] = post * fmaf(w[j + 1], p.acc_scale, b4.y);
+                            w[j + 2] = post * fmaf(w[j + 2], p.acc_scale, b4.z); w[j + 3] = post * fmaf(w[j + 3], p.acc_scale, b4.w);
+                        }
+                        if (d.epi == BFLOW_EPI_STD && aligned && nb + 15 < d.Cout) {
+                            if (slow1) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) w[j] = apply_act(w[j], d.act1);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) w[j] = fmaxf(w[j], lo1);
+                            }
+                            if (d.res != nullptr) {
+                                const float* rrow = d.res + (size_t)m * d.ldr + nb;
+#pragma unroll
+                                for (int j = 0; j < 16; j += 4) {
+                                    const float4 r4 = *reinterpret_cast<const float4*>(rrow + j);
+                                    w[j] += r4.x; w[j + 1] += r4.y; w[j + 2] += r4.z; w[j + 3] += r4.w;
+                                }
+                            } else if (d.res16_hi != nullptr) {
+#pragma unroll
+                                for (int j = 0; j < 16; j += 4) {
+                                    const float4 r4 = load_split4(d.res16_hi, d.res16_lo, (size_t)m * d.ldr16 + nb + j);
+                                    w[j] += r4.x; w[j + 1] += r4.y; w[j + 2] += r4.z; w[j + 3] += r4.w;
+                                }
+                            }
+                            if (slow2) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) w[j] = apply_act(w[j], d.act2);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) w[j] = fmaxf(w[j], lo2);
+                            }
+                            if (d.y != nullptr) {
+                                float* yrow = d.y + (size_t)m * d.ldy + nb;
+#pragma unroll
+                                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(yrow + j) = make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
+                            }
+                            if (d.y16_hi != nullptr) {
+#pragma unroll
+                                for (int j = 0; j < 16; j += 4) store_split4(d.y16_hi, d.y16_lo, (size_t)m * d.ldy16 + nb + j, w[j], w[j + 1], w[j + 2], w[j + 3]);
+                            }
+                        } else {
+                            // GRU gate epilogues and ragged / unaligned tails
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                float t4[4] = {w[j], w[j + 1], w[j + 2], w[j + 3]};
+                                conv_epilogue4(d, m, nb + j, t4, aligned && (nb + j + 3 < d.Cout));
+                            }
+                        }
+                    }
+                }
+            } else {
+                t3_fence_before();
+                __syncwarp();
+                if (lane == 0) t3_mbar_arrive(tempty_bar(acc));
+            }
+            if (warp == 2 && lane == 0) T3_TRACE(5, lt);
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        t3_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                   cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+static EncodeIm2colFn get_encode_im2col() {
+    static EncodeIm2colFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeIm2colFn>(p);
+    }
+    return fn;
+}
+
+static int g_num_sms = 0;
+static int g_tc3_debug = 0;
+static long long* g_tc3_trace = nullptr;
+
+template <int BN, int STAGES>
+static int launch_tc3(const CUtensorMap* maps, const bflow_conv_desc& d, const void* wtc, const T3Params& p, int* err, cudaStream_t stream) {
+    constexpr int smem = STAGES * (2 * T3_A_BYTES + 2 * BN * 128) + 128 + BN * 4 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            set_error(cudaGetErrorString(e));
+            return BFLOW_ERR_CUDA;
+        }
+        configured = true;
+    }
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    const int n_tiles = p.n_mtiles * p.n_ntiles;
+    const int grid = n_tiles < g_num_sms ? n_tiles : g_num_sms;
+    conv_tc3_kernel<BN, STAGES><<<grid, T3_THREADS, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], d, reinterpret_cast<const uint8_t*>(wtc), p, err);
+    return check_launch("bflow_conv2d_nhwc_tc3");
+}
+
+__global__ void split_f16_kernel(const float* __restrict__ src, int ld, __half* __restrict__ hi, __half* __restrict__ lo, int ld16, long long rows, int C4) {
+    const long long total = rows * C4;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / C4;
+        const int c = (int)(idx - r * C4) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(src + r * ld + c);
+        store_split4(hi, lo, (size_t)r * ld16 + c, v.x, v.y, v.z, v.w);
+    }
+}
+
+}  // namespace bflow
+
+extern "C" void bflow_tc3_trace(long long* device_buf_6x256) { bflow::g_tc3_trace = device_buf_6x256; }
+
+extern "C" void bflow_tc3_debug(int flags) { bflow::g_tc3_debug = flags; }
+
+extern "C" int bflow_split_f16(const float* src, int ld, void* hi, void* lo, int ld16, long long rows, int C, void* stream) {
+    BFLOW_REQUIRE(src != nullptr && hi != nullptr && lo != nullptr, "split_f16: null tensor");
+    BFLOW_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && ld >= C && ld % 4 == 0 && ld16 >= C && ld16 % 4 == 0, "split_f16: bad shape");
+    BFLOW_REQUIRE(bflow::aligned16(src) && (reinterpret_cast<uintptr_t>(hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(lo) & 7) == 0, "split_f16: alignment");
+    const long long total = rows * (C / 4);
+    long long g = (total + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    bflow::split_f16_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(src, ld, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), ld16, rows, C / 4);
+    return bflow::check_launch("bflow_split_f16");
+}
+
+extern "C" int bflow_tma_im2col_map(void* map_out, const void* base, int N, int H, int W, int C, int ld_halves, int KH, int KW, int stride, int pad_h,
+                                    int pad_w) {
+    BFLOW_REQUIRE(map_out != nullptr && base != nullptr, "tma_im2col_map: null argument");
+    BFLOW_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && ld_halves >= C && ld_halves % 8 == 0, "tma_im2col_map: bad shape (ld must be a multiple of 8 halves)");
+    BFLOW_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tma_im2col_map: base must be 16-byte aligned");
+    BFLOW_REQUIRE(KH > 0 && KW > 0 && stride >= 1 && stride <= 8 && pad_h >= 0 && pad_w >= 0, "tma_im2col_map: bad window");
+    bflow::EncodeIm2colFn enc = bflow::get_encode_im2col();
+    BFLOW_REQUIRE(enc != nullptr, "tma_im2col_map: cuTensorMapEncodeIm2col not available from the driver");
+    alignas(64) CUtensorMap tm;
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)ld_halves * 2, (cuuint64_t)W * ld_halves * 2, (cuuint64_t)H * W * ld_halves * 2};
+    const int lower[2] = {-pad_w, -pad_h};                                    // {W, H}
+    const int upper[2] = {pad_w - (KW - 1), pad_h - (KH - 1)};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper, 64, bflow::T3_BM, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        bflow::set_error("tma_im2col_map: cuTensorMapEncodeIm2col failed");
+        return BFLOW_ERR_CUDA;
+    }
+    // driver workaround carried by CUTLASS (copy_traits_sm90_im2col.hpp): im2col descriptors of tensors smaller than 128 KiB
+    int drv = 0;
+    cudaDriverGetVersion(&drv);
+    if (drv <= 13010 && (unsigned long long)N * H * W * ld_halves * 2ull < 131072ull) reinterpret_cast<uint64_t*>(&tm)[1] &= ~(1ull << 21);
+    memcpy(map_out, &tm, sizeof(tm));
+    return BFLOW_OK;
+}
+
+extern "C" int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* dp, const void* maps, const void* w_tc, int bn, float acc_scale, int* err, void* stream) {
+    BFLOW_REQUIRE(dp != nullptr && maps != nullptr && w_tc != nullptr, "conv_tc3: null argument");
+    const bflow_conv_desc& d = *dp;
+    BFLOW_REQUIRE(d.c0 > 0 && d.c0 % 8 == 0 && d.c1 >= 0 && d.c1 % 8 == 0 && (d.c1 == 0 || d.c0 % 64 == 0), "conv_tc3: channel counts");
+    BFLOW_REQUIRE(d.N > 0 && d.H > 0 && d.W > 0 && d.Cout > 0 && d.KH > 0 && d.KW > 0 && d.stride > 0, "conv_tc3: bad shape");
+    BFLOW_REQUIRE(d.Ho == (d.H + 2 * d.pad_h - d.KH) / d.stride + 1 && d.Wo == (d.W + 2 * d.pad_w - d.KW) / d.stride + 1, "conv_tc3: Ho/Wo mismatch");
+    BFLOW_REQUIRE((d.y == nullptr || d.ldy >= d.Cout) && (d.res == nullptr || d.ldr >= d.Cout), "conv_tc3: bad output stride");
+    BFLOW_REQUIRE((reinterpret_cast<uintptr_t>(w_tc) & 15) == 0 && (reinterpret_cast<uintptr_t>(maps) & 7) == 0, "conv_tc3: alignment");
+    if (const char* msg = bflow::check_epilogue(d)) { bflow::set_error(msg); return BFLOW_ERR_INVALID; }
+    const long long Mll = (long long)d.N * d.Ho * d.Wo;
+    BFLOW_REQUIRE(Mll < (1ll << 31), "conv_tc3: too large");
+    bflow::T3Params p;
+    p.M = (int)Mll;
+    p.n_mtiles = (p.M + bflow::T3_BM - 1) / bflow::T3_BM;
+    p.n_ntiles = (d.Cout + bn - 1) / bn;
+    p.ntaps = d.KH * d.KW;
+    p.ncb0 = (d.c0 + 63) / 64;
+    p.ncb1 = (d.c1 + 63) / 64;
+    p.nkb = p.ntaps * (p.ncb0 + p.ncb1);
+    p.acc_scale = acc_scale;
+    p.dbg = bflow::g_tc3_debug;
+    p.trace = bflow::g_tc3_trace;
+    alignas(64) CUtensorMap tm[4];
+    memcpy(tm, maps, sizeof(tm));
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (bn) {
+        case 64: return bflow::launch_tc3<64, 4>(tm, d, w_tc, p, err, st);
+        case 128: return bflow::launch_tc3<128, 3>(tm, d, w_tc, p, err, st);
+        case 256: return bflow::launch_tc3<256, 2>(tm, d, w_tc, p, err, st);
+        default: bflow::set_error("conv_tc3: bn must be 64, 128 or 256"); return BFLOW_ERR_INVALID;
+    }
+}

@@ -237,7 +237,11 @@ __global__ void __launch_bounds__(LK2_WARPS * 32) corr_lookup_tiled_kernel(const
             for (int j = 0; j < 3; ++j) {
                 if (lane + 32 * j < 81) {
                     const float* f = f0 + soff[j];
-                    o[lane + 32 * j] = w00 * f[0] + w01 * f[1] + w10 * f[LK2_PITCH] + w11 * f[LK2_PITCH + 1];
+                    const float val = w00 * f[0] + w01 * f[1] + w10 * f[LK2_PITCH] + w11 * f[LK2_PITCH + 1];
+                    if (d.out16_hi != nullptr)
+                        store_split1(d.out16_hi, d.out16_lo, (size_t)bq * d.out16_ld + slot * 81 + lane + 32 * j, val);
+                    else
+                        o[lane + 32 * j] = val;
                 }
             }
         }
@@ -253,11 +257,13 @@ extern "C" int bflow_corr_lookup(const bflow_lookup_desc* dp, void* stream) {
     BFLOW_REQUIRE(d.n_targets > 0 && d.n_targets <= BFLOW_MAX_TARGETS, "lookup: bad target count");
     BFLOW_REQUIRE(d.B > 0 && d.h > 0 && d.w > 0, "lookup: bad shape");
     BFLOW_REQUIRE(d.radius == 4, "lookup: radius is fixed to 4 (raft.py:38-40, corr.py:279)");
-    BFLOW_REQUIRE(d.out != nullptr, "lookup: null output");
+    BFLOW_REQUIRE(d.out != nullptr || d.out16_hi != nullptr, "lookup: null output");
+    BFLOW_REQUIRE(d.out16_hi == nullptr || (d.out16_lo != nullptr && d.tiled && d.out_nhwc && d.out16_ld >= d.n_slots * 81),
+                  "lookup: split-fp16 output needs the tiled NHWC path");
     BFLOW_REQUIRE(d.coords != nullptr || (d.params != nullptr && d.degree >= 1 && d.degree <= BFLOW_MAX_DEGREE &&
                                           d.params_ld >= 2 * d.degree),
                   "lookup: need coords or Bezier params");
-    BFLOW_REQUIRE(!d.out_nhwc || d.out_ld >= d.n_slots * 81, "lookup: out_ld too small");
+    BFLOW_REQUIRE(!d.out_nhwc || d.out16_hi != nullptr || d.out_ld >= d.n_slots * 81, "lookup: out_ld too small");
     for (int s = 0; s < d.n_slots; ++s) {
         BFLOW_REQUIRE(d.vol[s] != nullptr && d.hl[s] > 0 && d.wl[s] > 0, "lookup: bad pyramid level");
         BFLOW_REQUIRE(d.target[s] >= 0 && d.target[s] < d.n_targets, "lookup: bad slot target");

@@ -121,6 +121,53 @@ __global__ void __launch_bounds__(256) instnorm_relu_kernel(const float* __restr
     }
 }
 
+__global__ void __launch_bounds__(256) instnorm_relu16_kernel(const float* __restrict__ a, int lda, const double* __restrict__ sums_a,
+                                                              const float* __restrict__ r, int ldr, const double* __restrict__ sums_r,
+                                                              const void* __restrict__ r16h, const void* __restrict__ r16l, int ldr16,
+                                                              float* __restrict__ out, int ldo, void* __restrict__ o16h, void* __restrict__ o16l, int ldo16,
+                                                              int HW, int C, float eps) {
+    __shared__ float mu_a[IN_MAXC], rs_a[IN_MAXC], mu_r[IN_MAXC], rs_r[IN_MAXC];
+    const int n = blockIdx.y;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double s = sums_a[((size_t)n * C + c) * 2], ss = sums_a[((size_t)n * C + c) * 2 + 1];
+        double m = s / HW;
+        double var = ss / HW - m * m;
+        if (var < 0.0) var = 0.0;
+        mu_a[c] = (float)m;
+        rs_a[c] = (float)(1.0 / sqrt(var + (double)eps));
+        mu_r[c] = 0.f;
+        rs_r[c] = 1.f;
+        if (sums_r != nullptr) {
+            s = sums_r[((size_t)n * C + c) * 2]; ss = sums_r[((size_t)n * C + c) * 2 + 1];
+            m = s / HW;
+            var = ss / HW - m * m;
+            if (var < 0.0) var = 0.0;
+            mu_r[c] = (float)m;
+            rs_r[c] = (float)(1.0 / sqrt(var + (double)eps));
+        }
+    }
+    __syncthreads();
+    const int p0 = blockIdx.x * IN_CHUNK;
+    const int np = min(IN_CHUNK, HW - p0);
+    const int C4 = C >> 2;
+    for (int idx = threadIdx.x; idx < np * C4; idx += blockDim.x) {
+        const int pp = idx / C4, c = (idx - pp * C4) * 4;
+        const size_t pix = (size_t)n * HW + p0 + pp;
+        const float4 v = *reinterpret_cast<const float4*>(a + pix * lda + c);
+        float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = fmaxf((o[j] - mu_a[c + j]) * rs_a[c + j], 0.f);
+        if (r != nullptr || r16h != nullptr) {
+            const float4 rv = r != nullptr ? *reinterpret_cast<const float4*>(r + pix * ldr + c) : load_split4(r16h, r16l, pix * ldr16 + c);
+            const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j] + (rr[j] - mu_r[c + j]) * rs_r[c + j], 0.f);
+        }
+        if (out != nullptr) *reinterpret_cast<float4*>(out + pix * ldo + c) = make_float4(o[0], o[1], o[2], o[3]);
+        if (o16h != nullptr) store_split4(o16h, o16l, pix * ldo16 + c, o[0], o[1], o[2], o[3]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // SepConvGRU gate arithmetic (models/raft_spline/update.py:37-40,44-47)
 // ---------------------------------------------------------------------------------------------
@@ -315,6 +362,23 @@ extern "C" int bflow_instnorm_relu(const float* a, int lda, const double* sums_a
     dim3 grid(ceil_div(HW, IN_CHUNK), N);
     instnorm_relu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, lda, sums_a, r, ldr, sums_r, out, ldo, HW, C, eps);
     return check_launch("bflow_instnorm_relu");
+}
+
+extern "C" int bflow_instnorm_relu16(const float* a, int lda, const double* sums_a, const float* r, int ldr, const double* sums_r,
+                                     const void* r16_hi, const void* r16_lo, int ldr16, float* out, int ldo, void* out16_hi, void* out16_lo,
+                                     int ldo16, int N, int HW, int C, float eps, void* stream) {
+    BFLOW_REQUIRE(a != nullptr && sums_a != nullptr && (out != nullptr || out16_hi != nullptr), "instnorm16: null tensor");
+    BFLOW_REQUIRE(N > 0 && N <= 65535 && HW > 0 && C > 0 && C <= IN_MAXC && C % 4 == 0, "instnorm16: bad shape (C%4==0, C<=512)");
+    BFLOW_REQUIRE(lda >= C && lda % 4 == 0 && aligned16(a), "instnorm16: alignment");
+    BFLOW_REQUIRE(out == nullptr || (ldo >= C && ldo % 4 == 0 && aligned16(out)), "instnorm16: fp32 output alignment");
+    BFLOW_REQUIRE(out16_hi == nullptr || (out16_lo != nullptr && ldo16 >= C && ldo16 % 4 == 0), "instnorm16: split output");
+    BFLOW_REQUIRE(r == nullptr || (r16_hi == nullptr && ldr >= C && ldr % 4 == 0 && aligned16(r)), "instnorm16: residual alignment");
+    BFLOW_REQUIRE(r16_hi == nullptr || (r16_lo != nullptr && ldr16 >= C && ldr16 % 4 == 0 && sums_r == nullptr), "instnorm16: split residual");
+    BFLOW_REQUIRE(r != nullptr || sums_r == nullptr, "instnorm16: residual sums without fp32 residual");
+    dim3 grid(ceil_div(HW, IN_CHUNK), N);
+    instnorm_relu16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, lda, sums_a, r, ldr, sums_r, r16_hi, r16_lo, ldr16, out, ldo, out16_hi, out16_lo, ldo16,
+                                                                   HW, C, eps);
+    return check_launch("bflow_instnorm_relu16");
 }
 
 extern "C" int bflow_gru_rh(const float* zr, int ldzr, const float* h, int ldh, float* rh, int ldrh, long long rows, int C, void* stream) {

@@ -23,6 +23,7 @@ from . import _lib, config as _cfg
 from ._lib import ACT, EPI, ConvDesc, LookupDesc, check
 from .bezier import bernstein_coeffs
 from .ops import pack_conv_weight, pack_conv_weight_tc, make_lookup_desc, tiled_plane_size
+from .engine_s16 import S16Recorder
 
 
 def _ceil(a: int, b: int) -> int:
@@ -43,6 +44,13 @@ class _Weight:
             self.tc[bn] = pack_conv_weight_tc(self.oihw, bn, self.cin_pad)
         return self.tc[bn]
 
+    def tc3_image(self, bn: int, c0: int):
+        """Weight image of the TMA-fed kernel: K ordered (tap, 64-channel block), sources padded separately."""
+        key = ('tc3', bn, c0)
+        if key not in self.tc:
+            self.tc[key] = pack_conv_weight_tc(self.oihw, bn, self.cin_pad, block_per_tap=True, c0=c0)
+        return self.tc[key]
+
 
 class Engine:
     def __init__(self, model, device: torch.device):
@@ -51,6 +59,8 @@ class Engine:
         self.lib = _lib.lib()
         self.use_graph = os.environ.get('BFLOW_GRAPH', '1') != '0'
         self.use_tc = os.environ.get('BFLOW_TC', '1') != '0'      # tcgen05 convolutions (0: fp32 CUDA-core kernels only)
+        # TMA-fed persistent tensor-core kernel on split-fp16 activations (0: register-staged tcgen05 kernel on fp32 activations)
+        self.use_tc3 = self.use_tc and os.environ.get('BFLOW_TC3', '1') != '0'
         self.err = torch.zeros(1, device=device, dtype=torch.int32)
         self._plans: Dict[tuple, '_Plan'] = {}
         self._pack(model)
@@ -161,7 +171,7 @@ class Engine:
         return self._plans[key]
 
 
-class _Plan:
+class _Plan(S16Recorder):
     """Workspace + recorded launch list (+ CUDA graph) for one (B, H, W, iters, test_mode)."""
 
     def __init__(self, eng: Engine, B: int, H: int, W: int, iters: int, test_mode: bool):
@@ -188,7 +198,10 @@ class _Plan:
         self.low = torch.empty(B, 2 * eng.deg, self.h, self.w, **f32)
         n_up = 1 if test_mode else iters
         self.ups = [torch.empty(B, 2 * eng.deg, H, W, **f32) for _ in range(n_up)]
-        self._record()
+        if eng.use_tc3:
+            self._record_s16()
+        else:
+            self._record()
 
     # ---- recording helpers -------------------------------------------------------------------------------
     def _add(self, fn, *args, label: Optional[str] = None, flops: float = 0.0):

@@ -1,0 +1,391 @@
+"""Launch recording for the TMA-fed tensor-core path (the default on sm_100a).
+
+Every tensor that feeds a convolution is kept as split-fp16 planes (x = hi + lo, ``_S16``): whoever produces it (conv
+epilogues, InstanceNorm, the correlation lookup) writes the two planes directly, and ``bflow_conv2d_nhwc_tc3`` reads them
+through im2col tensor maps.  fp32 copies exist only where something other than a convolution consumes the tensor: raw
+pre-norm conv outputs, the GRU state ``h``, the Bezier parameters, z|r gates, the upsampling mask and the correlation
+volume.  The structure of the forward pass is the same as in ``engine._Plan._record`` (models/raft_spline/raft.py:101-200).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT, EPI, ConvDesc, check
+from .ops import make_lookup_desc, tiled_plane_size
+
+
+class _S16:
+    """Split-fp16 activation: two fp16 planes (hi, lo) of ``rows x ld`` halves.  ``base``: device pointer of a caller-owned
+    region of ``rows*ld*4`` bytes, or None to allocate (zero-filled)."""
+
+    def __init__(self, rows: int, ld: int, dev, base: Optional[int] = None, lo_base: Optional[int] = None):
+        self.rows, self.ld = rows, ld
+        if base is None:
+            self.t = torch.zeros(2, rows, ld, device=dev, dtype=torch.float16)
+            base = self.t.data_ptr()
+        self.base = base
+        self.lo_base = base + 2 * rows * ld if lo_base is None else lo_base
+
+    def hi(self, c_off: int = 0) -> int:
+        return self.base + 2 * c_off
+
+    def lo(self, c_off: int = 0) -> int:
+        return self.lo_base + 2 * c_off
+
+    def rows_from(self, r0: int, nrows: int) -> '_S16':
+        """View of rows [r0, r0 + nrows) (same planes)."""
+        return _S16(nrows, self.ld, None, base=self.base + 2 * r0 * self.ld, lo_base=self.lo_base + 2 * r0 * self.ld)
+
+
+def choose_bn(cout: int, n_mtiles: int) -> int:
+    """Tile width: wide tiles keep the single MMA-issuing thread off the critical path; with few row tiles (the update
+    block at batch 1: 38) narrower tiles put more CTAs to work."""
+    if cout <= 64:
+        return 64
+    if n_mtiles >= 148:
+        return 128
+    return 128 if (cout >= 256 and cout % 128 == 0) else 64
+
+
+class S16Recorder:
+    """Mixin of engine._Plan."""
+
+    # ---- helpers -------------------------------------------------------------------------------------------------------
+    def _maps(self, srcs: Sequence[Tuple[_S16, int, int]], N, H, W, wt) -> C.Array:
+        buf = (C.c_uint8 * 512)()
+        ph, pw = wt.pad
+        for i, (s, c_off, cc) in enumerate(srcs):
+            for j, base in enumerate((s.hi(c_off), s.lo(c_off))):
+                check(self.eng.lib.bflow_tma_im2col_map(C.addressof(buf) + 128 * (2 * i + j), base, N, H, W, cc, s.ld, wt.kh, wt.kw, wt.stride, ph, pw),
+                      'tma_im2col_map')
+        self.keep.append(buf)
+        return buf
+
+    def _conv3(self, wt, srcs: Sequence[Tuple[_S16, int, int]], N, H, W, y=None, ldy=0, y16: Optional[Tuple[_S16, int]] = None,
+               act1='none', act2='none', res=None, ldr=0, res16: Optional[Tuple[_S16, int]] = None, scale=1.0, bias=True,
+               epi='std', aux0=None, ld_aux0=0, aux1_16: Optional[Tuple[_S16, int]] = None):
+        """Tensor-core convolution on split-fp16 sources [(tensor, channel offset, channels), ...] (channel concatenation)."""
+        lib = self.eng.lib
+        c0 = srcs[0][2]
+        c1 = srcs[1][2] if len(srcs) > 1 else 0
+        assert c0 + c1 == wt.cin, (c0, c1, wt.cin)
+        d = ConvDesc()
+        d.x0, d.c0, d.ld0 = None, c0, srcs[0][0].ld
+        d.x1, d.c1, d.ld1 = None, c1, (srcs[1][0].ld if c1 else 0)
+        d.w, d.ldw, d.bias = None, 0, (wt.b.data_ptr() if bias else None)
+        d.res, d.ldr = res, ldr
+        d.y, d.ldy = y, ldy
+        ph, pw = wt.pad
+        Ho, Wo = (H + 2 * ph - wt.kh) // wt.stride + 1, (W + 2 * pw - wt.kw) // wt.stride + 1
+        d.N, d.H, d.W, d.Ho, d.Wo, d.Cout = N, H, W, Ho, Wo, wt.cout
+        d.KH, d.KW, d.stride, d.pad_h, d.pad_w = wt.kh, wt.kw, wt.stride, ph, pw
+        d.act1, d.act2, d.scale = ACT[act1], ACT[act2], scale
+        d.epi, d.aux0, d.ld_aux0, d.aux1, d.ld_aux1 = EPI[epi], aux0, ld_aux0, None, 0
+        if y16 is not None:
+            d.y16_hi, d.y16_lo, d.ldy16 = y16[0].hi(y16[1]), y16[0].lo(y16[1]), y16[0].ld
+        if res16 is not None:
+            d.res16_hi, d.res16_lo, d.ldr16 = res16[0].hi(res16[1]), res16[0].lo(res16[1]), res16[0].ld
+        if aux1_16 is not None:
+            d.aux1_16_hi, d.aux1_16_lo, d.ld_aux1_16 = aux1_16[0].hi(aux1_16[1]), aux1_16[0].lo(aux1_16[1]), aux1_16[0].ld
+        self.keep.append(d)
+        M = N * Ho * Wo
+        bn = choose_bn(wt.cout, (M + 127) // 128)
+        img, acc_scale = wt.tc3_image(bn, c0)
+        maps = self._maps(srcs, N, H, W, wt)
+        self._add(lib.bflow_conv2d_nhwc_tc3, C.byref(d), C.addressof(maps), img.data_ptr(), bn, acc_scale, self.eng.err.data_ptr(),
+                  label=f'conv_tc3_{bn} {c0 + c1}->{wt.cout} {wt.kh}x{wt.kw}/{wt.stride} M={M}', flops=2.0 * M * wt.cout * wt.kh * wt.kw * (c0 + c1))
+        self.n_tc += 1
+        return Ho, Wo
+
+    def _conv_simt16(self, wt, x0, c0, ld0, N, H, W, y=None, ldy=0, y16=None, act1='none', res=None, ldr=0, kernel='auto'):
+        """CUDA-core convolution on an fp32 source (7x7 stems, convf1, the tiny Bezier head conv), fp32 and/or split output."""
+        lib = self.eng.lib
+        d = ConvDesc()
+        d.x0, d.c0, d.ld0 = x0, c0, ld0
+        d.x1, d.c1, d.ld1 = None, 0, 0
+        d.w, d.ldw, d.bias = wt.w.data_ptr(), wt.ldw, wt.b.data_ptr()
+        d.res, d.ldr = res, ldr
+        d.y, d.ldy = y, ldy
+        ph, pw = wt.pad
+        Ho, Wo = (H + 2 * ph - wt.kh) // wt.stride + 1, (W + 2 * pw - wt.kw) // wt.stride + 1
+        d.N, d.H, d.W, d.Ho, d.Wo, d.Cout = N, H, W, Ho, Wo, wt.cout
+        d.KH, d.KW, d.stride, d.pad_h, d.pad_w = wt.kh, wt.kw, wt.stride, ph, pw
+        d.act1, d.act2, d.scale, d.epi = ACT[act1], 0, 1.0, 0
+        if y16 is not None:
+            d.y16_hi, d.y16_lo, d.ldy16 = y16[0].hi(y16[1]), y16[0].lo(y16[1]), y16[0].ld
+        self.keep.append(d)
+        fn = lib.bflow_conv2d_small_n if kernel == 'small_n' else lib.bflow_conv2d_nhwc
+        name = 'conv_small_n' if kernel == 'small_n' else 'conv_simt'
+        self._add(fn, C.byref(d), label=f'{name} {c0}->{wt.cout} {wt.kh}x{wt.kw}/{wt.stride} M={N * Ho * Wo}',
+                  flops=2.0 * N * Ho * Wo * wt.cout * wt.kh * wt.kw * c0)
+        return Ho, Wo
+
+    # ---- encoders (models/raft_utils/extractor.py:47-55,103-125) ---------------------------------------------------------
+    def _encoder16(self, E: dict, windows, Np: int, H: int, W: int, pool: List[int], final):
+        """pool: device pointers of >= 5 scratch regions of Np*(H/2)*(W/2)*64*4 bytes; each holds either a raw fp32 conv output or a
+        split-fp16 activation of the same element count."""
+        L = self.eng.lib
+        dev = self.eng.device
+        inorm = E['kind'] == 'instance'
+        free = list(pool)
+
+        def s16(ptr, rows, c):
+            return _S16(rows, c, dev, base=ptr)
+
+        H2, W2 = H // 2, W // 2
+        rows = Np * H2 * W2
+        w1 = E['conv1']
+        # stem: 7x7 stride-2 conv on the fp32 NHWC input, one launch per window
+        if inorm:
+            raw = free.pop()
+            n0 = 0
+            for ptr, cin, ld, ns in windows:
+                self._conv_simt16(w1, ptr, cin, ld, ns, H, W, y=raw + n0 * H2 * W2 * 64 * 4, ldy=64)
+                n0 += ns
+            xptr = free.pop()
+            X = s16(xptr, rows, 64)
+            sm = self._sums(Np, 64)
+            self._add(L.bflow_plane_sums, raw, 64, sm, Np, H2 * W2, 64)
+            self._add(L.bflow_instnorm_relu16, raw, 64, sm, None, 0, None, None, None, 0, None, 0, X.hi(), X.lo(), 64, Np, H2 * W2, 64, 1e-5)
+            free.append(raw)
+        else:
+            xptr = free.pop()
+            X = s16(xptr, rows, 64)
+            n0 = 0
+            for ptr, cin, ld, ns in windows:
+                self._conv_simt16(w1, ptr, cin, ld, ns, H, W, y16=(X.rows_from(n0 * H2 * W2, ns * H2 * W2), 0), act1='relu')
+                n0 += ns
+        Hc, Wc, Cc = H2, W2, 64
+        for blk in E['blocks']:
+            c1, c2, dn = blk['conv1'], blk['conv2'], blk['down']
+            Co = c1.cout
+            st = c1.stride
+            Ho, Wo = Hc // st, Wc // st
+            rin, rout = Np * Hc * Wc, Np * Ho * Wo
+            if inorm:
+                raw1 = free.pop()
+                self._conv3(c1, [(X, 0, Cc)], Np, Hc, Wc, y=raw1, ldy=Co)
+                y1p = free.pop()
+                Y1 = s16(y1p, rout, Co)
+                sm = self._sums(Np, Co)
+                self._add(L.bflow_plane_sums, raw1, Co, sm, Np, Ho * Wo, Co)
+                self._add(L.bflow_instnorm_relu16, raw1, Co, sm, None, 0, None, None, None, 0, None, 0, Y1.hi(), Y1.lo(), Co, Np, Ho * Wo, Co, 1e-5)
+                raw2 = raw1                                     # raw1 is dead: reuse it for conv2's output
+                self._conv3(c2, [(Y1, 0, Co)], Np, Ho, Wo, y=raw2, ldy=Co)
+                sm2 = self._sums(Np, Co)
+                self._add(L.bflow_plane_sums, raw2, Co, sm2, Np, Ho * Wo, Co)
+                outp = y1p                                      # Y1 is dead after conv2: the block output takes its place
+                OUT = s16(outp, rout, Co)
+                if dn is not None:
+                    rawd = free.pop()
+                    self._conv3(dn, [(X, 0, Cc)], Np, Hc, Wc, y=rawd, ldy=Co)
+                    smd = self._sums(Np, Co)
+                    self._add(L.bflow_plane_sums, rawd, Co, smd, Np, Ho * Wo, Co)
+                    self._add(L.bflow_instnorm_relu16, raw2, Co, sm2, rawd, Co, smd, None, None, 0, None, 0, OUT.hi(), OUT.lo(), Co, Np, Ho * Wo, Co, 1e-5)
+                    free.append(rawd)
+                else:
+                    self._add(L.bflow_instnorm_relu16, raw2, Co, sm2, None, 0, None, X.hi(), X.lo(), Cc, None, 0, OUT.hi(), OUT.lo(), Co, Np, Ho * Wo, Co, 1e-5)
+                free.append(raw2)
+                free.append(xptr)
+                X, xptr = OUT, outp
+            else:
+                y1p = free.pop()
+                Y1 = s16(y1p, rout, Co)
+                self._conv3(c1, [(X, 0, Cc)], Np, Hc, Wc, y16=(Y1, 0), act1='relu')
+                outp = free.pop()
+                OUT = s16(outp, rout, Co)
+                if dn is not None:
+                    dp = free.pop()
+                    D = s16(dp, rout, Co)
+                    self._conv3(dn, [(X, 0, Cc)], Np, Hc, Wc, y16=(D, 0))
+                    self._conv3(c2, [(Y1, 0, Co)], Np, Ho, Wo, y16=(OUT, 0), act1='relu', act2='relu', res16=(D, 0))
+                    free.append(dp)
+                else:
+                    self._conv3(c2, [(Y1, 0, Co)], Np, Ho, Wo, y16=(OUT, 0), act1='relu', act2='relu', res16=(X, 0))
+                free.append(y1p)
+                free.append(xptr)
+                X, xptr = OUT, outp
+            Hc, Wc, Cc = Ho, Wo, Co
+        final(X, Np, Hc, Wc, Cc)
+
+    # ---- the whole forward ---------------------------------------------------------------------------------------------------
+    def _record_s16(self):
+        from .engine import _ceil
+        eng, L = self.eng, self.eng.lib
+        cfg, dev = eng.cfg, eng.device
+        B, H, W, h, w, Q, R = self.B, self.H, self.W, self.h, self.w, self.Q, self.R
+        f32 = dict(device=dev, dtype=torch.float32)
+        deg, hd, cd, md, fd = eng.deg, eng.hdim, eng.cdim, eng.mdim, eng.fdim
+        nctx, ncorr = cfg['num_bins']['context'], cfg['num_bins']['correlation']
+        T_ev = len(cfg['correlation']['ev']['target_indices']) if self.use_ev else 0
+        T = len(eng.levels)
+        np_max = max((T_ev + 1) * B if self.use_ev else 0, 2 * B if self.use_img else 0, B)
+        pool_bytes = np_max * (H // 2) * (W // 2) * 64 * 4
+        self.pool = [torch.empty(pool_bytes, device=dev, dtype=torch.uint8) for _ in range(5)]
+        pool = [t.data_ptr() for t in self.pool]
+        self.sums = torch.zeros(64 * np_max * 128 * 2, device=dev, dtype=torch.float64)
+        self._sums_off = 0
+        self._add(L.bflow_zero, self.sums.data_ptr(), self.sums.numel() * 8)
+
+        gw = hd + cd + md
+        poff = hd + cd + md - 2 * deg
+        self.hx = torch.zeros(R, gw, **f32)                 # fp32 masters: h (cols 0:hd) and the Bezier params (cols poff:)
+        self.hx16 = _S16(R, gw, dev)                        # what the convolutions read
+        self.poff, self.gw = poff, gw
+        hx, hx16 = self.hx.data_ptr(), self.hx16
+
+        # ---- inputs to NHWC fp32 (the 7x7 stems run on CUDA cores) ----
+        ctx_c = (nctx if self.use_ev else 0) + (3 if self.use_img else 0)
+        self.ctx = torch.zeros(B, H, W, ctx_c, **f32)
+        if self.use_ev:
+            self.vox = torch.zeros(B, H, W, self.cin_vox, **f32)
+            self._add(L.bflow_nchw_to_nhwc, self.voxel_in.data_ptr(), self.vox.data_ptr(), B, self.cin_vox, H, W, 0, self.cin_vox, self.cin_vox, 1.0, 0.0)
+        if self.use_img:
+            self.imgs = torch.zeros(2 * B, H, W, 3, **f32)
+            for i in range(2):
+                self._add(L.bflow_nchw_to_nhwc, self.img_in[i].data_ptr(), self.imgs.data_ptr() + i * B * H * W * 3 * 4, B, 3, H, W, 0, 3, 3, 2.0 / 255.0, -1.0)
+
+        # ---- feature encoders: fp32 feature map for the volume GEMM's B operand, split copy for its A operand ----
+        def fnet(name, windows, Np):
+            fm = torch.empty(Np, h, w, fd, **f32)
+            fm16 = _S16(Np * Q, fd, dev)
+            E = eng.enc[name]
+            self._encoder16(E, windows, Np, H, W, pool,
+                            lambda X, n_, Hc, Wc, Cc: self._conv3(E['conv2'][0], [(X, 0, Cc)], n_, Hc, Wc, y=fm.data_ptr(), ldy=fd, y16=(fm16, 0)))
+            return fm, fm16
+        fm_ev = fm_img = fm_ev16 = fm_img16 = None
+        if self.use_ev:
+            idxs = [0] + list(cfg['correlation']['ev']['target_indices'])
+            fm_ev, fm_ev16 = fnet('fnet_ev', [(self.vox.data_ptr() + i * 4, ncorr, self.cin_vox, B) for i in idxs], (T_ev + 1) * B)
+        if self.use_img:
+            fm_img, fm_img16 = fnet('fnet_img', [(self.imgs.data_ptr(), 3, 3, 2 * B)], 2 * B)
+        self.fm_ev, self.fm_img, self.fm_ev16, self.fm_img16 = fm_ev, fm_img, fm_ev16, fm_img16
+
+        # ---- context encoder: net = tanh -> h (fp32 master + split copy), inp = relu -> split only (raft.py:144-147) ----
+        if self.use_ev and self.use_img:
+            self._add(L.bflow_nchw_to_nhwc, self.voxel_in.data_ptr(), self.ctx.data_ptr(), B, self.cin_vox, H, W, self.cin_vox - nctx, nctx, ctx_c, 1.0, 0.0)
+            self._add(L.bflow_nchw_to_nhwc, self.img_in[0].data_ptr(), self.ctx.data_ptr() + nctx * 4, B, 3, H, W, 0, 3, ctx_c, 2.0 / 255.0, -1.0)
+            cwin = [(self.ctx.data_ptr(), ctx_c, ctx_c, B)]
+        elif self.use_ev:
+            cwin = [(self.vox.data_ptr() + (self.cin_vox - nctx) * 4, nctx, self.cin_vox, B)]
+        else:
+            cwin = [(self.imgs.data_ptr(), 3, 3, B)]
+        Ec = eng.enc['cnet']
+
+        def cnet_final(X, n_, Hc, Wc, Cc):
+            self._conv3(Ec['conv2'][0], [(X, 0, Cc)], n_, Hc, Wc, y=hx, ldy=gw, y16=(hx16, 0), act1='tanh')
+            self._conv3(Ec['conv2'][1], [(X, 0, Cc)], n_, Hc, Wc, y16=(hx16, hd), act1='relu')
+        self._encoder16(Ec, cwin, B, H, W, pool, cnet_final)
+
+        # ---- initial Bezier parameters: zeros (+ flow_init) (raft.py:150-153): fp32 master + split copy ----
+        self._add(L.bflow_nchw_to_nhwc, self.init_in.data_ptr(), hx + poff * 4, B, 2 * deg, h, w, 0, 2 * deg, gw, 1.0, 0.0)
+        self._add(L.bflow_split_f16, hx + poff * 4, gw, hx16.hi(poff), hx16.lo(poff), gw, R, 2 * deg)
+
+        # ---- correlation volume (tensor-core GEMM, granule-tiled planes) + pyramid (corr.py:264-272, 293-305) ----
+        self.tiled = True
+        bnv = 128
+        Np0 = tiled_plane_size(h, w)
+        self.vol0 = torch.empty(T, R, Np0, **f32)
+        img_bytes = ((Np0 + bnv - 1) // bnv) * ((fd + 63) // 64) * 2 * bnv * 128
+        self.f2img = torch.zeros(T, B, img_bytes, device=dev, dtype=torch.uint8)
+        srcs = [(fm_ev, (t + 1) * B, fm_ev16) for t in range(T_ev)] + ([(fm_img, B, fm_img16)] if self.use_img else [])
+        for t, (fm2, n0, fm1_16) in enumerate(srcs):
+            for b in range(B):
+                self._add(L.bflow_pack_b_tc, fm2.data_ptr() + (n0 + b) * Q * fd * 4, fd, self.f2img[t, b].data_ptr(), Q, fd, bnv, h, w)
+                # corr[bq, n] = <f1[bq, :], f2[n, :]> / sqrt(D): a 1x1 "convolution" over the Q query pixels of sample b whose weight
+                # image is the packed target feature map
+                d = ConvDesc()
+                d.c0, d.ld0 = fd, fd
+                d.y, d.ldy = self.vol0[t].data_ptr() + b * Q * Np0 * 4, Np0
+                d.N, d.H, d.W, d.Ho, d.Wo, d.Cout = 1, 1, Q, 1, Q, Np0
+                d.KH, d.KW, d.stride = 1, 1, 1
+                d.scale = 1.0 / (fd ** 0.5)
+                self.keep.append(d)
+                sub = fm1_16.rows_from(b * Q, Q)
+                maps = (C.c_uint8 * 512)()
+                for j, base in enumerate((sub.hi(), sub.lo())):
+                    check(L.bflow_tma_im2col_map(C.addressof(maps) + 128 * j, base, 1, 1, Q, fd, fd, 1, 1, 1, 0, 0), 'tma_im2col_map')
+                self.keep.append(maps)
+                self._add(L.bflow_conv2d_nhwc_tc3, C.byref(d), C.addressof(maps), self.f2img[t, b].data_ptr(), bnv, 1.0, eng.err.data_ptr(),
+                          label=f'corr_volume_tc3 Q={Q} D={fd}', flops=2.0 * Q * Q * fd)
+        pyr = [(list(range(T)), self.vol0, h, w)]
+        for lvl in range(1, max(eng.levels)):
+            prev_idx, prev, hp_, wp_ = pyr[-1]
+            keep = [t for t in range(T) if eng.levels[t] > lvl]
+            hl, wl = hp_ // 2, wp_ // 2
+            cur = torch.empty(len(keep), R, tiled_plane_size(hl, wl), **f32)
+            for j, t in enumerate(keep):
+                self._add(L.bflow_corr_pool_tiled, prev[prev_idx.index(t)].data_ptr(), cur[j].data_ptr(), R, hp_, wp_)
+            pyr.append((keep, cur, hl, wl))
+        self.pyr = pyr
+
+        # ---- lookup: centres from the fp32 Bezier params, output written as split planes for convc1 ----
+        slots = [(lvl, t, pyr[lvl][1][pyr[lvl][0].index(t)], pyr[lvl][2], pyr[lvl][3]) for (lvl, t) in eng.slots]
+        self.corr16 = _S16(R, eng.ldc, dev)                 # zero-filled: the channels padding S*81 up to ldc stay zero
+        ld = make_lookup_desc(slots, T, B, h, w, True)
+        ld.coords = None
+        ld.params, ld.params_ld, ld.degree = hx + poff * 4, gw, deg
+        for t in range(T):
+            for k in range(deg):
+                ld.coef[t][k] = float(eng.coef[t, k])
+        ld.out, ld.out_nhwc, ld.out_ld = None, 1, eng.ldc
+        ld.out16_hi, ld.out16_lo, ld.out16_ld = self.corr16.hi(), self.corr16.lo(), eng.ldc
+        self.keep.append(ld)
+        self.lookup_desc = ld
+
+        # ---- update-block workspace ----
+        U = eng.upd
+        self.c1_16 = _S16(R, 256, dev)
+        self.cb16 = _S16(R, 256, dev)
+        self.f1_16 = _S16(R, 128, dev)
+        self.rh16 = _S16(R, hd, dev)
+        self.hm16 = _S16(R, 256, dev)
+        self.zr = torch.empty(R, 2 * hd, **f32)
+        self.hh = torch.empty(R, 256, **f32)
+        self.mask = torch.empty(R, 576, **f32)
+        zr, hh, mk = self.zr.data_ptr(), self.hh.data_ptr(), self.mask.data_ptr()
+        c1_16, cb16, f1_16, rh16, hm16 = self.c1_16, self.cb16, self.f1_16, self.rh16, self.hm16
+
+        def upsample(out_t):
+            self._conv3(U['mask0'], [(hx16, 0, hd)], B, h, w, y16=(hm16, 0), act1='relu')
+            self._conv3(U['mask2'], [(hm16, 0, 256)], B, h, w, y=mk, ldy=576, scale=0.25)
+            self._add(L.bflow_cvx_upsample, hx + poff * 4, gw, 0, mk, 576, 0, out_t.data_ptr(), B, 2 * deg, h, w)
+
+        self.pre = {k: torch.empty(R, (2 * hd if k.startswith('zr') else hd), **f32) for k in ('zr1', 'q1', 'zr2', 'q2')}
+        pre = {k: v.data_ptr() for k, v in self.pre.items()}
+        for k in ('zr1', 'q1', 'zr2', 'q2'):
+            self._conv3(U[k + '_inp'], [(hx16, hd, cd)], B, h, w, y=pre[k], ldy=self.pre[k].shape[1])
+
+        self.iter_start = len(self.launches)
+        for itr in range(self.iters):
+            if itr == 1:
+                self.iter_len = len(self.launches) - self.iter_start
+            self._add(L.bflow_corr_lookup, C.byref(ld))
+            # motion encoder (update.py:88-97)
+            self._conv3(U['convc1'], [(self.corr16, 0, eng.ldc)], B, h, w, y16=(c1_16, 0), act1='relu')
+            self._conv3(U['convc2'], [(c1_16, 0, 256)], B, h, w, y16=(cb16, 0), act1='relu')
+            self._conv_simt16(U['convf1'], hx + poff * 4, 2 * deg, gw, B, h, w, y16=(f1_16, 0), act1='relu')
+            self._conv3(U['convf2'], [(f1_16, 0, 128)], B, h, w, y16=(cb16, 192), act1='relu')
+            self._conv3(U['conv'], [(cb16, 0, 256)], B, h, w, y16=(hx16, hd + cd), act1='relu')
+            # SepConvGRU (update.py:33-48) with the iteration-invariant inp part hoisted and the gate arithmetic in the epilogues
+            for sfx in '12':
+                self._conv3(U['zr' + sfx + '_dyn'], [(hx16, 0, hd), (hx16, hd + cd, md)], B, h, w, y=zr, ldy=2 * hd, bias=False,
+                            res=pre['zr' + sfx], ldr=2 * hd, epi='gru_zr', aux0=hx, ld_aux0=gw, aux1_16=(rh16, 0))
+                self._conv3(U['q' + sfx + '_dyn'], [(rh16, 0, hd), (hx16, hd + cd, md)], B, h, w, y=hx, ldy=gw, y16=(hx16, 0), bias=False,
+                            res=pre['q' + sfx], ldr=hd, epi='gru_q', aux0=zr, ld_aux0=2 * hd)
+            # Bezier head + delta update in place (update.py:17-18, bezier.py:137-139): fp32 master and split copy
+            self._conv3(U['head1'], [(hx16, 0, hd)], B, h, w, y=hh, ldy=256, act1='relu')
+            self._conv_simt16(U['head2'], hh, 256, 256, B, h, w, y=hx + poff * 4, ldy=gw, y16=(hx16, poff), res=hx + poff * 4, ldr=gw,
+                              kernel='small_n' if 2 * deg <= 32 else 'auto')
+            if not self.test_mode:
+                upsample(self.ups[itr])
+        if self.iters == 1:
+            self.iter_len = len(self.launches) - self.iter_start
+        if self.test_mode:
+            upsample(self.ups[0])
+        self._add(L.bflow_nhwc_to_nchw, hx + poff * 4, self.low.data_ptr(), B, 2 * deg, h, w, gw)
+        self.n_launches = len(self.launches)

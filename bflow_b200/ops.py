@@ -60,7 +60,8 @@ def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None) -> Tuple[to
     return p.reshape(KH * KW * ci, ldw).contiguous(), ldw
 
 
-def pack_conv_weight_tc(w: torch.Tensor, bn: int, cin_pad: Optional[int] = None, prescale: bool = True) -> Tuple[torch.Tensor, float]:
+def pack_conv_weight_tc(w: torch.Tensor, bn: int, cin_pad: Optional[int] = None, prescale: bool = True,
+                        block_per_tap: bool = False, c0: Optional[int] = None) -> Tuple[torch.Tensor, float]:
     """OIHW fp32 → (tensor-core weight image of bflow_conv2d_nhwc_tc, acc_scale).
     Image: [ceil(O/bn)][ceil(K/64)][hi | lo (fp16)][bn][64] with K = (kh*KW+kw)*Cin + c flattened and the 16-byte
     chunks of every 128-byte row XOR-swizzled by (row % 8) — byte for byte the SWIZZLE_128B shared-memory tile.
@@ -68,9 +69,24 @@ def pack_conv_weight_tc(w: torch.Tensor, bn: int, cin_pad: Optional[int] = None,
     acc_scale = 2^-k is applied to the fp32 accumulator (exact)."""
     O, I, KH, KW = w.shape
     ci = I if cin_pad is None else cin_pad
+    w = w.detach().float()
+    if block_per_tap:
+        # K order of the TMA-fed kernel: (tap, 64-channel block); each of the (up to two) concatenated sources is padded to a
+        # multiple of 64 channels on its own
+        c0 = ci if c0 is None else c0
+        c1 = ci - c0
+        p0, p1 = (c0 + 63) // 64 * 64, (c1 + 63) // 64 * 64
+        wp = torch.zeros(O, KH, KW, p0 + p1, device=w.device, dtype=torch.float32)
+        wsrc = torch.zeros(O, KH, KW, ci, device=w.device, dtype=torch.float32)
+        wsrc[..., :I] = w.permute(0, 2, 3, 1)
+        wp[..., :c0] = wsrc[..., :c0]
+        if c1 > 0:
+            wp[..., p0:p0 + c1] = wsrc[..., c0:]
+        w = wp.permute(0, 3, 1, 2).contiguous()
+        O, I, KH, KW = w.shape
+        ci = I
     K = KH * KW * ci
     nkb, nt = (K + 63) // 64, (O + bn - 1) // bn
-    w = w.detach().float()
     k = 0
     amax = float(w.abs().max())
     if prescale and amax > 0:
@@ -90,6 +106,28 @@ def pack_conv_weight_tc(w: torch.Tensor, bn: int, cin_pad: Optional[int] = None,
         return torch.gather(x, 3, idx)
     img = torch.stack([tile(hi), tile(lo)], dim=2).contiguous()                    # tile, k-block, hi|lo, row, chunk, element
     return img.view(-1), 2.0 ** (-k)
+
+
+def split_f16(x_nhwc: torch.Tensor, ld16: Optional[int] = None) -> torch.Tensor:
+    """(..., C) fp32 rows → (2, rows, ld16) fp16 planes [hi, lo] with x = hi + lo."""
+    x = _f32c(x_nhwc, 'x')
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    ld16 = Cc if ld16 is None else ld16
+    out = torch.zeros(2, rows, ld16, device=x.device, dtype=torch.float16)
+    check(_lib.lib().bflow_split_f16(x.data_ptr(), Cc, out[0].data_ptr(), out[1].data_ptr(), ld16, rows, Cc, _stream()), 'split_f16')
+    return out
+
+
+def tma_im2col_maps(planes: torch.Tensor, N: int, H: int, W: int, Cc: int, KH: int, KW: int, stride: int, ph: int, pw: int,
+                    c_off: int = 0):
+    """Host buffer with the {hi, lo} im2col tensor maps of a split-fp16 activation (2, N*H*W, ld16), channels [c_off, c_off+C)."""
+    ld16 = planes.shape[-1]
+    buf = (C.c_uint8 * 256)()
+    for i in range(2):
+        base = planes[i].data_ptr() + c_off * 2
+        check(_lib.lib().bflow_tma_im2col_map(C.addressof(buf) + 128 * i, base, N, H, W, Cc, ld16, KH, KW, stride, ph, pw), 'tma_im2col_map')
+    return buf
 
 
 def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, stride: int = 1,
@@ -115,7 +153,18 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     d.N, d.H, d.W, d.Ho, d.Wo, d.Cout = N, H, W, Ho, Wo, O
     d.KH, d.KW, d.stride, d.pad_h, d.pad_w = KH, KW, stride, ph, pw
     d.act1, d.act2, d.scale = ACT[act], 0, scale
-    if backend == 'tc':
+    if backend == 'tc3':
+        x16 = split_f16(xh, (Cin + 7) // 8 * 8)
+        m = tma_im2col_maps(x16, N, H, W, Cin, KH, KW, stride, ph, pw)
+        maps = (C.c_uint8 * 512)()
+        C.memmove(maps, m, 256)
+        wtc, acc_scale = pack_conv_weight_tc(weight, bn, block_per_tap=True)
+        err = torch.zeros(1, device=x.device, dtype=torch.int32)
+        d.x0 = None
+        check(_lib.lib().bflow_conv2d_nhwc_tc3(C.byref(d), C.addressof(maps), wtc.data_ptr(), bn, acc_scale, err.data_ptr(), _stream()), 'conv2d_tc3')
+        if int(err.item()) != 0:
+            raise RuntimeError('bflow_conv2d_nhwc_tc3: pipeline wait timed out inside the kernel')
+    elif backend == 'tc':
         wtc, acc_scale = pack_conv_weight_tc(weight, bn)
         err = torch.zeros(1, device=x.device, dtype=torch.int32)
         check(_lib.lib().bflow_conv2d_nhwc_tc(C.byref(d), wtc.data_ptr(), bn, acc_scale, err.data_ptr(), _stream()), 'conv2d_tc')

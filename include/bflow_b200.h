@@ -83,6 +83,12 @@ typedef struct bflow_conv_desc {
     int epi;
     const float* aux0; int ld_aux0;
     float* aux1; int ld_aux1;
+    /* split-fp16 twins (x = hi + lo, two fp16 planes with pixel stride in halves): what the TMA-fed tensor-core kernel
+     * (bflow_conv2d_nhwc_tc3) reads.  Every kernel that produces a convolution input can emit them next to, or instead of
+     * (y == NULL), the fp32 tensor; res16 lets a residual be read from a split tensor; aux1_16 is the split form of aux1. */
+    void* y16_hi; void* y16_lo; int ldy16;
+    const void* res16_hi; const void* res16_lo; int ldr16;
+    void* aux1_16_hi; void* aux1_16_lo; int ld_aux1_16;
 } bflow_conv_desc;
 int bflow_conv2d_nhwc(const bflow_conv_desc* d, void* stream);
 
@@ -97,6 +103,19 @@ int bflow_conv2d_nhwc(const bflow_conv_desc* d, void* stream);
  * (bflow_conv2d_tc_supported returns 1).  bn in {64,128,256}.  `err`: optional device int, set to 1 if an
  * in-kernel pipeline wait timed out (never expected; the waits are bounded so that a bug cannot hang the GPU). */
 int bflow_conv2d_tc_supported(const bflow_conv_desc* d);
+/* TMA-fed, persistent form of the tensor-core convolution.  Activations are read as split-fp16 planes (hi, lo) through
+ * im2col tensor maps (cp.async.bulk.tensor.4d...im2col: the TMA unit does the implicit-GEMM gather and the zero padding),
+ * weights as in bflow_conv2d_nhwc_tc but with K ordered (tap, 64-channel block) — pack_conv_weight_tc(block_per_tap=True).
+ * One CTA per SM loops over 128 x bn tiles; TMEM holds two accumulators so the epilogue of a tile overlaps the MMAs of the
+ * next.  Warp roles: TMA producer / MMA issuer / 4 epilogue warps.  d->x0/x1 are ignored (c0/c1 and the geometry are used).
+ * maps: host array of four 128-byte tensor maps {source0 hi, source0 lo, source1 hi, source1 lo} from bflow_tma_im2col_map
+ * (source1 entries unused when c1 == 0).  Needs c0 % 8 == 0, c1 % 8 == 0, (c1 == 0 or c0 % 64 == 0). */
+int bflow_tma_im2col_map(void* map_out_128B, const void* base_fp16, int N, int H, int W, int C, int ld_halves,
+                         int KH, int KW, int stride, int pad_h, int pad_w);
+int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* d, const void* maps, const void* w_tc, int bn, float acc_scale, int* err, void* stream);
+/* fp32 NHWC rows -> split-fp16 planes (x = hi + lo): operand staging for tensors produced outside this library */
+int bflow_split_f16(const float* src, int ld, void* hi, void* lo, int ld16, long long rows, int C, void* stream);
+
 /* Packs NHWC fp32 rows (rows x K at stride ld) into the tensor-core B-operand image above (rows play the role of
  * output channels): used for the correlation volume, whose "weights" are the target feature map.  dst must be
  * zero-initialised once (rows beyond `rows` in the last tile stay zero).  Row r of the source lands at image row
@@ -124,6 +143,13 @@ int bflow_plane_sums(const float* x, int ld, double* sums, int N, int HW, int C,
 int bflow_instnorm_relu(const float* a, int lda, const double* sums_a,
                         const float* r, int ldr, const double* sums_r,
                         float* out, int ldo, int N, int HW, int C, float eps, void* stream);
+/* split-fp16 form: the residual may come from a split tensor (r16_hi/lo, identity skip of an encoder block whose input is
+ * stored split) and the result may be written as fp32 (out, may be NULL) and/or split planes (out16_hi/lo, may be NULL). */
+int bflow_instnorm_relu16(const float* a, int lda, const double* sums_a,
+                          const float* r, int ldr, const double* sums_r,
+                          const void* r16_hi, const void* r16_lo, int ldr16,
+                          float* out, int ldo, void* out16_hi, void* out16_lo, int ldo16,
+                          int N, int HW, int C, float eps, void* stream);
 int bflow_zero(void* ptr, unsigned long long bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -159,6 +185,8 @@ typedef struct bflow_lookup_desc {
     float* out;
     int out_nhwc;                          /* 0: (B, S*81, h, w) like the reference; 1: rows (B*Q) x out_ld */
     int out_ld;
+    void* out16_hi; void* out16_lo;        /* when non-NULL (NHWC only): write split-fp16 planes (x = hi + lo) instead of `out`, */
+    int out16_ld;                          /* row stride in halves — the form the TMA-fed convolution reads */
     int tiled;                             /* 0: planes row-major (hl x wl) like the reference; 1: planes stored as 4x4-pixel
                                               tiles (64-byte DRAM granules), ceil(hl/4) x ceil(wl/4) tiles of 16 floats, zero padded */
 } bflow_lookup_desc;

@@ -18,6 +18,8 @@ def main():
     for k, v in dict(n=1, cin=384, h=60, w=80, cout=128, kh=1, kw=5, stride=1, bn=64, reps=10).items():
         ap.add_argument('--' + k, type=int, default=v)
     ap.add_argument('--backend', default='tc')
+    ap.add_argument('--dbg', type=int, default=0)
+    ap.add_argument('--trace', action='store_true')
     a = ap.parse_args()
     dev = torch.device('cuda:0')
     lib = _lib.lib()
@@ -30,6 +32,11 @@ def main():
     wp, ldw = ops.pack_conv_weight(w)
     wtc, acc_scale = ops.pack_conv_weight_tc(w, a.bn)
     err = torch.zeros(1, device=dev, dtype=torch.int32)
+    x16 = ops.split_f16(x, (a.cin + 7) // 8 * 8)
+    m = ops.tma_im2col_maps(x16, a.n, a.h, a.w, a.cin, a.kh, a.kw, a.stride, ph, pw)
+    maps = (C.c_uint8 * 512)()
+    C.memmove(maps, m, 256)
+    wtc3, acc3 = ops.pack_conv_weight_tc(w, a.bn, block_per_tap=True)
     d = ConvDesc()
     d.x0, d.c0, d.ld0 = x.data_ptr(), a.cin, a.cin
     d.x1, d.c1, d.ld1 = None, 0, 0
@@ -40,9 +47,12 @@ def main():
     d.KH, d.KW, d.stride, d.pad_h, d.pad_w = a.kh, a.kw, a.stride, ph, pw
     d.act1, d.act2, d.scale = 1, 0, 1.0
     st = torch.cuda.current_stream().cuda_stream
+    C.CDLL(_lib._build.LIB).bflow_tc3_debug(a.dbg)
 
     def run():
-        if a.backend == 'tc':
+        if a.backend == 'tc3':
+            _lib.check(lib.bflow_conv2d_nhwc_tc3(C.byref(d), C.addressof(maps), wtc3.data_ptr(), a.bn, acc3, err.data_ptr(), st), 'tc3')
+        elif a.backend == 'tc':
             _lib.check(lib.bflow_conv2d_nhwc_tc(C.byref(d), wtc.data_ptr(), a.bn, acc_scale, err.data_ptr(), st), 'tc')
         else:
             _lib.check(lib.bflow_conv2d_nhwc(C.byref(d), st), 'simt')
@@ -55,8 +65,21 @@ def main():
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     t = statistics.median(ts)
+    if a.trace:
+        tr = torch.zeros(6, 256, device=dev, dtype=torch.int64)
+        L = C.CDLL(_lib._build.LIB)
+        L.bflow_tc3_trace.argtypes = [C.c_void_p]
+        L.bflow_tc3_trace(tr.data_ptr())
+        run(); torch.cuda.synchronize()
+        L.bflow_tc3_trace(None)
+        tr = tr.cpu()
+        t0 = int(tr[tr > 0].min())
+        names = ['prod:empty-ok', 'mma:full-ok', 'mma:committed', 'epi:tfull-ok', 'epi:tmem-released', 'epi:tile-done']
+        for r in range(6):
+            vals = [int(v) - t0 for v in tr[r] if int(v) > 0][:40]
+            print(f'{names[r]:18s}', vals)
     fl = 2.0 * a.n * Ho * Wo * a.cout * a.kh * a.kw * a.cin
-    print(f'{a.backend} bn={a.bn} {a.cin}->{a.cout} {a.kh}x{a.kw}/{a.stride} M={a.n * Ho * Wo}: {t * 1e3:.1f} us  {fl / (t * 1e-3) / 1e12:.1f} TF/s useful; err flag {int(err.item())}')
+    print(f'{a.backend} bn={a.bn} {a.cin}->{a.cout} {a.kh}x{a.kw}/{a.stride} M={a.n * Ho * Wo}: {t * 1e3:.1f} us  {fl / (t * 1e-3) / 1e12:.1f} TF/s useful; err flag {int(err.item())} dbg {a.dbg}')
 
 
 if __name__ == '__main__':

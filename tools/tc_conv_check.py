@@ -27,6 +27,7 @@ CASES = [
 
 
 def main():
+    backend = sys.argv[1] if len(sys.argv) > 1 else 'tc'
     torch.manual_seed(0)
     worst = 0.0
     for (N, Cin, H, W, Cout, k, s, p, bn) in CASES:
@@ -35,7 +36,7 @@ def main():
         b = torch.randn(Cout)
         ref = F.conv2d(x.double(), w.double(), b.double(), stride=s, padding=p).float()
         try:
-            tc = ops.conv2d(x.to(DEV), w.to(DEV), b.to(DEV), stride=s, padding=p, backend='tc', bn=bn).cpu()
+            tc = ops.conv2d(x.to(DEV), w.to(DEV), b.to(DEV), stride=s, padding=p, backend=backend, bn=bn).cpu()
         except Exception as e:   # noqa: BLE001
             print(f'case {(N, Cin, H, W, Cout, k, s, p, bn)}: EXCEPTION {e}')
             worst = float('inf')
