@@ -62,6 +62,7 @@ class Engine:
         # TMA-fed persistent tensor-core kernel on split-fp16 activations (0: register-staged tcgen05 kernel on fp32 activations)
         self.use_tc3 = self.use_tc and os.environ.get('BFLOW_TC3', '1') != '0'
         self.err = torch.zeros(1, device=device, dtype=torch.int32)
+        self.use_side_stream = os.environ.get('BFLOW_STREAMS', '1') != '0'
         self._plans: Dict[tuple, '_Plan'] = {}
         self._pack(model)
 
@@ -181,6 +182,9 @@ class _Plan(S16Recorder):
         self.Q = self.h * self.w
         self.R = B * self.Q
         self.launches: List[Tuple] = []
+        self.schedule: List[Tuple] = []          # ('launch', index, stream) | ('fork',) | ('join',)
+        self._cur_stream = 0
+        self.side_stream = None
         self.labels: List[Tuple[str, float]] = []
         self.keep: List = []           # descriptors / tensors referenced by raw pointer
         self.graph = None
@@ -205,8 +209,22 @@ class _Plan(S16Recorder):
 
     # ---- recording helpers -------------------------------------------------------------------------------
     def _add(self, fn, *args, label: Optional[str] = None, flops: float = 0.0):
+        self.schedule.append(('launch', len(self.launches), self._cur_stream))
         self.launches.append((fn, args))
         self.labels.append((label or fn.__name__.replace('bflow_', ''), flops))
+
+    # independent branches of the forward pass run on a second stream (graph branches): every convolution of the update block
+    # at batch 1 fills at most half of the SMs, so two of them side by side cost little more than one
+    def _fork(self):
+        self.schedule.append(('fork',))
+        self._cur_stream = 1
+
+    def _main(self):
+        self._cur_stream = 0
+
+    def _join(self):
+        self.schedule.append(('join',))
+        self._cur_stream = 0
 
     def _conv(self, wt, x0, c0, ld0, N, H, W, y, ldy, act1='none', act2='none', res=None, ldr=0,
               x1=None, c1=0, ld1=0, scale=1.0, bias=True, epi='std', aux0=None, ld_aux0=0, aux1=None, ld_aux1=0, kernel='auto'):
@@ -507,12 +525,24 @@ class _Plan(S16Recorder):
             self.init_in.zero_()
             self._init_dirty = False
 
-    def launch_all(self, lo: int = 0, hi: Optional[int] = None):
-        s = torch.cuda.current_stream().cuda_stream
-        for fn, args in self.launches[lo:hi]:
-            rc = fn(*args, s)
-            if rc != 0:
-                check(rc, fn.__name__)
+    def launch_all(self):
+        main = torch.cuda.current_stream()
+        if self.side_stream is None:
+            self.side_stream = torch.cuda.Stream(device=self.eng.device)
+        side = self.side_stream
+        handles = (main.cuda_stream, side.cuda_stream)
+        use_side = self.eng.use_side_stream
+        for item in self.schedule:
+            if item[0] == 'launch':
+                fn, args = self.launches[item[1]]
+                rc = fn(*args, handles[item[2] if use_side else 0])
+                if rc != 0:
+                    check(rc, fn.__name__)
+            elif use_side:
+                if item[0] == 'fork':
+                    side.wait_stream(main)
+                else:
+                    main.wait_stream(side)
 
     def check(self):
         """Synchronises and raises if a tensor-core pipeline wait timed out (never expected)."""

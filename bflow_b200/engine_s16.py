@@ -227,6 +227,9 @@ class S16Recorder:
         pool_bytes = np_max * (H // 2) * (W // 2) * 64 * 4
         self.pool = [torch.empty(pool_bytes, device=dev, dtype=torch.uint8) for _ in range(5)]
         pool = [t.data_ptr() for t in self.pool]
+        # the context encoder runs beside the feature encoder on the second stream and needs its own scratch
+        self.pool_c = [torch.empty(B * (H // 2) * (W // 2) * 64 * 4, device=dev, dtype=torch.uint8) for _ in range(5)]
+        pool_c = [t.data_ptr() for t in self.pool_c]
         self.sums = torch.zeros(64 * np_max * 128 * 2, device=dev, dtype=torch.float64)
         self._sums_off = 0
         self._add(L.bflow_zero, self.sums.data_ptr(), self.sums.numel() * 8)
@@ -249,6 +252,33 @@ class S16Recorder:
             for i in range(2):
                 self._add(L.bflow_nchw_to_nhwc, self.img_in[i].data_ptr(), self.imgs.data_ptr() + i * B * H * W * 3 * 4, B, 3, H, W, 0, 3, 3, 2.0 / 255.0, -1.0)
 
+        # ---- context encoder on the second stream: net = tanh -> h (fp32 master + split copy), inp = relu -> split only
+        #      (raft.py:144-147); then the iteration-invariant GRU terms conv(inp) + bias ----
+        U = eng.upd
+        self._fork()
+        if self.use_ev and self.use_img:
+            self._add(L.bflow_nchw_to_nhwc, self.voxel_in.data_ptr(), self.ctx.data_ptr(), B, self.cin_vox, H, W, self.cin_vox - nctx, nctx, ctx_c, 1.0, 0.0)
+            self._add(L.bflow_nchw_to_nhwc, self.img_in[0].data_ptr(), self.ctx.data_ptr() + nctx * 4, B, 3, H, W, 0, 3, ctx_c, 2.0 / 255.0, -1.0)
+            cwin = [(self.ctx.data_ptr(), ctx_c, ctx_c, B)]
+        elif self.use_ev:
+            cwin = [(self.vox.data_ptr() + (self.cin_vox - nctx) * 4, nctx, self.cin_vox, B)]
+        else:
+            cwin = [(self.imgs.data_ptr(), 3, 3, B)]
+        Ec = eng.enc['cnet']
+
+        def cnet_final(X, n_, Hc, Wc, Cc):
+            self._conv3(Ec['conv2'][0], [(X, 0, Cc)], n_, Hc, Wc, y=hx, ldy=gw, y16=(hx16, 0), act1='tanh')
+            self._conv3(Ec['conv2'][1], [(X, 0, Cc)], n_, Hc, Wc, y16=(hx16, hd), act1='relu')
+        self._encoder16(Ec, cwin, B, H, W, pool_c, cnet_final)
+        self.pre = {k: torch.empty(R, (2 * hd if k.startswith('zr') else hd), **f32) for k in ('zr1', 'q1', 'zr2', 'q2')}
+        pre = {k: v.data_ptr() for k, v in self.pre.items()}
+        for k in ('zr1', 'q1', 'zr2', 'q2'):
+            self._conv3(U[k + '_inp'], [(hx16, hd, cd)], B, h, w, y=pre[k], ldy=self.pre[k].shape[1])
+        # initial Bezier parameters: zeros (+ flow_init) (raft.py:150-153): fp32 master + split copy
+        self._add(L.bflow_nchw_to_nhwc, self.init_in.data_ptr(), hx + poff * 4, B, 2 * deg, h, w, 0, 2 * deg, gw, 1.0, 0.0)
+        self._add(L.bflow_split_f16, hx + poff * 4, gw, hx16.hi(poff), hx16.lo(poff), gw, R, 2 * deg)
+        self._main()
+
         # ---- feature encoders: fp32 feature map for the volume GEMM's B operand, split copy for its A operand ----
         def fnet(name, windows, Np):
             fm = torch.empty(Np, h, w, fd, **f32)
@@ -264,26 +294,6 @@ class S16Recorder:
         if self.use_img:
             fm_img, fm_img16 = fnet('fnet_img', [(self.imgs.data_ptr(), 3, 3, 2 * B)], 2 * B)
         self.fm_ev, self.fm_img, self.fm_ev16, self.fm_img16 = fm_ev, fm_img, fm_ev16, fm_img16
-
-        # ---- context encoder: net = tanh -> h (fp32 master + split copy), inp = relu -> split only (raft.py:144-147) ----
-        if self.use_ev and self.use_img:
-            self._add(L.bflow_nchw_to_nhwc, self.voxel_in.data_ptr(), self.ctx.data_ptr(), B, self.cin_vox, H, W, self.cin_vox - nctx, nctx, ctx_c, 1.0, 0.0)
-            self._add(L.bflow_nchw_to_nhwc, self.img_in[0].data_ptr(), self.ctx.data_ptr() + nctx * 4, B, 3, H, W, 0, 3, ctx_c, 2.0 / 255.0, -1.0)
-            cwin = [(self.ctx.data_ptr(), ctx_c, ctx_c, B)]
-        elif self.use_ev:
-            cwin = [(self.vox.data_ptr() + (self.cin_vox - nctx) * 4, nctx, self.cin_vox, B)]
-        else:
-            cwin = [(self.imgs.data_ptr(), 3, 3, B)]
-        Ec = eng.enc['cnet']
-
-        def cnet_final(X, n_, Hc, Wc, Cc):
-            self._conv3(Ec['conv2'][0], [(X, 0, Cc)], n_, Hc, Wc, y=hx, ldy=gw, y16=(hx16, 0), act1='tanh')
-            self._conv3(Ec['conv2'][1], [(X, 0, Cc)], n_, Hc, Wc, y16=(hx16, hd), act1='relu')
-        self._encoder16(Ec, cwin, B, H, W, pool, cnet_final)
-
-        # ---- initial Bezier parameters: zeros (+ flow_init) (raft.py:150-153): fp32 master + split copy ----
-        self._add(L.bflow_nchw_to_nhwc, self.init_in.data_ptr(), hx + poff * 4, B, 2 * deg, h, w, 0, 2 * deg, gw, 1.0, 0.0)
-        self._add(L.bflow_split_f16, hx + poff * 4, gw, hx16.hi(poff), hx16.lo(poff), gw, R, 2 * deg)
 
         # ---- correlation volume (tensor-core GEMM, granule-tiled planes) + pyramid (corr.py:264-272, 293-305) ----
         self.tiled = True
@@ -337,8 +347,9 @@ class S16Recorder:
         self.keep.append(ld)
         self.lookup_desc = ld
 
+        self._join()                                        # context branch done
+
         # ---- update-block workspace ----
-        U = eng.upd
         self.c1_16 = _S16(R, 256, dev)
         self.cb16 = _S16(R, 256, dev)
         self.f1_16 = _S16(R, 128, dev)
@@ -355,21 +366,19 @@ class S16Recorder:
             self._conv3(U['mask2'], [(hm16, 0, 256)], B, h, w, y=mk, ldy=576, scale=0.25)
             self._add(L.bflow_cvx_upsample, hx + poff * 4, gw, 0, mk, 576, 0, out_t.data_ptr(), B, 2 * deg, h, w)
 
-        self.pre = {k: torch.empty(R, (2 * hd if k.startswith('zr') else hd), **f32) for k in ('zr1', 'q1', 'zr2', 'q2')}
-        pre = {k: v.data_ptr() for k, v in self.pre.items()}
-        for k in ('zr1', 'q1', 'zr2', 'q2'):
-            self._conv3(U[k + '_inp'], [(hx16, hd, cd)], B, h, w, y=pre[k], ldy=self.pre[k].shape[1])
-
         self.iter_start = len(self.launches)
         for itr in range(self.iters):
             if itr == 1:
                 self.iter_len = len(self.launches) - self.iter_start
-            self._add(L.bflow_corr_lookup, C.byref(ld))
-            # motion encoder (update.py:88-97)
-            self._conv3(U['convc1'], [(self.corr16, 0, eng.ldc)], B, h, w, y16=(c1_16, 0), act1='relu')
-            self._conv3(U['convc2'], [(c1_16, 0, 256)], B, h, w, y16=(cb16, 0), act1='relu')
+            # motion encoder (update.py:88-97): the Bezier branch (convf1 -> convf2) runs beside lookup -> convc1 -> convc2
+            self._fork()
             self._conv_simt16(U['convf1'], hx + poff * 4, 2 * deg, gw, B, h, w, y16=(f1_16, 0), act1='relu')
             self._conv3(U['convf2'], [(f1_16, 0, 128)], B, h, w, y16=(cb16, 192), act1='relu')
+            self._main()
+            self._add(L.bflow_corr_lookup, C.byref(ld))
+            self._conv3(U['convc1'], [(self.corr16, 0, eng.ldc)], B, h, w, y16=(c1_16, 0), act1='relu')
+            self._conv3(U['convc2'], [(c1_16, 0, 256)], B, h, w, y16=(cb16, 0), act1='relu')
+            self._join()
             self._conv3(U['conv'], [(cb16, 0, 256)], B, h, w, y16=(hx16, hd + cd), act1='relu')
             # SepConvGRU (update.py:33-48) with the iteration-invariant inp part hoisted and the gate arithmetic in the epilogues
             for sfx in '12':
