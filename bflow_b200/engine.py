@@ -98,6 +98,14 @@ class Engine:
         bn = kind == 'batch'
         f = (lambda c, n: self._mk_folded(c, n)) if bn else (lambda c, n: self._mk(c))
         out = {'kind': kind, 'conv1': f(enc.conv1, enc.norm1 if bn else None), 'blocks': []}
+        w1 = out['conv1']
+        O, I, KH, KW = w1.oihw.shape
+        if KH * KW * I <= 512:      # stem as a GEMM over the materialised patch matrix (engine_s16: 'im2col' stem)
+            kp = _ceil(KH * KW * I, 64)
+            wm = torch.zeros(O, kp, 1, 1, device=self.device, dtype=torch.float32)
+            wm[:, :KH * KW * I, 0, 0] = w1.oihw.permute(0, 2, 3, 1).reshape(O, -1)
+            wp, ldw = pack_conv_weight(wm)
+            out['conv1_mat'] = _Weight(wp, ldw, w1.b, O, kp, 1, 1, 1, (0, 0), wm, None)
         for layer in (enc.layer1, enc.layer2, enc.layer3):
             for blk in layer:
                 e = {'conv1': f(blk.conv1, blk.norm1 if bn else None), 'conv2': f(blk.conv2, blk.norm2 if bn else None), 'down': None}

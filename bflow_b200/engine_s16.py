@@ -124,6 +124,36 @@ class S16Recorder:
                   flops=2.0 * N * Ho * Wo * wt.cout * wt.kh * wt.kw * c0)
         return Ho, Wo
 
+    def _stem_window(self, src_nchw: torch.Tensor, C_total: int, c_off: int, cin: int, ns: int, H: int, W: int, scale: float = 1.0,
+                     shift: float = 0.0, shared: Optional[dict] = None) -> dict:
+        """How one input window (channels [c_off, c_off+cin) of an NCHW fp32 input) reaches the 7x7 stem."""
+        from .engine import _ceil
+        L, dev = self.eng.lib, self.eng.device
+        shared = {} if shared is None else shared
+        if 49 * cin <= 512:
+            if 'buf' not in shared:      # one patch-matrix buffer per encoder call, reused window after window (same stream)
+                shared['buf'] = _S16(ns * (H // 2) * (W // 2), _ceil(49 * cin, 64), dev)
+                self.keep.append(shared['buf'])
+            return dict(kind='im2col', src=src_nchw.data_ptr(), C_total=C_total, c_off=c_off, cin=cin, ns=ns, scale=scale, shift=shift, buf=shared['buf'])
+        if c_off % 8 == 0 and cin >= 16:
+            key = ('x16', src_nchw.data_ptr())
+            if key not in shared:        # NCHW fp32 -> NHWC fp32 -> split planes, once per source tensor
+                ld = _ceil(C_total, 8)
+                x32 = torch.zeros(ns, H, W, ld, device=dev, dtype=torch.float32)
+                x16 = _S16(ns * H * W, ld, dev)
+                self._add(L.bflow_nchw_to_nhwc, src_nchw.data_ptr(), x32.data_ptr(), ns, C_total, H, W, 0, C_total, ld, scale, shift)
+                self._add(L.bflow_split_f16, x32.data_ptr(), ld, x16.hi(), x16.lo(), ld, ns * H * W, ld)
+                self.keep += [x32, x16]
+                shared[key] = x16
+            return dict(kind='tma', x16=shared[key], c_off=c_off, cin=cin, ns=ns)
+        key = ('x32', src_nchw.data_ptr())
+        if key not in shared:
+            x32 = torch.zeros(ns, H, W, C_total, device=dev, dtype=torch.float32)
+            self._add(L.bflow_nchw_to_nhwc, src_nchw.data_ptr(), x32.data_ptr(), ns, C_total, H, W, 0, C_total, C_total, scale, shift)
+            shared[key] = x32
+            self.keep.append(x32)
+        return dict(kind='simt', ptr=shared[key].data_ptr() + 4 * c_off, cin=cin, ld=C_total, ns=ns)
+
     # ---- encoders (models/raft_utils/extractor.py:47-55,103-125) ---------------------------------------------------------
     def _encoder16(self, E: dict, windows, Np: int, H: int, W: int, pool: List[int], final):
         """pool: device pointers of >= 5 scratch regions of Np*(H/2)*(W/2)*64*4 bytes; each holds either a raw fp32 conv output or a
@@ -139,13 +169,28 @@ class S16Recorder:
         H2, W2 = H // 2, W // 2
         rows = Np * H2 * W2
         w1 = E['conv1']
-        # stem: 7x7 stride-2 conv on the fp32 NHWC input, one launch per window
+        # stem: 7x7 stride-2 conv (extractor.py:112), one launch group per input window.  Three forms:
+        #   'im2col'  few input channels (K = 49*cin <= 512): patch matrix in split-fp16 + 1x1 tensor-core GEMM
+        #   'tma'     cin >= 16 at an 8-aligned channel offset of a split-fp16 NHWC input: 7x7 im2col-TMA convolution
+        #   'simt'    fp32 NHWC input on CUDA cores
+        def stem(win, n0, ns, y=None, y16=None, act='none'):
+            if win['kind'] == 'im2col':
+                wm = E['conv1_mat']
+                buf = win['buf']
+                self._add(L.bflow_im2col_split16, win['src'], win['C_total'], win['c_off'], win['cin'], ns, H, W, 7, 7, 2, 3, 3, win.get('scale', 1.0),
+                          win.get('shift', 0.0), buf.hi(), buf.lo(), buf.ld)
+                self._conv3(wm, [(buf, 0, wm.cin)], 1, 1, ns * H2 * W2, y=y, ldy=64, y16=y16, act1=act)
+            elif win['kind'] == 'tma':
+                self._conv3(w1, [(win['x16'], win['c_off'], win['cin'])], ns, H, W, y=y, ldy=64, y16=y16, act1=act)
+            else:
+                self._conv_simt16(w1, win['ptr'], win['cin'], win['ld'], ns, H, W, y=y, ldy=64, y16=y16, act1=act)
+
         if inorm:
             raw = free.pop()
             n0 = 0
-            for ptr, cin, ld, ns in windows:
-                self._conv_simt16(w1, ptr, cin, ld, ns, H, W, y=raw + n0 * H2 * W2 * 64 * 4, ldy=64)
-                n0 += ns
+            for win in windows:
+                stem(win, n0, win['ns'], y=raw + n0 * H2 * W2 * 64 * 4)
+                n0 += win['ns']
             xptr = free.pop()
             X = s16(xptr, rows, 64)
             sm = self._sums(Np, 64)
@@ -156,9 +201,9 @@ class S16Recorder:
             xptr = free.pop()
             X = s16(xptr, rows, 64)
             n0 = 0
-            for ptr, cin, ld, ns in windows:
-                self._conv_simt16(w1, ptr, cin, ld, ns, H, W, y16=(X.rows_from(n0 * H2 * W2, ns * H2 * W2), 0), act1='relu')
-                n0 += ns
+            for win in windows:
+                stem(win, n0, win['ns'], y16=(X.rows_from(n0 * H2 * W2, win['ns'] * H2 * W2), 0), act='relu')
+                n0 += win['ns']
         Hc, Wc, Cc = H2, W2, 64
         for blk in E['blocks']:
             c1, c2, dn = blk['conv1'], blk['conv2'], blk['down']
@@ -241,29 +286,24 @@ class S16Recorder:
         self.poff, self.gw = poff, gw
         hx, hx16 = self.hx.data_ptr(), self.hx16
 
-        # ---- inputs to NHWC fp32 (the 7x7 stems run on CUDA cores) ----
-        ctx_c = (nctx if self.use_ev else 0) + (3 if self.use_img else 0)
-        self.ctx = torch.zeros(B, H, W, ctx_c, **f32)
-        if self.use_ev:
-            self.vox = torch.zeros(B, H, W, self.cin_vox, **f32)
-            self._add(L.bflow_nchw_to_nhwc, self.voxel_in.data_ptr(), self.vox.data_ptr(), B, self.cin_vox, H, W, 0, self.cin_vox, self.cin_vox, 1.0, 0.0)
-        if self.use_img:
-            self.imgs = torch.zeros(2 * B, H, W, 3, **f32)
-            for i in range(2):
-                self._add(L.bflow_nchw_to_nhwc, self.img_in[i].data_ptr(), self.imgs.data_ptr() + i * B * H * W * 3 * 4, B, 3, H, W, 0, 3, 3, 2.0 / 255.0, -1.0)
-
         # ---- context encoder on the second stream: net = tanh -> h (fp32 master + split copy), inp = relu -> split only
         #      (raft.py:144-147); then the iteration-invariant GRU terms conv(inp) + bias ----
         U = eng.upd
         self._fork()
+        ctx_c = (nctx if self.use_ev else 0) + (3 if self.use_img else 0)
         if self.use_ev and self.use_img:
-            self._add(L.bflow_nchw_to_nhwc, self.voxel_in.data_ptr(), self.ctx.data_ptr(), B, self.cin_vox, H, W, self.cin_vox - nctx, nctx, ctx_c, 1.0, 0.0)
-            self._add(L.bflow_nchw_to_nhwc, self.img_in[0].data_ptr(), self.ctx.data_ptr() + nctx * 4, B, 3, H, W, 0, 3, ctx_c, 2.0 / 255.0, -1.0)
-            cwin = [(self.ctx.data_ptr(), ctx_c, ctx_c, B)]
+            # context = cat(voxel[:, -nctx:], image0) (raft.py:137-138): NHWC fp32 -> split planes -> 7x7 im2col-TMA stem
+            ctx_ld = _ceil(ctx_c, 8)
+            self.ctx = torch.zeros(B, H, W, ctx_ld, **f32)
+            self.ctx16 = _S16(B * H * W, ctx_ld, dev)
+            self._add(L.bflow_nchw_to_nhwc, self.voxel_in.data_ptr(), self.ctx.data_ptr(), B, self.cin_vox, H, W, self.cin_vox - nctx, nctx, ctx_ld, 1.0, 0.0)
+            self._add(L.bflow_nchw_to_nhwc, self.img_in[0].data_ptr(), self.ctx.data_ptr() + nctx * 4, B, 3, H, W, 0, 3, ctx_ld, 2.0 / 255.0, -1.0)
+            self._add(L.bflow_split_f16, self.ctx.data_ptr(), ctx_ld, self.ctx16.hi(), self.ctx16.lo(), ctx_ld, B * H * W, ctx_ld)
+            cwin = [dict(kind='tma', x16=self.ctx16, c_off=0, cin=ctx_c, ns=B)]
         elif self.use_ev:
-            cwin = [(self.vox.data_ptr() + (self.cin_vox - nctx) * 4, nctx, self.cin_vox, B)]
+            cwin = [self._stem_window(self.voxel_in, self.cin_vox, self.cin_vox - nctx, nctx, B, H, W)]
         else:
-            cwin = [(self.imgs.data_ptr(), 3, 3, B)]
+            cwin = [self._stem_window(self.img_in[0], 3, 0, 3, B, H, W, 2.0 / 255.0, -1.0)]
         Ec = eng.enc['cnet']
 
         def cnet_final(X, n_, Hc, Wc, Cc):
@@ -290,9 +330,11 @@ class S16Recorder:
         fm_ev = fm_img = fm_ev16 = fm_img16 = None
         if self.use_ev:
             idxs = [0] + list(cfg['correlation']['ev']['target_indices'])
-            fm_ev, fm_ev16 = fnet('fnet_ev', [(self.vox.data_ptr() + i * 4, ncorr, self.cin_vox, B) for i in idxs], (T_ev + 1) * B)
+            shared = {}
+            fm_ev, fm_ev16 = fnet('fnet_ev', [self._stem_window(self.voxel_in, self.cin_vox, i, ncorr, B, H, W, shared=shared) for i in idxs], (T_ev + 1) * B)
         if self.use_img:
-            fm_img, fm_img16 = fnet('fnet_img', [(self.imgs.data_ptr(), 3, 3, 2 * B)], 2 * B)
+            shared = {}
+            fm_img, fm_img16 = fnet('fnet_img', [self._stem_window(self.img_in[i], 3, 0, 3, B, H, W, 2.0 / 255.0, -1.0, shared=shared) for i in range(2)], 2 * B)
         self.fm_ev, self.fm_img, self.fm_ev16, self.fm_img16 = fm_ev, fm_img, fm_ev16, fm_img16
 
         # ---- correlation volume (tensor-core GEMM, granule-tiled planes) + pyramid (corr.py:264-272, 293-305) ----

@@ -109,10 +109,17 @@ int bflow_conv2d_tc_supported(const bflow_conv_desc* d);
  * One CTA per SM loops over 128 x bn tiles; TMEM holds two accumulators so the epilogue of a tile overlaps the MMAs of the
  * next.  Warp roles: TMA producer / MMA issuer / 4 epilogue warps.  d->x0/x1 are ignored (c0/c1 and the geometry are used).
  * maps: host array of four 128-byte tensor maps {source0 hi, source0 lo, source1 hi, source1 lo} from bflow_tma_im2col_map
- * (source1 entries unused when c1 == 0).  Needs c0 % 8 == 0, c1 % 8 == 0, (c1 == 0 or c0 % 64 == 0). */
+ * (source1 entries unused when c1 == 0).  Channel counts are free (the TMA unit zero-fills beyond C); needs c1 == 0 or c0 % 64 == 0,
+ * channel offsets that are multiples of 8 and row strides that are multiples of 8 halves. */
 int bflow_tma_im2col_map(void* map_out_128B, const void* base_fp16, int N, int H, int W, int C, int ld_halves,
                          int KH, int KW, int stride, int pad_h, int pad_w);
 int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* d, const void* maps, const void* w_tc, int bn, float acc_scale, int* err, void* stream);
+/* im2col of a channel window of an NCHW fp32 tensor straight into split-fp16 rows (the 7x7 stride-2 encoder stems on few input
+ * channels, extractor.py:112: K = KH*KW*cin is too thin per tap for 64-channel TMA boxes, so the patch matrix is materialised
+ * once and the stem becomes a 1x1 tensor-core GEMM).  out[row, (kh*KW+kw)*cin + c] = scale*src[n, c_off+c, oh*s-ph+kh, ow*s-pw+kw] + shift
+ * (zero outside the image), row = (n*Ho + oh)*Wo + ow; columns K..ld16-1 are written as zeros.  ld16 % 8 == 0. */
+int bflow_im2col_split16(const float* src_nchw, int C_total, int c_off, int cin, int N, int H, int W, int KH, int KW, int stride,
+                         int pad_h, int pad_w, float scale, float shift, void* out_hi, void* out_lo, int ld16, void* stream);
 /* fp32 NHWC rows -> split-fp16 planes (x = hi + lo): operand staging for tensors produced outside this library */
 int bflow_split_f16(const float* src, int ld, void* hi, void* lo, int ld16, long long rows, int C, void* stream);
 
