@@ -277,6 +277,25 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
         const float post = d.scale;
         uint32_t lt = 0;
         int bias_tile = -1;
+        // fused InstanceNorm statistics: per-CTA partial (sum, sum of squares) of the current image in shared memory, flushed with
+        // one double atomicAdd pair per column when the CTA moves on to another image (contention on the global table stays low)
+        float* s_stat = s_bias + BN;                 // [2][BN]
+        int cur_img = -1;
+        const int shw = d.stats_hw > 0 ? d.stats_hw : d.Ho * d.Wo;
+        auto flush_stats = [&](int img, int n0_) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int j = etid; j < BN; j += 256) {       // every thread reads and clears only its own columns
+                if (img >= 0 && n0_ + j < d.Cout) {
+                    atomicAdd(d.stats + ((size_t)img * d.Cout + n0_ + j) * 2, (double)s_stat[j]);
+                    atomicAdd(d.stats + ((size_t)img * d.Cout + n0_ + j) * 2 + 1, (double)s_stat[BN + j]);
+                }
+                s_stat[j] = 0.f;
+                s_stat[BN + j] = 0.f;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        };
+        int stat_n0 = 0;
+        if (d.stats != nullptr) flush_stats(-1, 0);
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
             const int m_tile = tile / p.n_ntiles, n_tile = tile - m_tile * p.n_ntiles;
             const int m = m_tile * T3_BM + quad * 32 + lane;
@@ -286,6 +305,14 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 for (int j = etid; j < BN; j += 256) s_bias[j] = (d.bias != nullptr && n0 + j < d.Cout) ? __ldg(d.bias + n0 + j) : 0.f;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 bias_tile = n_tile;
+            }
+            if (d.stats != nullptr) {
+                const int tile_img = (m_tile * T3_BM) / shw;
+                if (tile_img != cur_img || n0 != stat_n0) {
+                    flush_stats(cur_img, stat_n0);
+                    cur_img = tile_img;
+                    stat_n0 = n0;
+                }
             }
             const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
             t3_mbar_wait(tfull_bar(acc), aph, err);
@@ -312,6 +339,59 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 __syncwarp();
                 if (lane == 0) t3_mbar_arrive(tempty_bar(acc));
                 if (warp == 2 && lane == 0) T3_TRACE(4, lt);
+                if (d.stats != nullptr) {
+                    // butterfly transpose-reduce over the warp's 32 rows, 16 columns at a time; lanes with the low bit clear then own one
+                    // column's (sum, sum of squares) and add it to the CTA's shared accumulators
+                    const int m_first = m_tile * T3_BM + quad * 32;
+                    const int m_last = min(m_first + 31, p.M - 1);
+                    const bool uniform = m_first < p.M && (m_first / shw) == (m_last / shw);       // warp-uniform
+#pragma unroll
+                    for (int c = 0; c < HALF; c += 16) {
+                        const int nb = nb0 + c;
+                        if (nb + 15 >= d.Cout) break;
+                        float sv[16], sq[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float b = s_bias[chalf * HALF + c + j];
+                            const float x = m < p.M ? post * fmaf(v[c + j], p.acc_scale, b) : 0.f;
+                            sv[j] = x;
+                            sq[j] = x * x;
+                        }
+                        if (uniform) {
+#pragma unroll
+                            for (int width = 8, bit = 16; width >= 1; width >>= 1, bit >>= 1) {
+                                const bool upper = (lane & bit) != 0;
+#pragma unroll
+                                for (int i = 0; i < width; ++i) {
+                                    const float keep_s = upper ? sv[width + i] : sv[i], send_s = upper ? sv[i] : sv[width + i];
+                                    const float keep_q = upper ? sq[width + i] : sq[i], send_q = upper ? sq[i] : sq[width + i];
+                                    sv[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
+                                    sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
+                                }
+                            }
+                            const float ts = sv[0] + __shfl_xor_sync(0xffffffffu, sv[0], 1);
+                            const float tq = sq[0] + __shfl_xor_sync(0xffffffffu, sq[0], 1);
+                            if ((lane & 1) == 0) {
+                                const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                                if (m_first / shw == cur_img) {
+                                    atomicAdd(s_stat + chalf * HALF + c + col, ts);
+                                    atomicAdd(s_stat + BN + chalf * HALF + c + col, tq);
+                                } else {             // a tile that straddles two images: the minority warps go straight to the table
+                                    double* st = d.stats + ((size_t)(m_first / shw) * d.Cout + nb + col) * 2;
+                                    atomicAdd(st, (double)ts);
+                                    atomicAdd(st + 1, (double)tq);
+                                }
+                            }
+                        } else if (m < p.M) {
+                            double* st = d.stats + ((size_t)(m / shw) * d.Cout + nb) * 2;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                atomicAdd(st + 2 * j, (double)sv[j]);
+                                atomicAdd(st + 2 * j + 1, (double)sq[j]);
+                            }
+                        }
+                    }
+                }
                 if (m < p.M) {
 #pragma unroll
                     for (int c = 0; c < HALF; c += 16) {
@@ -379,6 +459,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
             }
             if (warp == 2 && lane == 0) T3_TRACE(5, lt);
         }
+        if (d.stats != nullptr) flush_stats(cur_img, stat_n0);
     }
     __syncthreads();
     if (warp == 1) {
@@ -411,7 +492,7 @@ static long long* g_tc3_trace = nullptr;
 
 template <int BN, int STAGES>
 static int launch_tc3(const CUtensorMap* maps, const bflow_conv_desc& d, const void* wtc, const T3Params& p, int* err, cudaStream_t stream) {
-    constexpr int smem = STAGES * (2 * T3_A_BYTES + 2 * BN * 128) + 128 + BN * 4 + 1024;
+    constexpr int smem = STAGES * (2 * T3_A_BYTES + 2 * BN * 128) + 128 + 3 * BN * 4 + 1024;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -443,44 +524,69 @@ __global__ void split_f16_kernel(const float* __restrict__ src, int ld, __half* 
     }
 }
 
-// one thread = one 8-column chunk of one patch row; the chunks of a row are adjacent threads (coalesced 16-byte stores), the
-// gathers hit L1/L2 (the source is a few MB)
-__global__ void im2col_split16_kernel(const float* __restrict__ src, int C_total, int c_off, int cin, int H, int W, int Ho, int Wo, int KH, int KW,
-                                      int stride, int pad_h, int pad_w, float scale, float shift, __half* __restrict__ hi, __half* __restrict__ lo,
-                                      int ld16, long long rows) {
-    const int chunks = ld16 >> 3;
+// CTA = 32 consecutive patch rows.  Phase 1 gathers column k for the 32 rows with one warp-wide load (consecutive output pixels read
+// a stride-`stride` run of the same input row: two 128-byte lines) into shared memory; phase 2 turns every 8 consecutive k of a
+// row into one 16-byte hi and one 16-byte lo store (a full 2*ld16-byte row per 32 threads: coalesced).
+constexpr int I2C_ROWS = 32;
+__global__ void __launch_bounds__(256) im2col_split16_kernel(const float* __restrict__ src, int C_total, int c_off, int cin, int H, int W, int Ho, int Wo,
+                                                             int KH, int KW, int stride, int pad_h, int pad_w, float scale, float shift,
+                                                             __half* __restrict__ hi, __half* __restrict__ lo, int ld16, long long rows) {
+    extern __shared__ float patch[];              // [I2C_ROWS][ld16 + 1] floats, then the tap table: int off[ld16], int khkw[ld16]
+    const int pitch = ld16 + 1;
     const int K = KH * KW * cin;
-    const long long total = rows * chunks;
+    int* t_off = reinterpret_cast<int*>(patch + I2C_ROWS * pitch);
+    int* t_khkw = t_off + ld16;
+    for (int k = threadIdx.x; k < ld16; k += blockDim.x) {
+        int off = 0, code = -1;
+        if (k < K) {
+            const int tap = k / cin, c = k - tap * cin;
+            const int kh = tap / KW, kw = tap - kh * KW;
+            off = c * (H * W) + kh * W + kw;
+            code = (kh << 8) | kw;
+        }
+        t_off[k] = off;
+        t_khkw[k] = code;
+    }
+    __syncthreads();
     const size_t HW = (size_t)H * W;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const long long row = idx / chunks;
-        const int k0 = (int)(idx - row * chunks) * 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long row0 = (long long)blockIdx.x * I2C_ROWS;
+    const long long row = row0 + lane;
+    const bool row_ok = row < rows;
+    int ih0 = 0, iw0 = 0;
+    const float* base = src;
+    if (row_ok) {
         const int ow = (int)(row % Wo);
         const long long t = row / Wo;
         const int oh = (int)(t % Ho);
         const int n = (int)(t / Ho);
-        const int ih0 = oh * stride - pad_h, iw0 = ow * stride - pad_w;
-        const float* base = src + ((size_t)n * C_total + c_off) * HW;
-        float v[8];
-        int tap = k0 / cin, c = k0 - tap * cin;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float x = 0.f;
-            if (k0 + e < K) {
-                const int kh = tap / KW, kw = tap - kh * KW;
-                const int ih = ih0 + kh, iw = iw0 + kw;
-                if (ih >= 0 && ih < H && iw >= 0 && iw < W) x = fmaf(__ldg(base + (size_t)c * HW + (size_t)ih * W + iw), scale, shift);
-            }
-            v[e] = x;
-            if (++c == cin) { c = 0; ++tap; }
+        ih0 = oh * stride - pad_h;
+        iw0 = ow * stride - pad_w;
+        base = src + ((size_t)n * C_total + c_off) * HW;
+    }
+    const float* p00 = base + (long long)ih0 * W + iw0;      // tap (0,0), channel 0 (may point outside: only dereferenced when in bounds)
+    for (int k = warp; k < ld16; k += 8) {        // warp-uniform k
+        float x = 0.f;
+        const int code = t_khkw[k];
+        if (code >= 0 && row_ok) {
+            const int ih = ih0 + (code >> 8), iw = iw0 + (code & 255);
+            if (ih >= 0 && ih < H && iw >= 0 && iw < W) x = fmaf(__ldg(p00 + t_off[k]), scale, shift);
         }
+        patch[lane * pitch + k] = x;
+    }
+    __syncthreads();
+    const int chunks = ld16 >> 3;
+    for (int idx = threadIdx.x; idx < I2C_ROWS * chunks; idx += 256) {
+        const int r = idx / chunks, ck = idx - r * chunks;
+        if (row0 + r >= rows) continue;
+        const float* p = patch + r * pitch + ck * 8;
         uint4 h4, l4;
-        split2(v[0], v[1], h4.x, l4.x);
-        split2(v[2], v[3], h4.y, l4.y);
-        split2(v[4], v[5], h4.z, l4.z);
-        split2(v[6], v[7], h4.w, l4.w);
-        *reinterpret_cast<uint4*>(hi + (size_t)row * ld16 + k0) = h4;
-        *reinterpret_cast<uint4*>(lo + (size_t)row * ld16 + k0) = l4;
+        split2(p[0], p[1], h4.x, l4.x);
+        split2(p[2], p[3], h4.y, l4.y);
+        split2(p[4], p[5], h4.z, l4.z);
+        split2(p[6], p[7], h4.w, l4.w);
+        *reinterpret_cast<uint4*>(hi + (size_t)(row0 + r) * ld16 + ck * 8) = h4;
+        *reinterpret_cast<uint4*>(lo + (size_t)(row0 + r) * ld16 + ck * 8) = l4;
     }
 }
 
@@ -494,10 +600,16 @@ extern "C" int bflow_im2col_split16(const float* src, int C_total, int c_off, in
     BFLOW_REQUIRE((reinterpret_cast<uintptr_t>(out_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_lo) & 15) == 0, "im2col_split16: alignment");
     const int Ho = (H + 2 * pad_h - KH) / stride + 1, Wo = (W + 2 * pad_w - KW) / stride + 1;
     const long long rows = (long long)N * Ho * Wo;
-    const long long total = rows * (ld16 / 8);
-    long long g = (total + 255) / 256;
-    if (g > 148 * 32) g = 148 * 32;
-    bflow::im2col_split16_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(src, C_total, c_off, cin, H, W, Ho, Wo, KH, KW, stride, pad_h, pad_w, scale, shift,
+    BFLOW_REQUIRE(ld16 <= 1024, "im2col_split16: ld16 > 1024");
+    const long long g = (rows + bflow::I2C_ROWS - 1) / bflow::I2C_ROWS;
+    BFLOW_REQUIRE((long long)cin * H * W < (1ll << 31), "im2col_split16: source too large");
+    const size_t smem = (size_t)bflow::I2C_ROWS * (ld16 + 1) * sizeof(float) + (size_t)ld16 * 2 * sizeof(int);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(bflow::im2col_split16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1025 * 4 + 1024 * 8);
+        configured = true;
+    }
+    bflow::im2col_split16_kernel<<<(unsigned)g, 256, smem, (cudaStream_t)stream>>>(src, C_total, c_off, cin, H, W, Ho, Wo, KH, KW, stride, pad_h, pad_w, scale, shift,
                                                                                 reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), ld16, rows);
     return bflow::check_launch("bflow_im2col_split16");
 }
@@ -555,6 +667,9 @@ extern "C" int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* dp, const void* maps
     BFLOW_REQUIRE((d.y == nullptr || d.ldy >= d.Cout) && (d.res == nullptr || d.ldr >= d.Cout), "conv_tc3: bad output stride");
     BFLOW_REQUIRE((reinterpret_cast<uintptr_t>(w_tc) & 15) == 0 && (reinterpret_cast<uintptr_t>(maps) & 7) == 0, "conv_tc3: alignment");
     if (const char* msg = bflow::check_epilogue(d)) { bflow::set_error(msg); return BFLOW_ERR_INVALID; }
+    BFLOW_REQUIRE(d.stats == nullptr || (d.epi == BFLOW_EPI_STD && d.Cout % 16 == 0 && d.res == nullptr && d.res16_hi == nullptr &&
+                                         d.act1 == BFLOW_ACT_NONE && d.act2 == BFLOW_ACT_NONE && d.stats_hw >= 0),
+                  "conv_tc3: fused statistics need the plain epilogue and Cout % 16 == 0");
     const long long Mll = (long long)d.N * d.Ho * d.Wo;
     BFLOW_REQUIRE(Mll < (1ll << 31), "conv_tc3: too large");
     bflow::T3Params p;

@@ -67,7 +67,7 @@ class S16Recorder:
 
     def _conv3(self, wt, srcs: Sequence[Tuple[_S16, int, int]], N, H, W, y=None, ldy=0, y16: Optional[Tuple[_S16, int]] = None,
                act1='none', act2='none', res=None, ldr=0, res16: Optional[Tuple[_S16, int]] = None, scale=1.0, bias=True,
-               epi='std', aux0=None, ld_aux0=0, aux1_16: Optional[Tuple[_S16, int]] = None):
+               epi='std', aux0=None, ld_aux0=0, aux1_16: Optional[Tuple[_S16, int]] = None, stats=None, stats_hw=0):
         """Tensor-core convolution on split-fp16 sources [(tensor, channel offset, channels), ...] (channel concatenation)."""
         lib = self.eng.lib
         c0 = srcs[0][2]
@@ -89,6 +89,7 @@ class S16Recorder:
             d.y16_hi, d.y16_lo, d.ldy16 = y16[0].hi(y16[1]), y16[0].lo(y16[1]), y16[0].ld
         if res16 is not None:
             d.res16_hi, d.res16_lo, d.ldr16 = res16[0].hi(res16[1]), res16[0].lo(res16[1]), res16[0].ld
+        d.stats, d.stats_hw = stats, stats_hw
         if aux1_16 is not None:
             d.aux1_16_hi, d.aux1_16_lo, d.ld_aux1_16 = aux1_16[0].hi(aux1_16[1]), aux1_16[0].lo(aux1_16[1]), aux1_16[0].ld
         self.keep.append(d)
@@ -173,28 +174,30 @@ class S16Recorder:
         #   'im2col'  few input channels (K = 49*cin <= 512): patch matrix in split-fp16 + 1x1 tensor-core GEMM
         #   'tma'     cin >= 16 at an 8-aligned channel offset of a split-fp16 NHWC input: 7x7 im2col-TMA convolution
         #   'simt'    fp32 NHWC input on CUDA cores
-        def stem(win, n0, ns, y=None, y16=None, act='none'):
+        def stem(win, n0, ns, y=None, y16=None, act='none', stats=None):
             if win['kind'] == 'im2col':
                 wm = E['conv1_mat']
                 buf = win['buf']
                 self._add(L.bflow_im2col_split16, win['src'], win['C_total'], win['c_off'], win['cin'], ns, H, W, 7, 7, 2, 3, 3, win.get('scale', 1.0),
                           win.get('shift', 0.0), buf.hi(), buf.lo(), buf.ld)
-                self._conv3(wm, [(buf, 0, wm.cin)], 1, 1, ns * H2 * W2, y=y, ldy=64, y16=y16, act1=act)
+                self._conv3(wm, [(buf, 0, wm.cin)], 1, 1, ns * H2 * W2, y=y, ldy=64, y16=y16, act1=act, stats=stats, stats_hw=H2 * W2)
             elif win['kind'] == 'tma':
-                self._conv3(w1, [(win['x16'], win['c_off'], win['cin'])], ns, H, W, y=y, ldy=64, y16=y16, act1=act)
+                self._conv3(w1, [(win['x16'], win['c_off'], win['cin'])], ns, H, W, y=y, ldy=64, y16=y16, act1=act, stats=stats)
             else:
                 self._conv_simt16(w1, win['ptr'], win['cin'], win['ld'], ns, H, W, y=y, ldy=64, y16=y16, act1=act)
 
         if inorm:
             raw = free.pop()
+            sm = self._sums(Np, 64)
+            fused = all(win['kind'] != 'simt' for win in windows)      # tensor-core stems accumulate the IN statistics themselves
             n0 = 0
             for win in windows:
-                stem(win, n0, win['ns'], y=raw + n0 * H2 * W2 * 64 * 4)
+                stem(win, n0, win['ns'], y=raw + n0 * H2 * W2 * 64 * 4, stats=(sm + n0 * 64 * 2 * 8) if fused else None)
                 n0 += win['ns']
             xptr = free.pop()
             X = s16(xptr, rows, 64)
-            sm = self._sums(Np, 64)
-            self._add(L.bflow_plane_sums, raw, 64, sm, Np, H2 * W2, 64)
+            if not fused:
+                self._add(L.bflow_plane_sums, raw, 64, sm, Np, H2 * W2, 64)
             self._add(L.bflow_instnorm_relu16, raw, 64, sm, None, 0, None, None, None, 0, None, 0, X.hi(), X.lo(), 64, Np, H2 * W2, 64, 1e-5)
             free.append(raw)
         else:
@@ -213,23 +216,20 @@ class S16Recorder:
             rin, rout = Np * Hc * Wc, Np * Ho * Wo
             if inorm:
                 raw1 = free.pop()
-                self._conv3(c1, [(X, 0, Cc)], Np, Hc, Wc, y=raw1, ldy=Co)
+                sm = self._sums(Np, Co)
+                self._conv3(c1, [(X, 0, Cc)], Np, Hc, Wc, y=raw1, ldy=Co, stats=sm)
                 y1p = free.pop()
                 Y1 = s16(y1p, rout, Co)
-                sm = self._sums(Np, Co)
-                self._add(L.bflow_plane_sums, raw1, Co, sm, Np, Ho * Wo, Co)
                 self._add(L.bflow_instnorm_relu16, raw1, Co, sm, None, 0, None, None, None, 0, None, 0, Y1.hi(), Y1.lo(), Co, Np, Ho * Wo, Co, 1e-5)
                 raw2 = raw1                                     # raw1 is dead: reuse it for conv2's output
-                self._conv3(c2, [(Y1, 0, Co)], Np, Ho, Wo, y=raw2, ldy=Co)
                 sm2 = self._sums(Np, Co)
-                self._add(L.bflow_plane_sums, raw2, Co, sm2, Np, Ho * Wo, Co)
+                self._conv3(c2, [(Y1, 0, Co)], Np, Ho, Wo, y=raw2, ldy=Co, stats=sm2)
                 outp = y1p                                      # Y1 is dead after conv2: the block output takes its place
                 OUT = s16(outp, rout, Co)
                 if dn is not None:
                     rawd = free.pop()
-                    self._conv3(dn, [(X, 0, Cc)], Np, Hc, Wc, y=rawd, ldy=Co)
                     smd = self._sums(Np, Co)
-                    self._add(L.bflow_plane_sums, rawd, Co, smd, Np, Ho * Wo, Co)
+                    self._conv3(dn, [(X, 0, Cc)], Np, Hc, Wc, y=rawd, ldy=Co, stats=smd)
                     self._add(L.bflow_instnorm_relu16, raw2, Co, sm2, rawd, Co, smd, None, None, 0, None, 0, OUT.hi(), OUT.lo(), Co, Np, Ho * Wo, Co, 1e-5)
                     free.append(rawd)
                 else:
@@ -429,9 +429,12 @@ class S16Recorder:
                 self._conv3(U['q' + sfx + '_dyn'], [(rh16, 0, hd), (hx16, hd + cd, md)], B, h, w, y=hx, ldy=gw, y16=(hx16, 0), bias=False,
                             res=pre['q' + sfx], ldr=hd, epi='gru_q', aux0=zr, ld_aux0=2 * hd)
             # Bezier head + delta update in place (update.py:17-18, bezier.py:137-139): fp32 master and split copy
-            self._conv3(U['head1'], [(hx16, 0, hd)], B, h, w, y=hh, ldy=256, act1='relu')
-            self._conv_simt16(U['head2'], hh, 256, 256, B, h, w, y=hx + poff * 4, ldy=gw, y16=(hx16, poff), res=hx + poff * 4, ldr=gw,
-                              kernel='small_n' if 2 * deg <= 32 else 'auto')
+            if 2 * deg <= 8:      # tiny head: warp-per-pixel CUDA-core kernel on the fp32 hidden tensor
+                self._conv3(U['head1'], [(hx16, 0, hd)], B, h, w, y=hh, ldy=256, act1='relu')
+                self._conv_simt16(U['head2'], hh, 256, 256, B, h, w, y=hx + poff * 4, ldy=gw, y16=(hx16, poff), res=hx + poff * 4, ldr=gw, kernel='small_n')
+            else:
+                self._conv3(U['head1'], [(hx16, 0, hd)], B, h, w, y16=(hm16, 0), act1='relu')
+                self._conv3(U['head2'], [(hm16, 0, 256)], B, h, w, y=hx + poff * 4, ldy=gw, y16=(hx16, poff), res=hx + poff * 4, ldr=gw)
             if not self.test_mode:
                 upsample(self.ups[itr])
         if self.iters == 1:

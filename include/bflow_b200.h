@@ -89,6 +89,10 @@ typedef struct bflow_conv_desc {
     void* y16_hi; void* y16_lo; int ldy16;
     const void* res16_hi; const void* res16_lo; int ldr16;
     void* aux1_16_hi; void* aux1_16_lo; int ld_aux1_16;
+    /* InstanceNorm statistics fused into the epilogue (bflow_conv2d_nhwc_tc3 only, standard epilogue, Cout % 16 == 0):
+     * stats[(m / stats_hw) * Cout + n] += (v, v*v) of every value v written to y — the (sum, sum of squares) table that
+     * bflow_instnorm_relu(16) consumes, so no separate bflow_plane_sums pass.  stats_hw = rows per image (0: Ho*Wo). */
+    double* stats; int stats_hw;
 } bflow_conv_desc;
 int bflow_conv2d_nhwc(const bflow_conv_desc* d, void* stream);
 
