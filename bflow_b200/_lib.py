@@ -79,6 +79,10 @@ _SIGNATURES = {
     'bflow_corr_pool': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     'bflow_corr_pool_tiled': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     'bflow_corr_lookup': (C.c_int, [C.POINTER(LookupDesc), C.c_void_p]),
+    'bflow_voxelize': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_void_p]),
+    'bflow_voxel_norm': (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
+    'bflow_epe_masked': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
     'bflow_gru_rh': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
     'bflow_gru_update': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
     'bflow_bezier_eval': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),

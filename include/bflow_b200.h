@@ -228,6 +228,19 @@ int bflow_bezier_eval(const float* params_nchw, const float* coef_host, float* f
 int bflow_cvx_upsample(const float* data, int ldd, int data_nchw, const float* mask, int ldm, int mask_nchw,
                        float* out, int N, int C, int h, int w, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Scope rows (f1)/(f2): the steps on either side of forward().
+ * bflow_voxelize: VoxelGrid.convert (data/utils/representations.py:64-111).  x, y: int64 pixel coordinates (xy_is_float = 0) or
+ * fp32 sub-pixel coordinates (1); pol: uint8/bool 0|1; time: int64; out: (channels, H, W) fp32, ACCUMULATED into (zero it first).
+ * bflow_voxel_norm: norm_voxel_grid (representations.py:9-18), in place; stats3: 3 doubles of scratch.
+ * bflow_epe_masked: epe_masked (utils/metrics.py:196-213) as (sum, count): sum_count[0] += sum of sqrt(sum_c (src-tgt)^2) over the
+ * valid pixels, sum_count[1] += their number (valid: uint8/bool (N, HW) or NULL); src/tgt NCHW (N, C, HW).
+ * ------------------------------------------------------------------------------------------- */
+int bflow_voxelize(const void* x, const void* y, int xy_is_float, const unsigned char* pol, const long long* time, long long n_events,
+                   long long t0_center, long long t1_center, int channels, int H, int W, float* out, void* stream);
+int bflow_voxel_norm(float* voxel, long long numel, double* stats3, void* stream);
+int bflow_epe_masked(const float* src, const float* tgt, const unsigned char* valid, int N, int C, long long HW, double* sum_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -113,11 +113,35 @@ def make_bezier():
     print('bezier ok')
 
 
+def make_events():
+    """Reference VoxelGrid.convert / norm_voxel_grid (data/utils/representations.py) on seeded synthetic events."""
+    import importlib
+    ref_loader.load()
+    rep = importlib.import_module('data.utils.representations')
+    g = torch.Generator().manual_seed(11)
+    C_, H, W, n = 5, 24, 32, 6000
+    t = torch.sort(torch.randint(1000, 51000, (n,), generator=g)).values
+    xi = torch.randint(0, W, (n,), generator=g)
+    yi = torch.randint(0, H, (n,), generator=g)
+    xf = torch.rand(n, generator=g) * (W + 1) - 1          # some events fall outside the sensor
+    yf = torch.rand(n, generator=g) * (H + 1) - 1
+    pol = torch.randint(0, 2, (n,), generator=g).bool()
+    vg = rep.VoxelGrid(C_, H, W)
+    out_int = vg.convert(xi, yi, pol, t, 5000, 45000)
+    out_flt = vg.convert(xf, yf, pol, t, 5000, 45000)
+    out_default = vg.convert(xi, yi, pol, t)
+    normed = rep.norm_voxel_grid(out_int.clone())
+    np.savez_compressed(os.path.join(GOLD, 'events.npz'), C=C_, H=H, W=W, t=t.numpy(), xi=xi.numpy(), yi=yi.numpy(), xf=xf.numpy(), yf=yf.numpy(),
+                        pol=pol.numpy(), out_int=out_int.numpy(), out_flt=out_flt.numpy(), out_default=out_default.numpy(), normed=normed.numpy())
+    print('events ok', float(out_int.abs().sum()), float(out_flt.abs().sum()))
+
+
 if __name__ == '__main__':
     assert ref_loader.available(), 'needs /root/reference (build container only)'
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     make_bezier()
     make_lookup()
+    make_events()
     for c in CASES:
         make_case(*c)
