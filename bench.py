@@ -275,18 +275,19 @@ def main():
     line = {
         'metric': METRIC, 'value': frames / (ms * 1e-3), 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
         'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'bf16x3' if eng.use_tc else 'f32', 'data': 'synthetic',
+        'dtype': 'f16x2-split (fp32-equivalent, 3 MMAs per product)' if eng.use_tc else 'f32', 'data': 'synthetic',
         'config': {'workload': f'{PRESET} {W}x{H} synthetic DSEC events (sparse_norm voxel grid 9 bins), {ITERS} iters, batch {Bp}/GPU, '
                                f'random-init weights seed 0', 'global_batch': Bp * world, 'parallelism': f'batch-sharded x{world}',
                    'l2': 'no explicit flush: one step streams a 369 MB correlation volume and ~0.5 GB of encoder activations (> 126 MB L2)',
-                   'cuda_graph': eng.use_graph,
-                   'arithmetic': ('split-bf16 operands (x = hi + lo; hi*hi + hi*lo + lo*hi) on tcgen05 with fp32 TMEM accumulation, fp32 storage; '
-                                  f'{plan.n_tc} of {sum(1 for f, _ in plan.launches if "conv2d" in f.__name__)} convolution launches on tensor cores, '
-                                  '7x7 stems and convf1 on fp32 CUDA cores') if eng.use_tc else 'fp32 FFMA (CUDA cores), fp32 storage'},
+                   'cuda_graph': eng.use_graph, 'graph_branches': eng.use_side_stream,
+                   'arithmetic': ('split-fp16 operands (x = hi + lo; hi*hi + hi*lo + lo*hi) on tcgen05 with fp32 TMEM accumulation; activations '
+                                  'stored as fp16 hi/lo planes, state/volume/outputs fp32; '
+                                  f'{plan.n_tc} of {sum(1 for f, _ in plan.launches if "conv2d" in f.__name__)} convolution launches on tensor cores '
+                                  '(convf1 and the 4-channel Bezier head on fp32 CUDA cores)') if eng.use_tc else 'fp32 FFMA (CUDA cores), fp32 storage'},
         'e2e': {'value': frames / (e2e_ms * 1e-3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': e2e_ms / K, 'api': 'RAFTSpline.forward(voxel_grid=pinned host tensor .to(cuda)) -> BezierCurves.cpu()'},
         'gpu_launches': plan.n_launches * K,
-        'roofline': {'kernel': 'corr_lookup_kernel (bflow_corr_lookup)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+        'roofline': {'kernel': 'corr_lookup_tiled_kernel (bflow_corr_lookup, granule-tiled volume)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                      'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src, 'bytes_per_launch': lk_bytes,
                      'us_per_launch': lk_ms * 1e3, 'launches_timed': len(lk),
                      'note': 'CUDA events around each of the 12 lookup launches of a step run eagerly in sequence; at batch 1 the launch moves '
@@ -319,12 +320,12 @@ def lookup_sweep(dev, peak):
     for B in (1, 4, 8, 16, 32):
         g = torch.Generator(device='cpu').manual_seed(7)
         R = B * h * w
-        lv = [torch.randn(R, h >> l, w >> l, device=dev) for l in range(4)]
-        slots = [(l, 0, lv[l]) for l in range(4)]
+        lv = [ops.to_tiled(torch.randn(R, h >> l, w >> l, device=dev)) for l in range(4)]       # granule-tiled planes (production layout)
+        slots = [(l, 0, lv[l], h >> l, w >> l) for l in range(4)]
         ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing='ij')
         coords = (torch.stack([xs, ys], 0).float()[None, None] + 8 * torch.randn(1, B, 2, h, w, generator=g)).to(dev)
         res = torch.empty(R, 4 * 81, device=dev)
-        d = ops.make_lookup_desc(slots, 1, B, h, w)
+        d = ops.make_lookup_desc(slots, 1, B, h, w, True)
         d.coords, d.params, d.params_ld, d.degree = coords.data_ptr(), None, 0, 0
         d.out, d.out_nhwc, d.out_ld = res.data_ptr(), 1, 4 * 81
         for _ in range(3):

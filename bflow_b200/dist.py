@@ -27,6 +27,9 @@ def shard_batch(t: Optional[torch.Tensor], rank: int, world: int) -> Optional[to
 
 def epe_sum_count(flow: torch.Tensor, target: torch.Tensor, valid: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Per-pixel end-point error sqrt(sum_c (flow-target)^2), masked (utils/metrics.py:196-213) → (sum f64, count i64)."""
+    if flow.is_cuda:
+        from .events import epe_sum_count as _device_epe          # bflow_epe_masked kernel
+        return _device_epe(flow, target, valid)
     e = torch.sqrt(((flow - target) ** 2).sum(dim=1))
     if valid is not None:
         v = valid.reshape(e.shape).bool()
