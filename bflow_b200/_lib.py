@@ -70,6 +70,7 @@ _SIGNATURES = {
     'bflow_pack_b_tc': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     'bflow_corr_volume_tc': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     'bflow_conv2d_small_n': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    'bflow_conv2d_thin7': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     'bflow_plane_sums': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'bflow_instnorm_relu': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),

@@ -134,6 +134,105 @@ __device__ __forceinline__ void conv_epilogue4(const bflow_conv_desc& d, int m, 
     }
 }
 
+// The same epilogue in two steps, for callers that batch several groups per thread: every global LOAD a group needs is issued by
+// conv_epilogue4_prefetch (so the loads of a whole batch are in flight together), conv_epilogue4_finish does the arithmetic and the
+// stores.  `vec` as above; ragged / unaligned groups fall back to conv_epilogue4 inside finish.
+struct EpiPre {
+    float4 r, a, y;
+};
+__device__ __forceinline__ void conv_epilogue4_prefetch(const bflow_conv_desc& d, int m, int n, bool vec, EpiPre& e) {
+    e.r = make_float4(0.f, 0.f, 0.f, 0.f);
+    e.a = e.r;
+    e.y = e.r;
+    if (!vec) return;
+    if (d.epi == BFLOW_EPI_STD) {
+        if (d.res != nullptr) e.r = *reinterpret_cast<const float4*>(d.res + (size_t)m * d.ldr + n);
+        else if (d.res16_hi != nullptr) e.r = load_split4(d.res16_hi, d.res16_lo, (size_t)m * d.ldr16 + n);
+    } else if (d.epi == BFLOW_EPI_GRU_ZR) {
+        if (d.res != nullptr) e.r = *reinterpret_cast<const float4*>(d.res + (size_t)m * d.ldr + n);
+        const int C = d.Cout >> 1;
+        if (n >= C) e.a = *reinterpret_cast<const float4*>(d.aux0 + (size_t)m * d.ld_aux0 + (n - C));
+    } else {
+        if (d.res != nullptr) e.r = *reinterpret_cast<const float4*>(d.res + (size_t)m * d.ldr + n);
+        e.a = *reinterpret_cast<const float4*>(d.aux0 + (size_t)m * d.ld_aux0 + n);
+        e.y = *reinterpret_cast<const float4*>(d.y + (size_t)m * d.ldy + n);
+    }
+}
+__device__ __forceinline__ void conv_epilogue4_finish(const bflow_conv_desc& d, int m, int n, float* v, bool vec, const EpiPre& e) {
+    if (!vec) {
+        conv_epilogue4(d, m, n, v, false);
+        return;
+    }
+    if (d.epi == BFLOW_EPI_STD) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], d.act1);
+        v[0] += e.r.x; v[1] += e.r.y; v[2] += e.r.z; v[3] += e.r.w;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], d.act2);
+        if (d.y != nullptr) *reinterpret_cast<float4*>(d.y + (size_t)m * d.ldy + n) = make_float4(v[0], v[1], v[2], v[3]);
+        if (d.y16_hi != nullptr) store_split4(d.y16_hi, d.y16_lo, (size_t)m * d.ldy16 + n, v[0], v[1], v[2], v[3]);
+    } else if (d.epi == BFLOW_EPI_GRU_ZR) {
+        const int C = d.Cout >> 1;
+        float4 g = make_float4(v[0] + e.r.x, v[1] + e.r.y, v[2] + e.r.z, v[3] + e.r.w);
+        g.x = apply_act(g.x, BFLOW_ACT_SIGMOID); g.y = apply_act(g.y, BFLOW_ACT_SIGMOID);
+        g.z = apply_act(g.z, BFLOW_ACT_SIGMOID); g.w = apply_act(g.w, BFLOW_ACT_SIGMOID);
+        *reinterpret_cast<float4*>(d.y + (size_t)m * d.ldy + n) = g;
+        if (n >= C) {
+            if (d.aux1 != nullptr)
+                *reinterpret_cast<float4*>(d.aux1 + (size_t)m * d.ld_aux1 + (n - C)) = make_float4(g.x * e.a.x, g.y * e.a.y, g.z * e.a.z, g.w * e.a.w);
+            if (d.aux1_16_hi != nullptr)
+                store_split4(d.aux1_16_hi, d.aux1_16_lo, (size_t)m * d.ld_aux1_16 + (n - C), g.x * e.a.x, g.y * e.a.y, g.z * e.a.z, g.w * e.a.w);
+        }
+    } else {
+        float4 q = make_float4(tanhf(v[0] + e.r.x), tanhf(v[1] + e.r.y), tanhf(v[2] + e.r.z), tanhf(v[3] + e.r.w));
+        float4 hv = e.y;
+        hv.x = (1.f - e.a.x) * hv.x + e.a.x * q.x;
+        hv.y = (1.f - e.a.y) * hv.y + e.a.y * q.y;
+        hv.z = (1.f - e.a.z) * hv.z + e.a.z * q.z;
+        hv.w = (1.f - e.a.w) * hv.w + e.a.w * q.w;
+        *reinterpret_cast<float4*>(d.y + (size_t)m * d.ldy + n) = hv;
+        if (d.y16_hi != nullptr) store_split4(d.y16_hi, d.y16_lo, (size_t)m * d.ldy16 + n, hv.x, hv.y, hv.z, hv.w);
+    }
+}
+
+// Development timeline (bflow_timeline): every instrumented launch owns a slot {first CTA start, last CTA end} in globaltimer
+// nanoseconds, baked into the launch at record time -- so a CUDA-graph replay leaves the true in-graph schedule behind.
+unsigned long long* timeline_next_slot(const char* name);      // runtime.cu; nullptr when the timeline is off
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void tl_begin(unsigned long long* slot) {
+    if (slot != nullptr && threadIdx.x == 0) atomicMin(slot, global_ns());
+}
+__device__ __forceinline__ void tl_end(unsigned long long* slot) {
+    if (slot != nullptr && (threadIdx.x & 31) == 0) atomicMax(slot + 1, global_ns());
+}
+
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may begin while its predecessor on the stream is
+// still running; it must call pdl_wait() before its first access to memory the predecessor touches.  pdl_trigger() lets the
+// successor's CTAs be scheduled (their prologue -- barrier init, TMEM allocation, descriptor fetch -- then overlaps our tail).
+// Both are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();      // runtime.cu: BFLOW_PDL != 0 (default on)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ __forceinline__ long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

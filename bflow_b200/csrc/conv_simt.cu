@@ -23,7 +23,8 @@ constexpr int BK = 16;
 constexpr int NTHREADS = 256;
 
 template <int TM, bool VEC>
-__global__ void __launch_bounds__(NTHREADS) conv_simt_kernel(const bflow_conv_desc d, const int M, const int K) {
+__global__ void __launch_bounds__(NTHREADS) conv_simt_kernel(const bflow_conv_desc d, const int M, const int K, unsigned long long* tl) {
+    tl_begin(tl);
     constexpr int BM = 16 * TM;
     constexpr int LDA = BM + 4;
     constexpr int NA_VEC = BM * 4 / NTHREADS;   // float4 loads per thread per k-block (2 or 1)
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_simt_kernel(const bflow_conv_de
         for (int j = 0; j < 4; ++j) v[j] = d.scale * (acc[i][j] + bias[j]);
         conv_epilogue4(d, m, nbase, v, vec_store);
     }
+    tl_end(tl);
 }
 
 static int launch_conv(const bflow_conv_desc& d, cudaStream_t stream) {
@@ -212,14 +214,15 @@ static int launch_conv(const bflow_conv_desc& d, cudaStream_t stream) {
     const long long ctas128 = ceil_div_ll(Mll, 128) * ceil_div(d.Cout, BN);
     const bool small = ctas128 < 2 * 148;
     dim3 block(NTHREADS);
+    unsigned long long* tls = timeline_next_slot("conv_simt");
     if (small) {
         dim3 grid((unsigned)ceil_div_ll(Mll, 64), (unsigned)ceil_div(d.Cout, BN));
-        if (vec) conv_simt_kernel<4, true><<<grid, block, 0, stream>>>(d, M, K);
-        else conv_simt_kernel<4, false><<<grid, block, 0, stream>>>(d, M, K);
+        if (vec) conv_simt_kernel<4, true><<<grid, block, 0, stream>>>(d, M, K, tls);
+        else conv_simt_kernel<4, false><<<grid, block, 0, stream>>>(d, M, K, tls);
     } else {
         dim3 grid((unsigned)ceil_div_ll(Mll, 128), (unsigned)ceil_div(d.Cout, BN));
-        if (vec) conv_simt_kernel<8, true><<<grid, block, 0, stream>>>(d, M, K);
-        else conv_simt_kernel<8, false><<<grid, block, 0, stream>>>(d, M, K);
+        if (vec) conv_simt_kernel<8, true><<<grid, block, 0, stream>>>(d, M, K, tls);
+        else conv_simt_kernel<8, false><<<grid, block, 0, stream>>>(d, M, K, tls);
     }
     return check_launch("bflow_conv2d_nhwc");
 }
@@ -251,9 +254,12 @@ extern "C" int bflow_conv2d_nhwc(const bflow_conv_desc* dp, void* stream) {
 // ---------------------------------------------------------------------------------------------
 namespace bflow {
 template <int NV>   // NV = ceil(Cout/4) float4 accumulators per lane
-__global__ void __launch_bounds__(256) conv_small_n_kernel(const bflow_conv_desc d, const int M) {
+__global__ void __launch_bounds__(256) conv_small_n_kernel(const bflow_conv_desc d, const int M, unsigned long long* tl) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = blockIdx.x * 8 + warp;
+    tl_begin(tl);
+    pdl_trigger();
+    pdl_wait();
     if (m >= M) return;
     const int ow = m % d.Wo;
     const int t = m / d.Wo;
@@ -310,6 +316,117 @@ __global__ void __launch_bounds__(256) conv_small_n_kernel(const bflow_conv_desc
                          (d.res == nullptr || (((d.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.res) & 15) == 0)));
         conv_epilogue4(d, m, nb, v, vec);
     }
+    tl_end(tl);
+}
+// Same operator for the shape the Bezier head really has (3x3, stride 1, Cin = 128 or 256, Cout <= 8): the weights sit in shared memory,
+// a warp owns a pixel, lane l owns channels {4l..4l+3} + 128 i, and all 9 x (Cin/128) activation loads of a pixel are issued before the first
+// FMA -- one memory round trip per pixel instead of one per (tap, channel chunk).
+template <int NV, int CB>   // CB = Cin / 128
+__global__ void __launch_bounds__(256) conv_head3x3_kernel(const bflow_conv_desc d, const int M, unsigned long long* tl) {
+    extern __shared__ __align__(16) float s_w[];          // [9][Cin][NV*4] weights, then 8 warp slabs of [9][Cin] inputs
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int Cin = CB * 128;
+    float* s_x = s_w + 9 * Cin * NV * 4;
+    tl_begin(tl);
+    pdl_trigger();
+    // shared layout [tap][cb][e][j][lane]: channel c = cb*128 + lane*4 + e -- for a fixed (tap, cb, e, j) consecutive lanes read consecutive
+    // float4, so the LDS.128 in the inner loop are conflict-free
+    for (int i = threadIdx.x; i < 9 * Cin * NV; i += 256) {            // weights are constants of the model: no pdl_wait needed yet
+        const int row = i / NV, j = i - row * NV;
+        const int tap = row / Cin, c = row - tap * Cin;
+        const int cb = c >> 7, ln = (c & 127) >> 2, e = c & 3;
+        // cp.async: the whole fill is in flight at once (a load -> store loop would pay one L2 round trip per iteration)
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<float4*>(s_w) + ((((tap * CB + cb) * 4 + e) * NV + j) << 5) + ln);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(d.w + (size_t)row * d.ldw + 4 * j) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    pdl_wait();
+    __syncthreads();
+    for (int m = blockIdx.x * 8 + warp; m < M; m += gridDim.x * 8) {
+        const int ow = m % d.Wo;
+        const int t = m / d.Wo;
+        const int oh = t % d.Ho;
+        const int n = t / d.Ho;
+        // the pixel's 9 x Cin inputs go to this warp's shared-memory slab with cp.async: all 9*CB 16-byte copies of a lane are in flight at
+        // once by construction (ptxas serialises plain loads to save registers); padding taps are zero-filled (src-size 0)
+        float* xs_w = s_x + warp * (9 * Cin);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int ih = oh - 1 + tap / 3, iw = ow - 1 + tap % 3;
+            const bool ok = ih >= 0 && ih < d.H && iw >= 0 && iw < d.W;
+            const float* xp = d.x0 + (((size_t)n * d.H + (ok ? ih : 0)) * d.W + (ok ? iw : 0)) * d.ld0 + lane * 4;
+#pragma unroll
+            for (int cb = 0; cb < CB; ++cb) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(xs_w + tap * Cin + cb * 128 + lane * 4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(xp + cb * 128), "r"(ok ? 16 : 0) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        float4 acc[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+            for (int cb = 0; cb < CB; ++cb) {
+                const float4 x4 = *reinterpret_cast<const float4*>(xs_w + tap * Cin + cb * 128 + lane * 4);
+                const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+                const float4* wr = reinterpret_cast<const float4*>(s_w) + (((tap * CB + cb) * 4 * NV) << 5) + lane;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) {
+                        const float4 wv = wr[(e * NV + j) << 5];
+                        acc[j].x = fmaf(xs[e], wv.x, acc[j].x);
+                        acc[j].y = fmaf(xs[e], wv.y, acc[j].y);
+                        acc[j].z = fmaf(xs[e], wv.z, acc[j].z);
+                        acc[j].w = fmaf(xs[e], wv.w, acc[j].w);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                acc[j].x += __shfl_xor_sync(0xffffffffu, acc[j].x, o);
+                acc[j].y += __shfl_xor_sync(0xffffffffu, acc[j].y, o);
+                acc[j].z += __shfl_xor_sync(0xffffffffu, acc[j].z, o);
+                acc[j].w += __shfl_xor_sync(0xffffffffu, acc[j].w, o);
+            }
+        }
+        if (lane < NV) {
+            float4 a = acc[0];
+#pragma unroll
+            for (int j = 1; j < NV; ++j) if (lane == j) a = acc[j];
+            const int nb = lane * 4;
+            float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = d.scale * (v[j] + ((d.bias != nullptr && nb + j < d.Cout) ? __ldg(d.bias + nb + j) : 0.f));
+            const bool vec = (d.y == nullptr || (((d.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15) == 0))) && (nb + 3 < d.Cout) &&
+                             (d.res == nullptr || (((d.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.res) & 15) == 0)));
+            conv_epilogue4(d, m, nb, v, vec);
+        }
+        __syncwarp();                                     // the slab is rewritten by the next pixel's copies
+    }
+    tl_end(tl);
+}
+
+template <int NV, int CB>
+static cudaError_t launch_head3x3(const bflow_conv_desc& d, int M, cudaStream_t st, unsigned long long* tls) {
+    const size_t smem = (size_t)9 * CB * 128 * NV * 16 + (size_t)8 * 9 * CB * 128 * 4;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_head3x3_kernel<NV, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    int g = ceil_div(M, 8);
+    if (g > 2 * 148) g = 2 * 148;
+    return launch_pdl(conv_head3x3_kernel<NV, CB>, dim3((unsigned)g), dim3(256), smem, st, d, M, tls);
 }
 }  // namespace bflow
 
@@ -329,17 +446,148 @@ extern "C" int bflow_conv2d_small_n(const bflow_conv_desc* dp, void* stream) {
     const int nv = (d.Cout + 3) / 4;
     dim3 grid((unsigned)bflow::ceil_div(M, 8));
     cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t le = cudaSuccess;
+    unsigned long long* tls = bflow::timeline_next_slot("conv_small_n");
+    if (d.KH == 3 && d.KW == 3 && d.stride == 1 && d.pad_h == 1 && d.pad_w == 1 && nv <= 2 && (d.c0 == 128 || d.c0 == 256)) {
+        if (nv == 1) le = d.c0 == 128 ? bflow::launch_head3x3<1, 1>(d, M, st, tls) : bflow::launch_head3x3<1, 2>(d, M, st, tls);
+        else le = d.c0 == 128 ? bflow::launch_head3x3<2, 1>(d, M, st, tls) : bflow::launch_head3x3<2, 2>(d, M, st, tls);
+        if (le != cudaSuccess) {
+            bflow::set_error(cudaGetErrorString(le));
+            return BFLOW_ERR_CUDA;
+        }
+        return bflow::check_launch("bflow_conv2d_small_n(head3x3)");
+    }
     switch (nv) {
-        case 1: bflow::conv_small_n_kernel<1><<<grid, 256, 0, st>>>(d, M); break;
-        case 2: bflow::conv_small_n_kernel<2><<<grid, 256, 0, st>>>(d, M); break;
-        case 3: bflow::conv_small_n_kernel<3><<<grid, 256, 0, st>>>(d, M); break;
-        case 4: bflow::conv_small_n_kernel<4><<<grid, 256, 0, st>>>(d, M); break;
-        case 5: bflow::conv_small_n_kernel<5><<<grid, 256, 0, st>>>(d, M); break;
-        case 6: bflow::conv_small_n_kernel<6><<<grid, 256, 0, st>>>(d, M); break;
-        case 7: bflow::conv_small_n_kernel<7><<<grid, 256, 0, st>>>(d, M); break;
-        default: bflow::conv_small_n_kernel<8><<<grid, 256, 0, st>>>(d, M); break;
+        case 1: le = bflow::launch_pdl(bflow::conv_small_n_kernel<1>, grid, dim3(256), 0, st, d, M, tls); break;
+        case 2: le = bflow::launch_pdl(bflow::conv_small_n_kernel<2>, grid, dim3(256), 0, st, d, M, tls); break;
+        case 3: le = bflow::launch_pdl(bflow::conv_small_n_kernel<3>, grid, dim3(256), 0, st, d, M, tls); break;
+        case 4: le = bflow::launch_pdl(bflow::conv_small_n_kernel<4>, grid, dim3(256), 0, st, d, M, tls); break;
+        case 5: le = bflow::launch_pdl(bflow::conv_small_n_kernel<5>, grid, dim3(256), 0, st, d, M, tls); break;
+        case 6: le = bflow::launch_pdl(bflow::conv_small_n_kernel<6>, grid, dim3(256), 0, st, d, M, tls); break;
+        case 7: le = bflow::launch_pdl(bflow::conv_small_n_kernel<7>, grid, dim3(256), 0, st, d, M, tls); break;
+        default: le = bflow::launch_pdl(bflow::conv_small_n_kernel<8>, grid, dim3(256), 0, st, d, M, tls); break;
+    }
+    if (le != cudaSuccess) {
+        bflow::set_error(cudaGetErrorString(le));
+        return BFLOW_ERR_CUDA;
     }
     return bflow::check_launch("bflow_conv2d_small_n");
+}
+
+// ---------------------------------------------------------------------------------------------
+// 7x7 stride-1 convolution of a THIN input (Cin = 4, 8, ... 32) to 128 channels: convf1 of the motion encoder (update.py:91,
+// Bezier parameters 2*degree -> 128).  K = 49*Cin is too small and too ragged for the tensor-core tiles, and the generic CUDA-core
+// kernel gathers it element by element.  Here a CTA owns a 4x8 patch of output pixels; per chunk of 4 input channels the 49*4*128
+// weights (100 KB) sit in shared memory next to the (4+6)x(8+6) input patch; a thread owns 4 consecutive pixels x 4 output channels and,
+// per (channel, filter row), loads the 10 inputs its pixels need once and reuses them across the 7 filter columns: 112 FMAs per 17
+// shared-memory loads.
+// ---------------------------------------------------------------------------------------------
+namespace bflow {
+constexpr int TH_ROWS = 4, TH_COLS = 8, TH_CO = 128, TH_K = 7, TH_PR = TH_ROWS + TH_K - 1, TH_PC = TH_COLS + TH_K - 1;
+__global__ void __launch_bounds__(256) conv_thin7_kernel(const bflow_conv_desc d, unsigned long long* tl) {
+    extern __shared__ __align__(16) float th_smem[];
+    float* s_w = th_smem;                                    // [49][4][128]
+    float* s_x = th_smem + TH_K * TH_K * 4 * TH_CO;          // [4][TH_PR][TH_PC]
+    const int tid = threadIdx.x;
+    const int cg = tid & 31, r = tid >> 5;
+    const int prow = r >> 1, px0 = (r & 1) * 4;
+    const int tiles_x = (d.Wo + TH_COLS - 1) / TH_COLS, tiles_y = (d.Ho + TH_ROWS - 1) / TH_ROWS;
+    int bid = blockIdx.x;
+    const int tx = bid % tiles_x; bid /= tiles_x;
+    const int ty = bid % tiles_y;
+    const int n = bid / tiles_y;
+    const int oy0 = ty * TH_ROWS, ox0 = tx * TH_COLS;
+    tl_begin(tl);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int c0 = 0; c0 < d.c0; c0 += 4) {
+        __syncthreads();
+        // weights of this channel chunk: rows (tap*Cin + c0 + ch) of the packed [K][ldw] matrix
+        for (int i = tid; i < TH_K * TH_K * 4 * (TH_CO / 4); i += 256) {
+            const int row = i >> 5, c4 = i & 31;             // row = tap*4 + ch
+            const int tap = row >> 2, ch = row & 3;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<float4*>(s_w) + i);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(d.w + (size_t)(tap * d.c0 + c0 + ch) * d.ldw + c4 * 4) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (int i = tid; i < TH_PR * TH_PC; i += 256) {
+            const int yy = i / TH_PC, xx = i - yy * TH_PC;
+            const int iy = oy0 + yy - 3, ix = ox0 + xx - 3;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (iy >= 0 && iy < d.H && ix >= 0 && ix < d.W) v = *reinterpret_cast<const float4*>(d.x0 + (((size_t)n * d.H + iy) * d.W + ix) * d.ld0 + c0);
+            s_x[0 * TH_PR * TH_PC + i] = v.x;
+            s_x[1 * TH_PR * TH_PC + i] = v.y;
+            s_x[2 * TH_PR * TH_PC + i] = v.z;
+            s_x[3 * TH_PR * TH_PC + i] = v.w;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+#pragma unroll 1
+            for (int ky = 0; ky < TH_K; ++ky) {
+                float xr[10];
+                const float* xp = s_x + (ch * TH_PR + prow + ky) * TH_PC + px0;
+#pragma unroll
+                for (int i = 0; i < 10; ++i) xr[i] = xp[i];
+#pragma unroll
+                for (int kx = 0; kx < TH_K; ++kx) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(s_w + (((ky * TH_K + kx) * 4 + ch) * TH_CO) + cg * 4);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc[i][0] = fmaf(xr[i + kx], w4.x, acc[i][0]);
+                        acc[i][1] = fmaf(xr[i + kx], w4.y, acc[i][1]);
+                        acc[i][2] = fmaf(xr[i + kx], w4.z, acc[i][2]);
+                        acc[i][3] = fmaf(xr[i + kx], w4.w, acc[i][3]);
+                    }
+                }
+            }
+        }
+    }
+    const int oy = oy0 + prow;
+    const float4 b4 = d.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(d.bias + cg * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool vec = (d.y == nullptr || (((d.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15) == 0))) &&
+                     (d.res == nullptr || (((d.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.res) & 15) == 0)));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ox = ox0 + px0 + i;
+        if (oy < d.Ho && ox < d.Wo) {
+            float v[4] = {d.scale * (acc[i][0] + b4.x), d.scale * (acc[i][1] + b4.y), d.scale * (acc[i][2] + b4.z), d.scale * (acc[i][3] + b4.w)};
+            conv_epilogue4(d, (n * d.Ho + oy) * d.Wo + ox, cg * 4, v, vec);
+        }
+    }
+    tl_end(tl);
+}
+}  // namespace bflow
+
+extern "C" int bflow_conv2d_thin7(const bflow_conv_desc* dp, void* stream) {
+    BFLOW_REQUIRE(dp != nullptr, "conv_thin7: null descriptor");
+    const bflow_conv_desc& d = *dp;
+    BFLOW_REQUIRE(d.x0 != nullptr && d.w != nullptr, "conv_thin7: null tensor");
+    BFLOW_REQUIRE(d.c1 == 0 && d.c0 > 0 && d.c0 % 4 == 0 && d.ld0 % 4 == 0 && bflow::aligned16(d.x0), "conv_thin7: one aligned source, Cin % 4 == 0");
+    BFLOW_REQUIRE(d.KH == 7 && d.KW == 7 && d.stride == 1 && d.pad_h == 3 && d.pad_w == 3 && d.Ho == d.H && d.Wo == d.W, "conv_thin7: 7x7, stride 1, pad 3");
+    BFLOW_REQUIRE(d.Cout == bflow::TH_CO && d.ldw % 4 == 0 && d.ldw >= d.Cout && bflow::aligned16(d.w), "conv_thin7: Cout == 128, packed weights");
+    BFLOW_REQUIRE(d.bias == nullptr || bflow::aligned16(d.bias), "conv_thin7: bias alignment");
+    BFLOW_REQUIRE(d.epi == BFLOW_EPI_STD, "conv_thin7: standard epilogue only");
+    BFLOW_REQUIRE((d.y == nullptr || d.ldy >= d.Cout) && (d.res == nullptr || d.ldr >= d.Cout), "conv_thin7: bad output stride");
+    if (const char* msg = bflow::check_epilogue(d)) { bflow::set_error(msg); return BFLOW_ERR_INVALID; }
+    const long long tiles = (long long)d.N * ((d.Ho + bflow::TH_ROWS - 1) / bflow::TH_ROWS) * ((d.Wo + bflow::TH_COLS - 1) / bflow::TH_COLS);
+    BFLOW_REQUIRE(tiles > 0 && tiles < (1ll << 31), "conv_thin7: bad shape");
+    const size_t smem = (size_t)(bflow::TH_K * bflow::TH_K * 4 * bflow::TH_CO + 4 * bflow::TH_PR * bflow::TH_PC) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(bflow::conv_thin7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            bflow::set_error(cudaGetErrorString(e));
+            return BFLOW_ERR_CUDA;
+        }
+        configured = true;
+    }
+    bflow::conv_thin7_kernel<<<(unsigned)tiles, 256, smem, (cudaStream_t)stream>>>(d, bflow::timeline_next_slot("conv_thin7"));
+    return bflow::check_launch("bflow_conv2d_thin7");
 }
 
 // corr[bq, p] = sum_d f1[bq, d] * f2[b, d, p] / sqrt(D)   (models/raft_utils/corr.py:264-272)

@@ -15,6 +15,7 @@
 // K order: k-block = (tap, 64-channel block); the two concatenated sources are two tensor-map pairs.
 #include <cuda.h>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace bflow {
@@ -57,11 +58,8 @@ __device__ __forceinline__ bool t3_mbar_test_wait(uint32_t bar, uint32_t parity)
     return ok != 0;
 }
 // development: per-role clock64 stamps of CTA 0 (bflow_tc3_trace); the pointer travels as a kernel parameter
-#ifdef BFLOW_T3_TRACE
+#define T3_CTA(i) do { if (p.cta != nullptr) p.cta[blockIdx.x * 8 + (i)] = global_ns(); } while (0)
 #define T3_TRACE(slot, idx) do { if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 256) p.trace[(slot) * 256 + (idx)] = clock64(); } while (0)
-#else
-#define T3_TRACE(slot, idx) do { } while (0)
-#endif
 // bounded: a protocol bug sets the error word instead of hanging the GPU
 __device__ __forceinline__ void t3_mbar_wait(uint32_t bar, uint32_t parity, int* err) {
 #pragma unroll 1
@@ -132,6 +130,9 @@ struct T3Params {
     int M, n_mtiles, n_ntiles, ntaps, ncb0, ncb1, nkb;
     float acc_scale;
     long long* trace;
+    unsigned long long* tl;
+    unsigned long long* cta;   // development (bflow_tc3_cta_trace): [gridDim.x][8] globaltimer stamps of ONE chosen launch
+    int staged;   // every CTA owns exactly one tile: the epilogue goes through shared memory (coalesced, batched global accesses)
     int dbg;      // development switches (bflow_tc3_debug): 1 no TMA loads, 2 no MMA, 4 no epilogue stores, 8 one MMA per k-step
 };
 
@@ -162,6 +163,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
     const int lane = tid & 31;
     const int n_tiles = p.n_mtiles * p.n_ntiles;
 
+    if (tid == 0) T3_TRACE(5, 255);              // CTA start
+    if (tid == 0) T3_CTA(0);
+    tl_begin(p.tl);
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             t3_mbar_init(full_bar(s), 1);      // the producer's arrive.expect_tx (+ TMA bytes)
@@ -182,6 +186,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
     t3_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    // PDL: everything above touched only shared memory / TMEM; let the next kernel's CTAs set themselves up on idle SMs, then
+    // wait for the previous kernel's results before the first global access
+    pdl_trigger();
+    pdl_wait();
+    if (tid == 0) T3_TRACE(3, 255);              // prologue done
+    if (tid == 0) T3_CTA(1);
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer ------------------------------------------------
@@ -204,8 +214,13 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                         const uint32_t ph = (it / STAGES) & 1u;
                         t3_mbar_wait(empty_bar(s), ph ^ 1u, err);
                         T3_TRACE(0, it);
+                        if (it == 0) T3_CTA(2);
                         const uint32_t stage = smem_base + (uint32_t)s * STAGE_BYTES;
                         const uint32_t bar = full_bar(s);
+                        if (p.dbg & 1) {                 // development: no loads (MMA + epilogue path alone)
+                            t3_mbar_arrive(bar);
+                            continue;
+                        }
                         t3_mbar_arrive_expect_tx(bar, TX_BYTES);
                         const bool src0 = cb < p.ncb0;
                         const int cc = (src0 ? cb : cb - p.ncb0) * 64;
@@ -233,6 +248,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 t3_mbar_wait(full_bar(s), ph, err);
                 t3_fence_after();
                 if (lane == 0) T3_TRACE(1, it);
+                if (lane == 0 && it == 0) T3_CTA(3);
                 if (lane == 0) {
                     const uint32_t a_hi = smem_base + (uint32_t)s * STAGE_BYTES;
                     const uint32_t a_lo = a_hi + T3_A_BYTES;
@@ -240,6 +256,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                     const uint32_t b_lo = b_hi + B_BYTES;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
+                        if ((p.dbg & 2) && (kb > 0 || k > 0)) break;      // development: one MMA per tile (load path alone)
                         const uint32_t ko = (uint32_t)k * 32u;
                         const uint64_t dah = t3_umma_desc(a_hi + ko), dal = t3_umma_desc(a_lo + ko);
                         const uint64_t dbh = t3_umma_desc(b_hi + ko);
@@ -255,6 +272,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                     }
                     t3_commit(empty_bar(s));
                     if (kb == p.nkb - 1) t3_commit(tfull_bar(acc));
+                    if (kb == p.nkb - 1) T3_CTA(4);
                     T3_TRACE(2, it);
                 }
                 __syncwarp();
@@ -275,6 +293,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
         const bool aligned = (d.y == nullptr || (((d.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15) == 0))) &&
                              (d.res == nullptr || (((d.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.res) & 15) == 0)));
         const float post = d.scale;
+        const bool wide16 = d.y16_hi != nullptr && (d.ldy16 & 7) == 0 && ((reinterpret_cast<uintptr_t>(d.y16_hi) | reinterpret_cast<uintptr_t>(d.y16_lo)) & 15) == 0;
         uint32_t lt = 0;
         int bias_tile = -1;
         // fused InstanceNorm statistics: per-CTA partial (sum, sum of squares) of the current image in shared memory, flushed with
@@ -318,9 +337,75 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
             t3_mbar_wait(tfull_bar(acc), aph, err);
             t3_fence_after();
             if (warp == 2 && lane == 0) T3_TRACE(3, lt);
+            if (warp == 2 && lane == 0) T3_CTA(5);
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_COLS + (uint32_t)(chalf * HALF);
             const int nb0 = n0 + chalf * HALF;
-            if (nb0 < d.Cout) {                      // warp-uniform
+            if (p.staged) {
+                // Single-tile CTA: the pipeline stages are idle once tmem_full has fired (every TMA load was consumed, every MMA retired), so the
+                // fp32 tile is parked there, [128][BN + 4].  Then the 256 epilogue threads walk it row-major, 4 channels per thread: a warp
+                // touches 2-4 whole rows per instruction (full sectors) instead of 32 rows x 16 bytes, and the residual / gate operands of
+                // EPI_BATCH groups are loaded together before the first store (one L2 round trip per batch, not per group).
+                constexpr int PITCH = BN + 4;
+                constexpr int C4 = BN / 4;
+                constexpr int EPI_BATCH = 4;
+                float* T = reinterpret_cast<float*>(smem_raw + (smem_base - t3_smem_u32(smem_raw)));
+                {
+                    float* trow = T + (quad * 32 + lane) * PITCH + chalf * HALF;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < HALF; c0 += 32) {         // 32 columns at a time keeps the register count down
+                        float v[32];
+                        t3_tmem_ld16_nowait(taddr + (uint32_t)c0, v);
+                        t3_tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), v + 16);
+                        if (STACK) {
+                            float u[32];
+                            t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0), u);
+                            t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0 + 16), u + 16);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) v[c] += u[c];
+                        } else {
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        }
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + chalf * HALF + c0 + c);
+                            *reinterpret_cast<float4*>(trow + c0 + c) = make_float4(post * fmaf(v[c], p.acc_scale, b4.x), post * fmaf(v[c + 1], p.acc_scale, b4.y),
+                                                                                    post * fmaf(v[c + 2], p.acc_scale, b4.z), post * fmaf(v[c + 3], p.acc_scale, b4.w));
+                        }
+                    }
+                }
+                t3_fence_before();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const int mt0 = m_tile * T3_BM;
+#pragma unroll 1
+                for (int base = etid; base < T3_BM * C4; base += 256 * EPI_BATCH) {
+                    EpiPre pre[EPI_BATCH];
+                    float4 val[EPI_BATCH];
+                    bool ok[EPI_BATCH], vec[EPI_BATCH];
+#pragma unroll
+                    for (int u = 0; u < EPI_BATCH; ++u) {
+                        const int idx = base + u * 256;
+                        const int row = idx / C4, c = (idx - row * C4) * 4;
+                        const int mm = mt0 + row, nn = n0 + c;
+                        ok[u] = idx < T3_BM * C4 && mm < p.M && nn < d.Cout;
+                        vec[u] = aligned && nn + 3 < d.Cout;
+                        if (ok[u]) {
+                            val[u] = *reinterpret_cast<const float4*>(T + row * PITCH + c);
+                            conv_epilogue4_prefetch(d, mm, nn, vec[u], pre[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < EPI_BATCH; ++u) {
+                        const int idx = base + u * 256;
+                        const int row = idx / C4, c = (idx - row * C4) * 4;
+                        if (ok[u]) {
+                            float t4[4] = {val[u].x, val[u].y, val[u].z, val[u].w};
+                            conv_epilogue4_finish(d, mt0 + row, n0 + c, t4, vec[u], pre[u]);
+                        }
+                    }
+                }
+                if (lane == 0) t3_mbar_arrive(tempty_bar(acc));
+            } else if (nb0 < d.Cout) {                      // warp-uniform
                 float v[HALF];
 #pragma unroll
                 for (int c = 0; c < HALF; c += 16) t3_tmem_ld16_nowait(taddr + (uint32_t)c, v + c);
@@ -439,8 +524,21 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                                 for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(yrow + j) = make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
                             }
                             if (d.y16_hi != nullptr) {
+                                if (wide16) {            // 16-byte stores: half as many store requests per row
 #pragma unroll
-                                for (int j = 0; j < 16; j += 4) store_split4(d.y16_hi, d.y16_lo, (size_t)m * d.ldy16 + nb + j, w[j], w[j + 1], w[j + 2], w[j + 3]);
+                                    for (int j = 0; j < 16; j += 8) {
+                                        uint4 h4, l4;
+                                        split2(w[j], w[j + 1], h4.x, l4.x);
+                                        split2(w[j + 2], w[j + 3], h4.y, l4.y);
+                                        split2(w[j + 4], w[j + 5], h4.z, l4.z);
+                                        split2(w[j + 6], w[j + 7], h4.w, l4.w);
+                                        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y16_hi) + (size_t)m * d.ldy16 + nb + j) = h4;
+                                        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y16_lo) + (size_t)m * d.ldy16 + nb + j) = l4;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 16; j += 4) store_split4(d.y16_hi, d.y16_lo, (size_t)m * d.ldy16 + nb + j, w[j], w[j + 1], w[j + 2], w[j + 3]);
+                                }
                             }
                         } else {
                             // GRU gate epilogues and ragged / unaligned tails
@@ -458,10 +556,14 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 if (lane == 0) t3_mbar_arrive(tempty_bar(acc));
             }
             if (warp == 2 && lane == 0) T3_TRACE(5, lt);
+            if (warp == 2 && lane == 0) T3_CTA(6);
         }
         if (d.stats != nullptr) flush_stats(cur_img, stat_n0);
     }
     __syncthreads();
+    if (tid == 0) T3_TRACE(4, 255);              // CTA end
+    if (tid == 0) T3_CTA(7);
+    tl_end(p.tl);
     if (warp == 1) {
         t3_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -487,8 +589,19 @@ static EncodeIm2colFn get_encode_im2col() {
 }
 
 static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
 static int g_tc3_debug = 0;
 static long long* g_tc3_trace = nullptr;
+static unsigned long long* g_tc3_cta = nullptr;
+static int g_tc3_cta_nth = -1, g_tc3_cta_count = 0;
 
 template <int BN, int STAGES>
 static int launch_tc3(const CUtensorMap* maps, const bflow_conv_desc& d, const void* wtc, const T3Params& p, int* err, cudaStream_t stream) {
@@ -502,15 +615,14 @@ static int launch_tc3(const CUtensorMap* maps, const bflow_conv_desc& d, const v
         }
         configured = true;
     }
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
-    }
     const int n_tiles = p.n_mtiles * p.n_ntiles;
-    const int grid = n_tiles < g_num_sms ? n_tiles : g_num_sms;
-    conv_tc3_kernel<BN, STAGES><<<grid, T3_THREADS, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], d, reinterpret_cast<const uint8_t*>(wtc), p, err);
+    const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
+    cudaError_t le = launch_pdl(conv_tc3_kernel<BN, STAGES>, dim3(grid), dim3(T3_THREADS), smem, stream, maps[0], maps[1], maps[2], maps[3], d,
+                                reinterpret_cast<const uint8_t*>(wtc), p, err);
+    if (le != cudaSuccess) {
+        set_error(cudaGetErrorString(le));
+        return BFLOW_ERR_CUDA;
+    }
     return check_launch("bflow_conv2d_nhwc_tc3");
 }
 
@@ -530,8 +642,9 @@ __global__ void split_f16_kernel(const float* __restrict__ src, int ld, __half* 
 constexpr int I2C_ROWS = 32;
 __global__ void __launch_bounds__(256) im2col_split16_kernel(const float* __restrict__ src, int C_total, int c_off, int cin, int H, int W, int Ho, int Wo,
                                                              int KH, int KW, int stride, int pad_h, int pad_w, float scale, float shift,
-                                                             __half* __restrict__ hi, __half* __restrict__ lo, int ld16, long long rows) {
-    extern __shared__ float patch[];              // [I2C_ROWS][ld16 + 1] floats, then the tap table: int off[ld16], int khkw[ld16]
+                                                             __half* __restrict__ hi, __half* __restrict__ lo, int ld16, long long rows, unsigned long long* tl) {
+    extern __shared__ float patch[];
+    tl_begin(tl);              // [I2C_ROWS][ld16 + 1] floats, then the tap table: int off[ld16], int khkw[ld16]
     const int pitch = ld16 + 1;
     const int K = KH * KW * cin;
     int* t_off = reinterpret_cast<int*>(patch + I2C_ROWS * pitch);
@@ -588,6 +701,7 @@ __global__ void __launch_bounds__(256) im2col_split16_kernel(const float* __rest
         *reinterpret_cast<uint4*>(hi + (size_t)(row0 + r) * ld16 + ck * 8) = h4;
         *reinterpret_cast<uint4*>(lo + (size_t)(row0 + r) * ld16 + ck * 8) = l4;
     }
+    tl_end(tl);
 }
 
 }  // namespace bflow
@@ -610,11 +724,20 @@ extern "C" int bflow_im2col_split16(const float* src, int C_total, int c_off, in
         configured = true;
     }
     bflow::im2col_split16_kernel<<<(unsigned)g, 256, smem, (cudaStream_t)stream>>>(src, C_total, c_off, cin, H, W, Ho, Wo, KH, KW, stride, pad_h, pad_w, scale, shift,
-                                                                                reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), ld16, rows);
+                                                                                reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), ld16, rows,
+                                                                                bflow::timeline_next_slot("im2col_split16"));
     return bflow::check_launch("bflow_im2col_split16");
 }
 
 extern "C" void bflow_tc3_trace(long long* device_buf_6x256) { bflow::g_tc3_trace = device_buf_6x256; }
+
+// development: the nth tc3 launch from now on writes per-CTA stamps {start, prologue done, first TMA issued, first stage full, last commit,
+// accumulator ready, epilogue done, end} (globaltimer ns) into buf[grid][8]
+extern "C" void bflow_tc3_cta_trace(void* buf, int nth) {
+    bflow::g_tc3_cta = reinterpret_cast<unsigned long long*>(buf);
+    bflow::g_tc3_cta_nth = nth;
+    bflow::g_tc3_cta_count = 0;
+}
 
 extern "C" void bflow_tc3_debug(int flags) { bflow::g_tc3_debug = flags; }
 
@@ -682,7 +805,21 @@ extern "C" int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* dp, const void* maps
     p.nkb = p.ntaps * (p.ncb0 + p.ncb1);
     p.acc_scale = acc_scale;
     p.dbg = bflow::g_tc3_debug;
+    {
+        const int sms = bflow::num_sms();
+        static int staged_on = -1;
+        if (staged_on < 0) {
+            const char* e = getenv("BFLOW_TC3_STAGED");
+            staged_on = e == nullptr ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1));
+        }
+        // measured on B200 (tools/timeline.py): the shared-memory pass pays for itself when the epilogue LOADS something per element (GRU
+        // gates, residuals) or the tile is ragged; a plain store-only epilogue is ~2 us faster straight from registers
+        const bool wants = d.epi != BFLOW_EPI_STD || d.res != nullptr || d.res16_hi != nullptr || (d.Cout % 16) != 0 || staged_on == 2;
+        p.staged = (staged_on && wants && d.stats == nullptr && p.n_mtiles * p.n_ntiles <= sms) ? 1 : 0;
+    }
     p.trace = bflow::g_tc3_trace;
+    p.cta = (bflow::g_tc3_cta != nullptr && bflow::g_tc3_cta_count++ == bflow::g_tc3_cta_nth) ? bflow::g_tc3_cta : nullptr;
+    p.tl = bflow::timeline_next_slot(bn == 64 ? "tc3_64" : bn == 128 ? "tc3_128" : "tc3_256");
     alignas(64) CUtensorMap tm[4];
     memcpy(tm, maps, sizeof(tm));
     cudaStream_t st = (cudaStream_t)stream;

@@ -15,6 +15,7 @@
 //   phase 3  NHWC: the warp writes its query's 81 contiguous floats (coalesced 324 B)
 //            NCHW: taps are transposed through shared memory so that each channel row receives 32
 //            consecutive pixels (128 B segments)
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace bflow {
@@ -157,16 +158,83 @@ __global__ void __launch_bounds__(LK_WARPS * 32) corr_lookup_kernel(const bflow_
 constexpr int LK2_WARPS = 8;
 constexpr int LK2_PITCH = 20;      // floats per patch row in shared memory (16 used; 20 spreads the tap reads over banks)
 
-__global__ void __launch_bounds__(LK2_WARPS * 32) corr_lookup_tiled_kernel(const bflow_lookup_desc d, const long long n_units, const int slots_per_group) {
+// one unit = (query pixel bq, slot): fetch the 3x3..4x4 tiles under the 10x10 window, blend the 81 taps, store them
+__device__ __forceinline__ void lookup_unit(const bflow_lookup_desc& d, const unsigned bq, const unsigned b, const unsigned q, const float gx,
+                                            const float gy, const int slot, float* ps, const int (&soff)[3], const int lane, const int Q) {
+    const int tcA = lane & 3, rgA = lane >> 2;            // tile column, patch row 0..7   (second float4: patch row + 8)
+    const int trA = rgA >> 2, rrA = rgA & 3;              // tile row 0..1 (+2 for the second float4), row inside the tile
+    const int hl = d.hl[slot], wl = d.wl[slot];
+    const int t = d.target[slot];
+    float cx, cy;
+    if (d.coords != nullptr) {
+        const float* c = d.coords + (((size_t)t * d.B + b) * 2) * Q + q;
+        cx = __ldg(c);
+        cy = __ldg(c + Q);
+    } else {
+        // coords1 = pixel grid + sum_i coef[t][i] * P_i   (raft.py:180-181, bezier.py:165-186)
+        const float* prm = d.params + (size_t)bq * d.params_ld;
+        float fxv = 0.f, fyv = 0.f;
+        for (int k = 0; k < d.degree; ++k) {
+            const float ck = d.coef[t][k];
+            fxv = fmaf(ck, __ldg(prm + k), fxv);
+            fyv = fmaf(ck, __ldg(prm + d.degree + k), fyv);
+        }
+        cx = gx + fxv;
+        cy = gy + fyv;
+    }
+    const float inv_scale = d.inv_scale[slot];
+    // anything farther than the window from the plane samples zeros; clamp to keep the int cast defined
+    cx = fminf(fmaxf(cx * inv_scale, -16.f), (float)wl + 16.f);
+    cy = fminf(fmaxf(cy * inv_scale, -16.f), (float)hl + 16.f);
+    const float flx = floorf(cx), fly = floorf(cy);
+    const float fx = cx - flx, fy = cy - fly;
+    const int x0 = (int)flx - 4, y0 = (int)fly - 4;
+    const int tx0 = x0 >> 2, ty0 = y0 >> 2, ox = x0 & 3, oy = y0 & 3;
+    const int ntx = ((ox + 9) >> 2) + 1, nty = ((oy + 9) >> 2) + 1;   // 3 or 4 tiles per axis
+    const int tw = (wl + 3) >> 2, th = (hl + 3) >> 2;
+    const float* pl = d.vol[slot] + (size_t)bq * (size_t)(tw * th * 16);
+
+    float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+    {
+        const int txx = tx0 + tcA;
+        const bool colok = tcA < ntx && txx >= 0 && txx < tw;
+        const int tya = ty0 + trA, tyb = ty0 + trA + 2;
+        if (colok && tya >= 0 && tya < th) va = __ldg(reinterpret_cast<const float4*>(pl + ((tya * tw + txx) << 4) + (rrA << 2)));
+        if (colok && (trA + 2) < nty && tyb >= 0 && tyb < th) vb = __ldg(reinterpret_cast<const float4*>(pl + ((tyb * tw + txx) << 4) + (rrA << 2)));
+    }
+    __syncwarp();                                     // previous unit's tap reads are done
+    *reinterpret_cast<float4*>(ps + rgA * LK2_PITCH + tcA * 4) = va;
+    *reinterpret_cast<float4*>(ps + (rgA + 8) * LK2_PITCH + tcA * 4) = vb;
+    __syncwarp();
+    const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+    const float* f0 = ps + oy * LK2_PITCH + ox;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        if (lane + 32 * j < 81) {
+            const float* f = f0 + soff[j];
+            const float val = w00 * f[0] + w01 * f[1] + w10 * f[LK2_PITCH] + w11 * f[LK2_PITCH + 1];
+            if (d.out16_hi != nullptr)
+                store_split1(d.out16_hi, d.out16_lo, (size_t)bq * d.out16_ld + slot * 81 + lane + 32 * j, val);
+            else
+                d.out[(size_t)bq * d.out_ld + slot * 81 + lane + 32 * j] = val;
+        }
+    }
+}
+
+// FLAT = false: a warp walks query pixels (stride = warps in the grid) and, per pixel, the slots of its blockIdx.y group (no division
+//               in the inner loop) -- the bandwidth regime (many pixels).
+// FLAT = true:  units (pixel, slot) are dealt round-robin to the warps of a one-wave grid -- the batch-1 regime, where the launch is a few
+//               latency chains long and an uneven tail (a partial second wave of CTAs) would double it.
+template <bool FLAT>
+__global__ void __launch_bounds__(LK2_WARPS * 32) corr_lookup_tiled_kernel(const bflow_lookup_desc d, const long long n_units, const int slots_per_group, unsigned long long* tl) {
     __shared__ __align__(16) float patch[LK2_WARPS][16 * LK2_PITCH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = d.n_slots;
     const int Q = d.h * d.w;
     float* ps = patch[warp];
-
-    // lane-constant geometry: slot A = lane, slot B = lane + 32 of the 64 (tile row, tile column) float4 slots
-    const int tcA = lane & 3, rgA = lane >> 2;            // tile column, patch row 0..7   (slot B: patch row + 8)
-    const int trA = rgA >> 2, rrA = rgA & 3;              // tile row 0..1 (+2 for slot B), row inside the tile
+    tl_begin(tl);
+    pdl_trigger();
+    pdl_wait();
     int soff[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -174,78 +242,32 @@ __global__ void __launch_bounds__(LK2_WARPS * 32) corr_lookup_tiled_kernel(const
         const int iy = k / 9, ix = k - iy * 9;
         soff[j] = iy * LK2_PITCH + ix;
     }
-
-    // a warp walks query pixels (stride = warps in the grid) and, per pixel, all S slots: no division in the inner loop
-    const unsigned n_bq = (unsigned)(n_units / S);
-    for (unsigned bq = blockIdx.x * LK2_WARPS + warp; bq < n_bq; bq += gridDim.x * LK2_WARPS) {
-        const unsigned b = bq / (unsigned)Q;
-        const unsigned q = bq - b * (unsigned)Q;
-        const unsigned qy = q / (unsigned)d.w;
-        const float gx = (float)(q - qy * (unsigned)d.w), gy = (float)qy;
-        const float* prm = d.params + (size_t)bq * d.params_ld;
-        float* o = d.out + (size_t)bq * d.out_ld;
-        const int s_beg = (int)blockIdx.y * slots_per_group, s_end = min(S, s_beg + slots_per_group);
-        o += s_beg * 81;
-
+    if (FLAT) {
+        const unsigned nu = (unsigned)n_units, nw = gridDim.x * LK2_WARPS;
 #pragma unroll 1
-        for (int slot = s_beg; slot < s_end; ++slot, o += 81) {
-            const int hl = d.hl[slot], wl = d.wl[slot];
-            const int t = d.target[slot];
-            float cx, cy;
-            if (d.coords != nullptr) {
-                const float* c = d.coords + (((size_t)t * d.B + b) * 2) * Q + q;
-                cx = __ldg(c);
-                cy = __ldg(c + Q);
-            } else {
-                float fxv = 0.f, fyv = 0.f;
-                for (int k = 0; k < d.degree; ++k) {
-                    const float ck = d.coef[t][k];
-                    fxv = fmaf(ck, __ldg(prm + k), fxv);
-                    fyv = fmaf(ck, __ldg(prm + d.degree + k), fyv);
-                }
-                cx = gx + fxv;
-                cy = gy + fyv;
-            }
-            const float inv_scale = d.inv_scale[slot];
-            cx = fminf(fmaxf(cx * inv_scale, -16.f), (float)wl + 16.f);
-            cy = fminf(fmaxf(cy * inv_scale, -16.f), (float)hl + 16.f);
-            const float flx = floorf(cx), fly = floorf(cy);
-            const float fx = cx - flx, fy = cy - fly;
-            const int x0 = (int)flx - 4, y0 = (int)fly - 4;
-            const int tx0 = x0 >> 2, ty0 = y0 >> 2, ox = x0 & 3, oy = y0 & 3;
-            const int ntx = ((ox + 9) >> 2) + 1, nty = ((oy + 9) >> 2) + 1;   // 3 or 4 tiles per axis
-            const int tw = (wl + 3) >> 2, th = (hl + 3) >> 2;
-            const float* pl = d.vol[slot] + (size_t)bq * (size_t)(tw * th * 16);
-
+        for (unsigned u = blockIdx.x * LK2_WARPS + warp; u < nu; u += nw) {
+            const unsigned bq = u / (unsigned)S;
+            const int slot = (int)(u - bq * (unsigned)S);
+            const unsigned b = bq / (unsigned)Q;
+            const unsigned q = bq - b * (unsigned)Q;
+            const unsigned qy = q / (unsigned)d.w;
+            lookup_unit(d, bq, b, q, (float)(q - qy * (unsigned)d.w), (float)qy, slot, ps, soff, lane, Q);
+        }
+    } else {
+        const unsigned n_bq = (unsigned)(n_units / S);
+        for (unsigned bq = blockIdx.x * LK2_WARPS + warp; bq < n_bq; bq += gridDim.x * LK2_WARPS) {
+            const unsigned b = bq / (unsigned)Q;
+            const unsigned q = bq - b * (unsigned)Q;
+            const unsigned qy = q / (unsigned)d.w;
+            const float gx = (float)(q - qy * (unsigned)d.w), gy = (float)qy;
+            const int s_beg = (int)blockIdx.y * slots_per_group, s_end = min(S, s_beg + slots_per_group);
             // (a two-deep software pipeline over the slots was measured 10 % slower: 60 registers cost more occupancy than the
             //  extra loads in flight gain)
-            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-            {
-                const int txx = tx0 + tcA;
-                const bool colok = tcA < ntx && txx >= 0 && txx < tw;
-                const int tya = ty0 + trA, tyb = ty0 + trA + 2;
-                if (colok && tya >= 0 && tya < th) va = __ldg(reinterpret_cast<const float4*>(pl + ((tya * tw + txx) << 4) + (rrA << 2)));
-                if (colok && (trA + 2) < nty && tyb >= 0 && tyb < th) vb = __ldg(reinterpret_cast<const float4*>(pl + ((tyb * tw + txx) << 4) + (rrA << 2)));
-            }
-            __syncwarp();                                     // previous unit's tap reads are done
-            *reinterpret_cast<float4*>(ps + rgA * LK2_PITCH + tcA * 4) = va;
-            *reinterpret_cast<float4*>(ps + (rgA + 8) * LK2_PITCH + tcA * 4) = vb;
-            __syncwarp();
-            const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
-            const float* f0 = ps + oy * LK2_PITCH + ox;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                if (lane + 32 * j < 81) {
-                    const float* f = f0 + soff[j];
-                    const float val = w00 * f[0] + w01 * f[1] + w10 * f[LK2_PITCH] + w11 * f[LK2_PITCH + 1];
-                    if (d.out16_hi != nullptr)
-                        store_split1(d.out16_hi, d.out16_lo, (size_t)bq * d.out16_ld + slot * 81 + lane + 32 * j, val);
-                    else
-                        o[lane + 32 * j] = val;
-                }
-            }
+#pragma unroll 1
+            for (int slot = s_beg; slot < s_end; ++slot) lookup_unit(d, bq, b, q, gx, gy, slot, ps, soff, lane, Q);
         }
     }
+    tl_end(tl);
 }
 
 }  // namespace bflow
@@ -272,16 +294,41 @@ extern "C" int bflow_corr_lookup(const bflow_lookup_desc* dp, void* stream) {
     if (d.tiled && d.out_nhwc) {
         BFLOW_REQUIRE(BQ * d.n_slots < (1ll << 31), "lookup: too many units");
         const long long n_units = BQ * d.n_slots;
-        long long g = bflow::ceil_div_ll(BQ, bflow::LK2_WARPS);
-        const long long cap = 148ll * 8 * 8;
-        if (g > cap) g = cap;
-        // few query pixels (batch 1): split the slots over blockIdx.y so that every SM still holds a full set of warps
-        long long groups = bflow::ceil_div_ll(148ll * 48, BQ);
-        if (groups < 1) groups = 1;
-        if (groups > d.n_slots) groups = d.n_slots;
-        const int spg = (int)bflow::ceil_div_ll(d.n_slots, groups);
-        dim3 grid2((unsigned)g, (unsigned)bflow::ceil_div(d.n_slots, spg));
-        bflow::corr_lookup_tiled_kernel<<<grid2, bflow::LK2_WARPS * 32, 0, (cudaStream_t)stream>>>(d, n_units, spg);
+        static int mode = -1, occ = 0, sms = 0;
+        if (mode < 0) {
+            const char* e = getenv("BFLOW_LK_FLAT");
+            mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bflow::corr_lookup_tiled_kernel<true>, bflow::LK2_WARPS * 32, 0);
+            if (sms <= 0) sms = 148;
+            if (occ <= 0) occ = 6;
+        }
+        cudaError_t le;
+        unsigned long long* tls = bflow::timeline_next_slot("corr_lookup");
+        const long long resident_warps = (long long)sms * occ * bflow::LK2_WARPS;
+        if (mode == 1 && n_units <= 8 * resident_warps) {
+            // one wave of CTAs, units dealt round-robin (at most 8 units per warp; beyond that the per-pixel walk below is as balanced)
+            long long g = bflow::ceil_div_ll(n_units, bflow::LK2_WARPS);
+            if (g > (long long)sms * occ) g = (long long)sms * occ;
+            le = bflow::launch_pdl(bflow::corr_lookup_tiled_kernel<true>, dim3((unsigned)g), dim3(bflow::LK2_WARPS * 32), 0, (cudaStream_t)stream, d, n_units, 0, tls);
+        } else {
+            long long g = bflow::ceil_div_ll(BQ, bflow::LK2_WARPS);
+            const long long cap = 148ll * 8 * 8;
+            if (g > cap) g = cap;
+            // few query pixels: split the slots over blockIdx.y so that every SM still holds a full set of warps
+            long long groups = bflow::ceil_div_ll(148ll * 48, BQ);
+            if (groups < 1) groups = 1;
+            if (groups > d.n_slots) groups = d.n_slots;
+            const int spg = (int)bflow::ceil_div_ll(d.n_slots, groups);
+            dim3 grid2((unsigned)g, (unsigned)bflow::ceil_div(d.n_slots, spg));
+            le = bflow::launch_pdl(bflow::corr_lookup_tiled_kernel<false>, grid2, dim3(bflow::LK2_WARPS * 32), 0, (cudaStream_t)stream, d, n_units, spg, tls);
+        }
+        if (le != cudaSuccess) {
+            bflow::set_error(cudaGetErrorString(le));
+            return BFLOW_ERR_CUDA;
+        }
         return bflow::check_launch("bflow_corr_lookup(tiled)");
     }
     dim3 grid((unsigned)bflow::ceil_div_ll(BQ, bflow::LK_QPB), (unsigned)d.n_slots);

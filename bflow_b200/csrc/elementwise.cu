@@ -125,9 +125,10 @@ __global__ void __launch_bounds__(256) instnorm_relu16_kernel(const float* __res
                                                               const float* __restrict__ r, int ldr, const double* __restrict__ sums_r,
                                                               const void* __restrict__ r16h, const void* __restrict__ r16l, int ldr16,
                                                               float* __restrict__ out, int ldo, void* __restrict__ o16h, void* __restrict__ o16l, int ldo16,
-                                                              int HW, int C, float eps) {
+                                                              int HW, int C, float eps, unsigned long long* tl) {
     __shared__ float mu_a[IN_MAXC], rs_a[IN_MAXC], mu_r[IN_MAXC], rs_r[IN_MAXC];
     const int n = blockIdx.y;
+    tl_begin(tl);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         double s = sums_a[((size_t)n * C + c) * 2], ss = sums_a[((size_t)n * C + c) * 2 + 1];
         double m = s / HW;
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(256) instnorm_relu16_kernel(const float* __res
         if (out != nullptr) *reinterpret_cast<float4*>(out + pix * ldo + c) = make_float4(o[0], o[1], o[2], o[3]);
         if (o16h != nullptr) store_split4(o16h, o16l, pix * ldo16 + c, o[0], o[1], o[2], o[3]);
     }
+    tl_end(tl);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -377,7 +379,7 @@ extern "C" int bflow_instnorm_relu16(const float* a, int lda, const double* sums
     BFLOW_REQUIRE(r != nullptr || sums_r == nullptr, "instnorm16: residual sums without fp32 residual");
     dim3 grid(ceil_div(HW, IN_CHUNK), N);
     instnorm_relu16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, lda, sums_a, r, ldr, sums_r, r16_hi, r16_lo, ldr16, out, ldo, out16_hi, out16_lo, ldo16,
-                                                                   HW, C, eps);
+                                                                   HW, C, eps, timeline_next_slot("instnorm_relu16"));
     return check_launch("bflow_instnorm_relu16");
 }
 

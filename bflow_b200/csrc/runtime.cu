@@ -1,6 +1,7 @@
 // Error plumbing and trivial entry points of the C ABI (include/bflow_b200.h).
 #include <string.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace bflow {
@@ -16,6 +17,23 @@ int check_launch(const char* what) {
         return BFLOW_ERR_CUDA;
     }
     return BFLOW_OK;
+}
+static unsigned long long* g_tl_buf = nullptr;
+static int g_tl_cap = 0, g_tl_next = 0;
+static char g_tl_names[4096][24];
+unsigned long long* timeline_next_slot(const char* name) {
+    if (g_tl_buf == nullptr || g_tl_next >= g_tl_cap || g_tl_next >= 4096) return nullptr;
+    strncpy(g_tl_names[g_tl_next], name, 23);
+    g_tl_names[g_tl_next][23] = 0;
+    return g_tl_buf + 2 * (g_tl_next++);
+}
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("BFLOW_PDL");
+        on = (e != nullptr && strcmp(e, "1") == 0) ? 1 : 0;      // measured on B200: no gain inside the captured graph, so opt-in
+    }
+    return on == 1;
 }
 }  // namespace bflow
 
@@ -33,3 +51,15 @@ extern "C" int bflow_zero(void* ptr, unsigned long long bytes, void* stream) {
     }
     return BFLOW_OK;
 }
+
+// development: device buffer of `capacity` {start, end} pairs (caller initialises start = ~0, end = 0); nullptr switches it off.
+// Returns the number of slots handed out so far; bflow_timeline_name(i) names the launch that owns slot i.
+extern "C" int bflow_timeline(void* buf, int capacity) {
+    const int used = bflow::g_tl_next;
+    bflow::g_tl_buf = reinterpret_cast<unsigned long long*>(buf);
+    bflow::g_tl_cap = capacity;
+    bflow::g_tl_next = 0;
+    return used;
+}
+extern "C" int bflow_timeline_used(void) { return bflow::g_tl_next; }
+extern "C" const char* bflow_timeline_name(int i) { return (i >= 0 && i < bflow::g_tl_next) ? bflow::g_tl_names[i] : ""; }

@@ -119,8 +119,8 @@ class S16Recorder:
         if y16 is not None:
             d.y16_hi, d.y16_lo, d.ldy16 = y16[0].hi(y16[1]), y16[0].lo(y16[1]), y16[0].ld
         self.keep.append(d)
-        fn = lib.bflow_conv2d_small_n if kernel == 'small_n' else lib.bflow_conv2d_nhwc
-        name = 'conv_small_n' if kernel == 'small_n' else 'conv_simt'
+        fn = {'small_n': lib.bflow_conv2d_small_n, 'thin7': lib.bflow_conv2d_thin7}.get(kernel, lib.bflow_conv2d_nhwc)
+        name = {'small_n': 'conv_small_n', 'thin7': 'conv_thin7'}.get(kernel, 'conv_simt')
         self._add(fn, C.byref(d), label=f'{name} {c0}->{wt.cout} {wt.kh}x{wt.kw}/{wt.stride} M={N * Ho * Wo}',
                   flops=2.0 * N * Ho * Wo * wt.cout * wt.kh * wt.kw * c0)
         return Ho, Wo
@@ -414,7 +414,8 @@ class S16Recorder:
                 self.iter_len = len(self.launches) - self.iter_start
             # motion encoder (update.py:88-97): the Bezier branch (convf1 -> convf2) runs beside lookup -> convc1 -> convc2
             self._fork()
-            self._conv_simt16(U['convf1'], hx + poff * 4, 2 * deg, gw, B, h, w, y16=(f1_16, 0), act1='relu')
+            thin = U['convf1'].cout == 128 and (2 * deg) % 4 == 0 and poff % 4 == 0
+            self._conv_simt16(U['convf1'], hx + poff * 4, 2 * deg, gw, B, h, w, y16=(f1_16, 0), act1='relu', kernel='thin7' if thin else 'auto')
             self._conv3(U['convf2'], [(f1_16, 0, 128)], B, h, w, y16=(cb16, 192), act1='relu')
             self._main()
             self._add(L.bflow_corr_lookup, C.byref(ld))

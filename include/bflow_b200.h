@@ -140,6 +140,10 @@ int bflow_corr_volume_tc(const float* f1, int ld1, const void* f2_img, long long
 /* Direct convolution for tiny Cout (<= 32): one warp per output pixel, K split over lanes, shuffle reduction.
  * Same descriptor and packed weights as bflow_conv2d_nhwc (Bezier head conv2: 256 -> 2*degree, update.py:18). */
 int bflow_conv2d_small_n(const bflow_conv_desc* d, void* stream);
+/* 7x7 / stride 1 / pad 3 convolution of a thin input (Cin % 4 == 0) to exactly 128 channels on CUDA cores with the weights in
+ * shared memory: convf1 of the motion encoder, Bezier parameters -> 128 (update.py:91).  Same descriptor and packed fp32
+ * weights as bflow_conv2d_nhwc; standard epilogue only. */
+int bflow_conv2d_thin7(const bflow_conv_desc* d, void* stream);
 int bflow_conv2d_nhwc_tc(const bflow_conv_desc* d, const void* w_tc, int bn, float acc_scale, int* err, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -75,6 +75,8 @@ def main():
         tr = tr.cpu()
         t0 = int(tr[tr > 0].min())
         names = ['prod:empty-ok', 'mma:full-ok', 'mma:committed', 'epi:tfull-ok', 'epi:tmem-released', 'epi:tile-done']
+        print('cta start', int(tr[5, 255]) - t0, 'prologue done', int(tr[3, 255]) - t0, 'cta end', int(tr[4, 255]) - t0, '(SM cycles)')
+        tr[5, 255] = 0; tr[3, 255] = 0; tr[4, 255] = 0
         for r in range(6):
             vals = [int(v) - t0 for v in tr[r] if int(v) > 0][:40]
             print(f'{names[r]:18s}', vals)
