@@ -318,115 +318,151 @@ __global__ void __launch_bounds__(256) conv_small_n_kernel(const bflow_conv_desc
     }
     tl_end(tl);
 }
-// Same operator for the shape the Bezier head really has (3x3, stride 1, Cin = 128 or 256, Cout <= 8): the weights sit in shared memory,
-// a warp owns a pixel, lane l owns channels {4l..4l+3} + 128 i, and all 9 x (Cin/128) activation loads of a pixel are issued before the first
-// FMA -- one memory round trip per pixel instead of one per (tap, channel chunk).
-template <int NV, int CB>   // CB = Cin / 128
+// Same operator for the shape the Bezier head really has (3x3, stride 1, pad 1, Cin = 128 or 256, Cout <= 8).  Measured on B200: per-lane
+// loads from the 8 warps of a CTA move only ~9 B/clk per SM, and the warp-per-pixel kernel above reads every input row nine times.  Here a CTA
+// owns a 4x8 patch of output pixels: the 6x10 halo of input rows (1 KB each) and the whole weight matrix arrive by cp.async.bulk (the copy
+// engine is not bound by per-thread load slots), a warp owns 4 consecutive pixels, lane l owns channels l + 32 i -- activations are read with
+// conflict-free LDS.32, the weights of a (tap, channel) with one conflict-free LDS.128 shared by the 4 pixels.
+template <int NV, int CB>   // NV = ceil(Cout/4), CB = Cin / 128
 __global__ void __launch_bounds__(256) conv_head3x3_kernel(const bflow_conv_desc d, const int M, unsigned long long* tl) {
-    extern __shared__ __align__(16) float s_w[];          // [9][Cin][NV*4] weights, then 8 warp slabs of [9][Cin] inputs
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    extern __shared__ __align__(128) float hs[];          // [9*Cin][NV*4] weights (global order), then the [6][10][Cin] input patch
+    __shared__ __align__(8) unsigned long long bar;
     constexpr int Cin = CB * 128;
-    float* s_x = s_w + 9 * Cin * NV * 4;
+    constexpr int PR = 6, PC = 10;
+    float* s_w = hs;
+    float* s_x = hs + 9 * Cin * NV * 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = (d.Wo + 7) / 8, tiles_y = (d.Ho + 3) / 4;
+    int bid = blockIdx.x;
+    const int tx = bid % tiles_x; bid /= tiles_x;
+    const int ty = bid % tiles_y;
+    const int n = bid / tiles_y;
+    const int oy0 = ty * 4, ox0 = tx * 8;
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
     tl_begin(tl);
-    pdl_trigger();
-    // shared layout [tap][cb][e][j][lane]: channel c = cb*128 + lane*4 + e -- for a fixed (tap, cb, e, j) consecutive lanes read consecutive
-    // float4, so the LDS.128 in the inner loop are conflict-free
-    for (int i = threadIdx.x; i < 9 * Cin * NV; i += 256) {            // weights are constants of the model: no pdl_wait needed yet
-        const int row = i / NV, j = i - row * NV;
-        const int tap = row / Cin, c = row - tap * Cin;
-        const int cb = c >> 7, ln = (c & 127) >> 2, e = c & 3;
-        // cp.async: the whole fill is in flight at once (a load -> store loop would pay one L2 round trip per iteration)
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<float4*>(s_w) + ((((tap * CB + cb) * 4 + e) * NV + j) << 5) + ln);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(d.w + (size_t)row * d.ldw + 4 * j) : "memory");
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    pdl_wait();
     __syncthreads();
-    for (int m = blockIdx.x * 8 + warp; m < M; m += gridDim.x * 8) {
-        const int ow = m % d.Wo;
-        const int t = m / d.Wo;
-        const int oh = t % d.Ho;
-        const int n = t / d.Ho;
-        // the pixel's 9 x Cin inputs go to this warp's shared-memory slab with cp.async: all 9*CB 16-byte copies of a lane are in flight at
-        // once by construction (ptxas serialises plain loads to save registers); padding taps are zero-filled (src-size 0)
-        float* xs_w = s_x + warp * (9 * Cin);
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            const int ih = oh - 1 + tap / 3, iw = ow - 1 + tap % 3;
-            const bool ok = ih >= 0 && ih < d.H && iw >= 0 && iw < d.W;
-            const float* xp = d.x0 + (((size_t)n * d.H + (ok ? ih : 0)) * d.W + (ok ? iw : 0)) * d.ld0 + lane * 4;
-#pragma unroll
-            for (int cb = 0; cb < CB; ++cb) {
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(xs_w + tap * Cin + cb * 128 + lane * 4);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(xp + cb * 128), "r"(ok ? 16 : 0) : "memory");
-            }
+    // which patch pixels exist (the others are the zero padding): pixel i = py * PC + px
+    if (threadIdx.x < PR * PC) {
+        const int py = threadIdx.x / PC, px = threadIdx.x - py * PC;
+        const int iy = oy0 + py - 1, ix = ox0 + px - 1;
+        const bool ok = iy >= 0 && iy < d.H && ix >= 0 && ix < d.W;
+        float* dst = s_x + threadIdx.x * Cin;
+        if (ok) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(dst)),
+                         "l"(d.x0 + (((size_t)n * d.H + iy) * d.W + ix) * d.ld0), "r"(Cin * 4), "r"(bar_a)
+                         : "memory");
+        } else {
+            for (int c = 0; c < Cin; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
-        float4 acc[NV];
+    }
+    if (threadIdx.x == 64) {
+        // expected bytes: the weights + every in-image patch pixel
+        const int y_lo = max(oy0 - 1, 0), y_hi = min(oy0 + PR - 2, d.H - 1), x_lo = max(ox0 - 1, 0), x_hi = min(ox0 + PC - 2, d.W - 1);
+        const uint32_t npix = (uint32_t)(max(y_hi - y_lo + 1, 0) * max(x_hi - x_lo + 1, 0));
+        const uint32_t wbytes = 9u * Cin * NV * 16u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(wbytes + npix * Cin * 4u) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((uint32_t)__cvta_generic_to_shared(s_w)),
+                     "l"(d.w), "r"(wbytes), "r"(bar_a)
+                     : "memory");
+    }
+    __syncthreads();                                        // zero-filled padding pixels are visible
+    {
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(bar_a)
+                : "memory");
+        }
+    }
+    // warp -> 4 consecutive pixels of one tile row
+    const int prow = warp >> 1, pcol0 = (warp & 1) * 4;
+    float4 acc[4][NV];
 #pragma unroll
-        for (int j = 0; j < NV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int j = 0; j < NV; ++j) acc[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap - ky * 3;
+        const float* xrow = s_x + ((prow + ky) * PC + pcol0 + kx) * Cin + lane;
+        const float4* wrow = reinterpret_cast<const float4*>(s_w) + (size_t)(tap * Cin + lane) * NV;
 #pragma unroll
-            for (int cb = 0; cb < CB; ++cb) {
-                const float4 x4 = *reinterpret_cast<const float4*>(xs_w + tap * Cin + cb * 128 + lane * 4);
-                const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
-                const float4* wr = reinterpret_cast<const float4*>(s_w) + (((tap * CB + cb) * 4 * NV) << 5) + lane;
+        for (int i = 0; i < Cin / 32; ++i) {
+            float xv[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
+            for (int px = 0; px < 4; ++px) xv[px] = xrow[px * Cin + i * 32];
 #pragma unroll
-                    for (int j = 0; j < NV; ++j) {
-                        const float4 wv = wr[(e * NV + j) << 5];
-                        acc[j].x = fmaf(xs[e], wv.x, acc[j].x);
-                        acc[j].y = fmaf(xs[e], wv.y, acc[j].y);
-                        acc[j].z = fmaf(xs[e], wv.z, acc[j].z);
-                        acc[j].w = fmaf(xs[e], wv.w, acc[j].w);
-                    }
+            for (int j = 0; j < NV; ++j) {
+                const float4 wv = wrow[(size_t)i * 32 * NV + j];
+#pragma unroll
+                for (int px = 0; px < 4; ++px) {
+                    acc[px][j].x = fmaf(xv[px], wv.x, acc[px][j].x);
+                    acc[px][j].y = fmaf(xv[px], wv.y, acc[px][j].y);
+                    acc[px][j].z = fmaf(xv[px], wv.z, acc[px][j].z);
+                    acc[px][j].w = fmaf(xv[px], wv.w, acc[px][j].w);
                 }
             }
         }
+    }
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                acc[j].x += __shfl_xor_sync(0xffffffffu, acc[j].x, o);
-                acc[j].y += __shfl_xor_sync(0xffffffffu, acc[j].y, o);
-                acc[j].z += __shfl_xor_sync(0xffffffffu, acc[j].z, o);
-                acc[j].w += __shfl_xor_sync(0xffffffffu, acc[j].w, o);
+                acc[px][j].x += __shfl_xor_sync(0xffffffffu, acc[px][j].x, o);
+                acc[px][j].y += __shfl_xor_sync(0xffffffffu, acc[px][j].y, o);
+                acc[px][j].z += __shfl_xor_sync(0xffffffffu, acc[px][j].z, o);
+                acc[px][j].w += __shfl_xor_sync(0xffffffffu, acc[px][j].w, o);
             }
         }
-        if (lane < NV) {
-            float4 a = acc[0];
+    }
+    // lane (px * NV + j) finishes output group j of pixel px
+    if (lane < 4 * NV) {
+        const int px = lane / NV, j = lane - px * NV;
+        float4 a = acc[0][0];
 #pragma unroll
-            for (int j = 1; j < NV; ++j) if (lane == j) a = acc[j];
-            const int nb = lane * 4;
+        for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+            for (int jj = 0; jj < NV; ++jj)
+                if (pp == px && jj == j) a = acc[pp][jj];
+        const int oy = oy0 + prow, ox = ox0 + pcol0 + px;
+        if (oy < d.Ho && ox < d.Wo) {
+            const int m = (n * d.Ho + oy) * d.Wo + ox;
+            const int nb = j * 4;
             float v[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = d.scale * (v[j] + ((d.bias != nullptr && nb + j < d.Cout) ? __ldg(d.bias + nb + j) : 0.f));
+            for (int e = 0; e < 4; ++e) v[e] = d.scale * (v[e] + ((d.bias != nullptr && nb + e < d.Cout) ? __ldg(d.bias + nb + e) : 0.f));
             const bool vec = (d.y == nullptr || (((d.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15) == 0))) && (nb + 3 < d.Cout) &&
                              (d.res == nullptr || (((d.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.res) & 15) == 0)));
             conv_epilogue4(d, m, nb, v, vec);
         }
-        __syncwarp();                                     // the slab is rewritten by the next pixel's copies
     }
+    (void)M;
     tl_end(tl);
 }
 
 template <int NV, int CB>
 static cudaError_t launch_head3x3(const bflow_conv_desc& d, int M, cudaStream_t st, unsigned long long* tls) {
-    const size_t smem = (size_t)9 * CB * 128 * NV * 16 + (size_t)8 * 9 * CB * 128 * 4;
+    const size_t smem = (size_t)9 * CB * 128 * NV * 16 + (size_t)6 * 10 * CB * 128 * 4;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(conv_head3x3_kernel<NV, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    int g = ceil_div(M, 8);
-    if (g > 2 * 148) g = 2 * 148;
-    return launch_pdl(conv_head3x3_kernel<NV, CB>, dim3((unsigned)g), dim3(256), smem, st, d, M, tls);
+    const int g = d.N * ((d.Ho + 3) / 4) * ((d.Wo + 7) / 8);
+    conv_head3x3_kernel<NV, CB><<<(unsigned)g, 256, smem, st>>>(d, M, tls);
+    return cudaGetLastError();
 }
 }  // namespace bflow
 
@@ -448,7 +484,8 @@ extern "C" int bflow_conv2d_small_n(const bflow_conv_desc* dp, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t le = cudaSuccess;
     unsigned long long* tls = bflow::timeline_next_slot("conv_small_n");
-    if (d.KH == 3 && d.KW == 3 && d.stride == 1 && d.pad_h == 1 && d.pad_w == 1 && nv <= 2 && (d.c0 == 128 || d.c0 == 256)) {
+    if (d.KH == 3 && d.KW == 3 && d.stride == 1 && d.pad_h == 1 && d.pad_w == 1 && nv <= 2 && (d.c0 == 128 || d.c0 == 256) && d.ldw == nv * 4 &&
+        d.Ho == d.H && d.Wo == d.W) {
         if (nv == 1) le = d.c0 == 128 ? bflow::launch_head3x3<1, 1>(d, M, st, tls) : bflow::launch_head3x3<1, 2>(d, M, st, tls);
         else le = d.c0 == 128 ? bflow::launch_head3x3<2, 1>(d, M, st, tls) : bflow::launch_head3x3<2, 2>(d, M, st, tls);
         if (le != cudaSuccess) {

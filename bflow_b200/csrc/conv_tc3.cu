@@ -58,7 +58,7 @@ __device__ __forceinline__ bool t3_mbar_test_wait(uint32_t bar, uint32_t parity)
     return ok != 0;
 }
 // development: per-role clock64 stamps of CTA 0 (bflow_tc3_trace); the pointer travels as a kernel parameter
-#define T3_CTA(i) do { if (p.cta != nullptr) p.cta[blockIdx.x * 8 + (i)] = global_ns(); } while (0)
+#define T3_CTA(i) do { if (p.cta != nullptr) p.cta[blockIdx.x * 16 + (i)] = global_ns(); } while (0)
 #define T3_TRACE(slot, idx) do { if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 256) p.trace[(slot) * 256 + (idx)] = clock64(); } while (0)
 // bounded: a protocol bug sets the error word instead of hanging the GPU
 __device__ __forceinline__ void t3_mbar_wait(uint32_t bar, uint32_t parity, int* err) {
@@ -126,12 +126,19 @@ __device__ __forceinline__ void t3_tmem_ld16_nowait(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__host__ __device__ constexpr int t3_area_bytes(int bn, int stages) {
+    return bn <= 128 ? 224 * 1024 : stages * (2 * T3_A_BYTES + 2 * bn * 128);
+}
+__device__ __forceinline__ void t3_bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
 struct T3Params {
     int M, n_mtiles, n_ntiles, ntaps, ncb0, ncb1, nkb;
     float acc_scale;
     long long* trace;
     unsigned long long* tl;
-    unsigned long long* cta;   // development (bflow_tc3_cta_trace): [gridDim.x][8] globaltimer stamps of ONE chosen launch
+    unsigned long long* cta;   // development (bflow_tc3_cta_trace): [gridDim.x][16] globaltimer stamps of ONE chosen launch
     int staged;   // every CTA owns exactly one tile: the epilogue goes through shared memory (coalesced, batched global accesses)
     int dbg;      // development switches (bflow_tc3_debug): 1 no TMA loads, 2 no MMA, 4 no epilogue stores, 8 one MMA per k-step
 };
@@ -149,14 +156,18 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
     constexpr bool STACK = BN <= 128;
     constexpr int ACC_COLS = STACK ? 2 * BN : BN;
     constexpr int TMEM_COLS = 2 * ACC_COLS;                   // two accumulators
+    // data area: the pipeline stages; for BN <= 128 it is stretched to 224 KB so that the bulk-copy epilogue of a single-tile CTA (below) can
+    // park the fp32 tile and up to three operand tiles in it once the pipeline has drained
+    constexpr int AREA_BYTES = t3_area_bytes(BN, STAGES);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (t3_smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
+    const uint32_t bars = smem_base + AREA_BYTES;
     auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
     auto empty_bar = [&](int s) { return bars + 32u + 8u * (uint32_t)s; };
     auto tfull_bar = [&](int a) { return bars + 64u + 8u * (uint32_t)a; };
     auto tempty_bar = [&](int a) { return bars + 80u + 8u * (uint32_t)a; };
     const uint32_t tmem_slot = bars + 96u;
+    const uint32_t ebar = bars + 104u;          // bulk-copy epilogue: operand tiles have landed
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -171,6 +182,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
             t3_mbar_init(full_bar(s), 1);      // the producer's arrive.expect_tx (+ TMA bytes)
             t3_mbar_init(empty_bar(s), 1);     // one tcgen05.commit
         }
+        t3_mbar_init(ebar, 1);
         for (int a = 0; a < 2; ++a) {
             t3_mbar_init(tfull_bar(a), 1);     // one tcgen05.commit
             t3_mbar_init(tempty_bar(a), T3_EPI_WARPS);    // one arrive per epilogue warp
@@ -340,7 +352,157 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
             if (warp == 2 && lane == 0) T3_CTA(5);
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_COLS + (uint32_t)(chalf * HALF);
             const int nb0 = n0 + chalf * HALF;
-            if (p.staged) {
+            if (p.staged == 2) {
+                // Bulk-copy epilogue of a single-tile CTA.  Measured (tools/timeline.py --cta-label): ordinary loads / stores issued by the 8
+                // epilogue warps move ~9 bytes per clock per SM -- a 128x128 GRU epilogue took 13 us, longer than its main loop.  The
+                // pipeline stages are idle once tmem_full has fired, so: (1) one thread per tile row fetches the row of every per-element
+                // operand (hoisted GRU term, gate, state) with cp.async.bulk into the stage area; (2) meanwhile the accumulator goes
+                // TMEM -> registers -> T[128][BN+4]; (3) 256 threads walk the tile row-major out of shared memory and leave the results
+                // there (fp32 in place of an operand, split-fp16 planes in place of T); (4) one cp.async.bulk per row and output plane
+                // writes them back.  Global traffic never touches the LSU.
+                constexpr int PITCH = BN + 4;
+                constexpr int C4 = BN / 4;
+                constexpr int EPI_BATCH = 4;
+                constexpr int RPB = 256 * EPI_BATCH / C4;                   // tile rows per batch: 32 (BN 128), 64 (BN 64)
+                uint8_t* sb = smem_raw + (smem_base - t3_smem_u32(smem_raw));
+                float* T = reinterpret_cast<float*>(sb);
+                float* Rg = reinterpret_cast<float*>(sb + T3_BM * PITCH * 4);      // res, then fp32 output (unless GRU_Q)
+                float* Ag = Rg + T3_BM * BN;                                        // aux0: h (GRU_ZR, r tile) / z (GRU_Q)
+                float* Yg = Ag + T3_BM * BN;                                        // GRU_Q: h in, h out
+                const int mt0 = m_tile * T3_BM;
+                const int Cg = d.Cout >> 1;
+                const bool is_zr = d.epi == BFLOW_EPI_GRU_ZR, is_q = d.epi == BFLOW_EPI_GRU_Q;
+                const bool r_tile = is_zr && n0 >= Cg;
+                const bool hasR = d.res != nullptr, hasA = r_tile || is_q, hasY = is_q;
+                const bool out32 = d.y != nullptr;
+                const bool out16 = is_zr ? r_tile : d.y16_hi != nullptr;
+                float* Og = is_q ? Yg : Rg;
+                const int ncols = min(BN, d.Cout - n0);
+                const int vrows = min(T3_BM, p.M - mt0);
+                if (etid == 0) {
+                    const uint32_t per_row = (uint32_t)ncols * 4u * ((hasR ? 1u : 0u) + (hasA ? 1u : 0u) + (hasY ? 1u : 0u));
+                    t3_mbar_arrive_expect_tx(ebar, per_row * (uint32_t)vrows);
+                }
+                if (etid < vrows) {
+                    const size_t mm = (size_t)(mt0 + etid);
+                    const uint32_t nb = (uint32_t)ncols * 4u;
+                    if (hasR) t3_bulk_g2s(t3_smem_u32(Rg + etid * BN), d.res + mm * d.ldr + n0, nb, ebar);
+                    if (hasA) t3_bulk_g2s(t3_smem_u32(Ag + etid * BN), d.aux0 + mm * d.ld_aux0 + (is_zr ? n0 - Cg : n0), nb, ebar);
+                    if (hasY) t3_bulk_g2s(t3_smem_u32(Yg + etid * BN), d.y + mm * d.ldy + n0, nb, ebar);
+                }
+                {
+                    float* trow = T + (quad * 32 + lane) * PITCH + chalf * HALF;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < HALF; c0 += 32) {         // 32 columns at a time keeps the register count down
+                        float v[32];
+                        t3_tmem_ld16_nowait(taddr + (uint32_t)c0, v);
+                        t3_tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), v + 16);
+                        if (STACK) {
+                            float u[32];
+                            t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0), u);
+                            t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0 + 16), u + 16);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) v[c] += u[c];
+                        } else {
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        }
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + chalf * HALF + c0 + c);
+                            *reinterpret_cast<float4*>(trow + c0 + c) = make_float4(post * fmaf(v[c], p.acc_scale, b4.x), post * fmaf(v[c + 1], p.acc_scale, b4.y),
+                                                                                    post * fmaf(v[c + 2], p.acc_scale, b4.z), post * fmaf(v[c + 3], p.acc_scale, b4.w));
+                        }
+                    }
+                }
+                if (warp == 2 && lane == 0) T3_CTA(8);
+                t3_fence_before();
+                t3_mbar_wait(ebar, 0u, err);                    // operand rows have landed (async proxy writes, made visible by the barrier)
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (warp == 2 && lane == 0) T3_CTA(9);
+#pragma unroll 1
+                for (int rb = 0; rb < T3_BM; rb += RPB) {
+                    float4 val[EPI_BATCH], r4[EPI_BATCH], a4[EPI_BATCH], y4[EPI_BATCH];
+#pragma unroll
+                    for (int u = 0; u < EPI_BATCH; ++u) {
+                        const int idx = etid + u * 256;
+                        const int row = rb + idx / C4, c = (idx % C4) * 4;
+                        val[u] = *reinterpret_cast<const float4*>(T + row * PITCH + c);
+                        r4[u] = hasR ? *reinterpret_cast<const float4*>(Rg + row * BN + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        a4[u] = hasA ? *reinterpret_cast<const float4*>(Ag + row * BN + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        y4[u] = hasY ? *reinterpret_cast<const float4*>(Yg + row * BN + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");       // every T row of this batch has been read: its bytes now hold the fp16 planes
+                    uint8_t* o16h = reinterpret_cast<uint8_t*>(T + rb * PITCH);
+                    uint8_t* o16l = o16h + RPB * BN * 2;
+#pragma unroll
+                    for (int u = 0; u < EPI_BATCH; ++u) {
+                        const int idx = etid + u * 256;
+                        const int lrow = idx / C4, c = (idx % C4) * 4;
+                        const int row = rb + lrow;
+                        float o[4] = {val[u].x + r4[u].x, val[u].y + r4[u].y, val[u].z + r4[u].z, val[u].w + r4[u].w};
+                        float h[4];
+                        if (is_zr) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) o[j] = apply_act(o[j], BFLOW_ACT_SIGMOID);
+                            h[0] = o[0] * a4[u].x; h[1] = o[1] * a4[u].y; h[2] = o[2] * a4[u].z; h[3] = o[3] * a4[u].w;
+                        } else if (is_q) {
+                            const float zz[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w}, hh[4] = {y4[u].x, y4[u].y, y4[u].z, y4[u].w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                o[j] = (1.f - zz[j]) * hh[j] + zz[j] * fast_tanh(o[j]);
+                                h[j] = o[j];
+                            }
+                        } else {
+                            // standard epilogue without residual (host contract): act2 follows act1 directly
+                            if (slow1 || slow2) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) o[j] = apply_act(apply_act(o[j], d.act1), d.act2);      // r4 is zero here
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) o[j] = fmaxf(fmaxf(o[j], lo1), lo2);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) h[j] = o[j];
+                        }
+                        if (out32) *reinterpret_cast<float4*>(Og + row * BN + c) = make_float4(o[0], o[1], o[2], o[3]);
+                        if (out16) {
+                            uint2 hv, lv;
+                            split2(h[0], h[1], hv.x, lv.x);
+                            split2(h[2], h[3], hv.y, lv.y);
+                            *reinterpret_cast<uint2*>(o16h + (lrow * BN + c) * 2) = hv;
+                            *reinterpret_cast<uint2*>(o16l + (lrow * BN + c) * 2) = lv;
+                        }
+                    }
+                    if (warp == 2 && lane == 0 && rb / RPB < 5) T3_CTA(10 + rb / RPB);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the bulk-copy engine
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (etid < vrows) {
+                    const size_t mm = (size_t)(mt0 + etid);
+                    if (out32) t3_bulk_s2g(d.y + mm * d.ldy + n0, t3_smem_u32(Og + etid * BN), (uint32_t)ncols * 4u);
+                    if (out16) {
+                        const int b = etid / RPB, rr = etid - b * RPB;
+                        const uint32_t sh = t3_smem_u32(T + b * RPB * PITCH) + (uint32_t)(rr * BN * 2);
+                        __half* gh = reinterpret_cast<__half*>(is_zr ? d.aux1_16_hi : d.y16_hi);
+                        __half* gl = reinterpret_cast<__half*>(is_zr ? d.aux1_16_lo : d.y16_lo);
+                        const size_t off = mm * (size_t)(is_zr ? d.ld_aux1_16 : d.ldy16) + (is_zr ? n0 - Cg : n0);
+                        const int nc8 = ncols & ~7;             // bulk pieces are 16-byte multiples; a ragged tail (Cout % 8 = 4) goes out as plain stores
+                        if (nc8 > 0) {
+                            t3_bulk_s2g(gh + off, sh, (uint32_t)nc8 * 2u);
+                            t3_bulk_s2g(gl + off, sh + (uint32_t)(RPB * BN * 2), (uint32_t)nc8 * 2u);
+                        }
+                        if (nc8 < ncols) {
+                            const uint8_t* th = reinterpret_cast<const uint8_t*>(T + b * RPB * PITCH) + rr * BN * 2;
+                            *reinterpret_cast<uint2*>(gh + off + nc8) = *reinterpret_cast<const uint2*>(th + nc8 * 2);
+                            *reinterpret_cast<uint2*>(gl + off + nc8) = *reinterpret_cast<const uint2*>(th + RPB * BN * 2 + nc8 * 2);
+                        }
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                }
+                if (lane == 0) t3_mbar_arrive(tempty_bar(acc));
+            } else if (p.staged) {
                 // Single-tile CTA: the pipeline stages are idle once tmem_full has fired (every TMA load was consumed, every MMA retired), so the
                 // fp32 tile is parked there, [128][BN + 4].  Then the 256 epilogue threads walk it row-major, 4 channels per thread: a warp
                 // touches 2-4 whole rows per instruction (full sectors) instead of 32 rows x 16 bytes, and the residual / gate operands of
@@ -374,8 +536,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                         }
                     }
                 }
+                if (warp == 2 && lane == 0) T3_CTA(8);
                 t3_fence_before();
                 asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (warp == 2 && lane == 0) T3_CTA(9);
                 const int mt0 = m_tile * T3_BM;
 #pragma unroll 1
                 for (int base = etid; base < T3_BM * C4; base += 256 * EPI_BATCH) {
@@ -403,6 +567,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                             conv_epilogue4_finish(d, mt0 + row, n0 + c, t4, vec[u], pre[u]);
                         }
                     }
+                    if (warp == 2 && lane == 0 && base < 256 * EPI_BATCH * 5) T3_CTA(10 + base / (256 * EPI_BATCH));
                 }
                 if (lane == 0) t3_mbar_arrive(tempty_bar(acc));
             } else if (nb0 < d.Cout) {                      // warp-uniform
@@ -419,6 +584,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 } else {
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 }
+                if (warp == 2 && lane == 0) T3_CTA(8);
                 // the accumulator is in registers: hand the TMEM buffer back before the (slow) global stores
                 t3_fence_before();
                 __syncwarp();
@@ -571,6 +737,257 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Slab variant for the layer that dominates the encoders: 3x3 / stride 1 / pad 1, 64 -> 64 channels (extractor.py layer1, 59 % of the
+// encoder flops at 240x320).  Measured (tools/timeline.py --cta-label): the im2col kernel above moves 48 KB per k-block through L2 -> SM
+// for 384 tensor-pipe cycles of work -- 125 B/clk per SM against the ~42 B/clk every SM gets when all 148 pull -- so it runs at 30 % of
+// the tensor pipe.  Two changes cut the traffic 4x:
+//   * the whole weight image (9 taps x [hi|lo] x 64 x 64 fp16 = 144 KB) is loaded ONCE per CTA and stays in shared memory;
+//   * an output tile is an 8 (x) by 16 (y) patch of pixels, and for each filter column kw ONE halo slab of 8 x 18 pixels x 64 channels
+//     (TMA tiled mode, out-of-image rows / columns zero-filled = the convolution's padding) serves the three filter rows: row r of the
+//     slab is pixel (r / 8, r % 8), so filter row kh is the same slab advanced by 8 rows = 1024 bytes, which keeps the UMMA descriptor
+//     on a swizzle-atom boundary.  3 slabs x 36 KB per tile instead of 9 x 32 KB of im2col rows plus 9 x 16 KB of weights.
+// Roles as above: warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (thread = pixel row, half of the 64 channels), two TMEM accumulators.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SL_BN = 64;
+constexpr int SL_B_BYTES = 9 * 2 * SL_BN * 128;          // resident weights: 147456
+constexpr int SL_PLANE = 8 * 18 * 128;                   // one fp16 slab plane: 18432
+constexpr int SL_STAGE = 2 * SL_PLANE;                   // hi + lo
+constexpr int SL_STAGES = 2;
+
+struct SlabParams {
+    int tiles_x, tiles_y, n_tiles;
+    float acc_scale;
+    unsigned long long* tl;
+};
+
+__device__ __forceinline__ void sl_tma_tile(uint32_t dst, const CUtensorMap* map, int c, int x, int y, int n, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(x), "r"(y), "r"(n)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(T3_THREADS, 1)
+conv_slab64_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const bflow_conv_desc d,
+                   const uint8_t* __restrict__ wtc, const SlabParams p, int* err) {
+    constexpr int ACC_COLS = 2 * SL_BN;            // [hi*hi + lo*hi | hi*lo]
+    constexpr int TMEM_COLS = 2 * ACC_COLS;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (t3_smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bres = smem_base;
+    const uint32_t stage0 = smem_base + SL_B_BYTES;
+    const uint32_t bars = stage0 + SL_STAGES * SL_STAGE;
+    auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
+    auto empty_bar = [&](int s) { return bars + 32u + 8u * (uint32_t)s; };
+    auto tfull_bar = [&](int a) { return bars + 64u + 8u * (uint32_t)a; };
+    auto tempty_bar = [&](int a) { return bars + 80u + 8u * (uint32_t)a; };
+    const uint32_t tmem_slot = bars + 96u;
+    const uint32_t wbar = bars + 104u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    tl_begin(p.tl);
+    if (tid == 0) {
+        for (int s = 0; s < SL_STAGES; ++s) {
+            t3_mbar_init(full_bar(s), 1);
+            t3_mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            t3_mbar_init(tfull_bar(a), 1);
+            t3_mbar_init(tempty_bar(a), T3_EPI_WARPS);
+        }
+        t3_mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    t3_fence_before();
+    __syncthreads();
+    t3_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            t3_mbar_arrive_expect_tx(wbar, SL_B_BYTES);
+            for (int t = 0; t < 9; ++t) t3_bulk_g2s(bres + (uint32_t)t * (2 * SL_BN * 128), wtc + (size_t)t * (2 * SL_BN * 128), 2 * SL_BN * 128, wbar);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
+                const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+                const int x0 = tx * 8, y0 = ty * 16;
+                for (int kw = 0; kw < 3; ++kw, ++it) {
+                    const int s = (int)(it % SL_STAGES);
+                    const uint32_t ph = (it / SL_STAGES) & 1u;
+                    t3_mbar_wait(empty_bar(s), ph ^ 1u, err);
+                    const uint32_t st = stage0 + (uint32_t)s * SL_STAGE;
+                    t3_mbar_arrive_expect_tx(full_bar(s), SL_STAGE);
+                    sl_tma_tile(st, &map_hi, 0, x0 + kw - 1, y0 - 1, n, full_bar(s));
+                    sl_tma_tile(st + SL_PLANE, &map_lo, 0, x0 + kw - 1, y0 - 1, n, full_bar(s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(SL_BN >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
+        const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * SL_BN) >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
+        t3_mbar_wait(wbar, 0u, err);
+        uint32_t it = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
+            t3_mbar_wait(tempty_bar(acc), aph ^ 1u, err);
+            t3_fence_after();
+            const uint32_t tacc = tmem_base + acc * ACC_COLS;
+            for (int kw = 0; kw < 3; ++kw, ++it) {
+                const int s = (int)(it % SL_STAGES);
+                const uint32_t ph = (it / SL_STAGES) & 1u;
+                t3_mbar_wait(full_bar(s), ph, err);
+                t3_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_hi = stage0 + (uint32_t)s * SL_STAGE, a_lo = a_hi + SL_PLANE;
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const uint32_t b = bres + (uint32_t)(kh * 3 + kw) * (2 * SL_BN * 128);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t ko = (uint32_t)k * 32u;
+                            const uint64_t dbh = t3_umma_desc(b + ko);
+                            t3_umma(tacc, t3_umma_desc(a_hi + (uint32_t)kh * 1024u + ko), dbh, idesc2, (kw > 0 || kh > 0 || k > 0) ? 1u : 0u);
+                            t3_umma(tacc, t3_umma_desc(a_lo + (uint32_t)kh * 1024u + ko), dbh, idesc, 1u);
+                        }
+                    }
+                    t3_commit(empty_bar(s));
+                    if (kw == 2) t3_commit(tfull_bar(acc));
+                }
+                __syncwarp();
+            }
+        }
+        t3_fence_before();
+    } else {
+        const int quad = warp & 3, chalf = (warp - 2) >> 2, etid = tid - 64;
+        float* s_bias = reinterpret_cast<float*>(smem_raw + (bars - t3_smem_u32(smem_raw)) + 128);     // [64]
+        float* s_stat = s_bias + SL_BN;                                                                    // [2][64]
+        for (int j = etid; j < SL_BN; j += 256) {
+            s_bias[j] = d.bias != nullptr ? __ldg(d.bias + j) : 0.f;
+            s_stat[j] = 0.f;
+            s_stat[SL_BN + j] = 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float lo1 = d.act1 == BFLOW_ACT_RELU ? 0.f : -INFINITY, lo2 = d.act2 == BFLOW_ACT_RELU ? 0.f : -INFINITY;
+        const float post = d.scale;
+        int cur_img = -1;
+        auto flush_stats = [&](int img) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int j = etid; j < SL_BN; j += 256) {
+                if (img >= 0) {
+                    atomicAdd(d.stats + ((size_t)img * d.Cout + j) * 2, (double)s_stat[j]);
+                    atomicAdd(d.stats + ((size_t)img * d.Cout + j) * 2 + 1, (double)s_stat[SL_BN + j]);
+                }
+                s_stat[j] = 0.f;
+                s_stat[SL_BN + j] = 0.f;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        };
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
+            const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
+            const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+            const int row = quad * 32 + lane;
+            const int y = ty * 16 + (row >> 3), x = tx * 8 + (row & 7);
+            const bool valid = y < d.H;
+            const size_t m = ((size_t)n * d.H + y) * d.W + x;
+            if (d.stats != nullptr && n != cur_img) {
+                flush_stats(cur_img);
+                cur_img = n;
+            }
+            const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
+            t3_mbar_wait(tfull_bar(acc), aph, err);
+            t3_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_COLS + (uint32_t)(chalf * 32);
+            float v[32], u[32];
+            t3_tmem_ld16_nowait(taddr, v);
+            t3_tmem_ld16_nowait(taddr + 16u, v + 16);
+            t3_tmem_ld16_nowait(taddr + (uint32_t)SL_BN, u);
+            t3_tmem_ld16_nowait(taddr + (uint32_t)SL_BN + 16u, u + 16);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            t3_fence_before();
+            __syncwarp();
+            if (lane == 0) t3_mbar_arrive(tempty_bar(acc));
+            const int nb0 = chalf * 32;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = post * fmaf(v[c] + u[c], p.acc_scale, s_bias[nb0 + c]);
+            if (d.stats != nullptr) {
+                // column sums over the warp's 32 rows: butterfly transpose-reduce, 16 columns at a time (as in conv_tc3_kernel)
+#pragma unroll
+                for (int c = 0; c < 32; c += 16) {
+                    float sv[16], sq[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float xx = valid ? v[c + j] : 0.f;
+                        sv[j] = xx;
+                        sq[j] = xx * xx;
+                    }
+#pragma unroll
+                    for (int width = 8, bit = 16; width >= 1; width >>= 1, bit >>= 1) {
+                        const bool upper = (lane & bit) != 0;
+#pragma unroll
+                        for (int i = 0; i < width; ++i) {
+                            const float keep_s = upper ? sv[width + i] : sv[i], send_s = upper ? sv[i] : sv[width + i];
+                            const float keep_q = upper ? sq[width + i] : sq[i], send_q = upper ? sq[i] : sq[width + i];
+                            sv[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
+                            sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
+                        }
+                    }
+                    const float ts = sv[0] + __shfl_xor_sync(0xffffffffu, sv[0], 1);
+                    const float tq = sq[0] + __shfl_xor_sync(0xffffffffu, sq[0], 1);
+                    if ((lane & 1) == 0) {
+                        const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                        atomicAdd(s_stat + nb0 + c + col, ts);
+                        atomicAdd(s_stat + SL_BN + nb0 + c + col, tq);
+                    }
+                }
+            }
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], lo1);
+                if (d.res16_hi != nullptr) {
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) {
+                        const float4 r4 = load_split4(d.res16_hi, d.res16_lo, m * d.ldr16 + nb0 + c);
+                        v[c] += r4.x; v[c + 1] += r4.y; v[c + 2] += r4.z; v[c + 3] += r4.w;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], lo2);
+                if (d.y != nullptr) {
+                    float* yrow = d.y + m * d.ldy + nb0;
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(yrow + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                }
+                if (d.y16_hi != nullptr) {
+#pragma unroll
+                    for (int c = 0; c < 32; c += 8) {
+                        uint4 h4, l4;
+                        split2(v[c], v[c + 1], h4.x, l4.x);
+                        split2(v[c + 2], v[c + 3], h4.y, l4.y);
+                        split2(v[c + 4], v[c + 5], h4.z, l4.z);
+                        split2(v[c + 6], v[c + 7], h4.w, l4.w);
+                        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y16_hi) + m * d.ldy16 + nb0 + c) = h4;
+                        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y16_lo) + m * d.ldy16 + nb0 + c) = l4;
+                    }
+                }
+            }
+        }
+        if (d.stats != nullptr) flush_stats(cur_img);
+    }
+    __syncthreads();
+    tl_end(p.tl);
+    if (warp == 1) {
+        t3_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*, const int*,
@@ -605,7 +1022,7 @@ static int g_tc3_cta_nth = -1, g_tc3_cta_count = 0;
 
 template <int BN, int STAGES>
 static int launch_tc3(const CUtensorMap* maps, const bflow_conv_desc& d, const void* wtc, const T3Params& p, int* err, cudaStream_t stream) {
-    constexpr int smem = STAGES * (2 * T3_A_BYTES + 2 * BN * 128) + 128 + 3 * BN * 4 + 1024;
+    constexpr int smem = t3_area_bytes(BN, STAGES) + 128 + 3 * BN * 4 + 1024;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -815,7 +1232,30 @@ extern "C" int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* dp, const void* maps
         // measured on B200 (tools/timeline.py): the shared-memory pass pays for itself when the epilogue LOADS something per element (GRU
         // gates, residuals) or the tile is ragged; a plain store-only epilogue is ~2 us faster straight from registers
         const bool wants = d.epi != BFLOW_EPI_STD || d.res != nullptr || d.res16_hi != nullptr || (d.Cout % 16) != 0 || staged_on == 2;
-        p.staged = (staged_on && wants && d.stats == nullptr && p.n_mtiles * p.n_ntiles <= sms) ? 1 : 0;
+        const bool single = d.stats == nullptr && p.n_mtiles * p.n_ntiles <= sms;
+        p.staged = (staged_on && wants && single) ? 1 : 0;
+        // bulk-copy epilogue: every row piece must be a 16-byte multiple at a 16-byte aligned address
+        static int bulk_on = -1;
+        if (bulk_on < 0) {
+            const char* e = getenv("BFLOW_TC3_BULK");
+            bulk_on = (e != nullptr && e[0] == '0') ? 0 : 1;
+        }
+        auto a16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+        bool bulk = bulk_on && single && bn <= 128 && d.Cout % 4 == 0 && d.res16_hi == nullptr;
+        bulk = bulk && (d.y == nullptr || (a16(d.y) && d.ldy % 4 == 0)) && (d.res == nullptr || (a16(d.res) && d.ldr % 4 == 0));
+        if (d.epi == BFLOW_EPI_STD) {
+            bulk = bulk && d.res == nullptr && (d.y16_hi == nullptr || (a16(d.y16_hi) && a16(d.y16_lo) && d.ldy16 % 8 == 0));
+        } else if (d.epi == BFLOW_EPI_GRU_ZR) {
+            bulk = bulk && d.y != nullptr && a16(d.aux0) && d.ld_aux0 % 4 == 0 && d.aux1 == nullptr && d.aux1_16_hi != nullptr && a16(d.aux1_16_hi) &&
+                   a16(d.aux1_16_lo) && d.ld_aux1_16 % 8 == 0 && (d.Cout / 2) % bn == 0;
+        } else {
+            bulk = bulk && d.y != nullptr && a16(d.aux0) && d.ld_aux0 % 4 == 0 && (d.y16_hi == nullptr || (a16(d.y16_hi) && a16(d.y16_lo) && d.ldy16 % 8 == 0));
+        }
+        {   // the fp32 tile plus the operand / output tiles must fit the data area
+            const int regions = d.epi == BFLOW_EPI_GRU_Q ? 3 : (d.epi == BFLOW_EPI_GRU_ZR ? 2 : 1);
+            bulk = bulk && bflow::T3_BM * (bn + 4) * 4 + regions * bflow::T3_BM * bn * 4 <= bflow::t3_area_bytes(bn, 0);
+        }
+        if (bulk) p.staged = 2;
     }
     p.trace = bflow::g_tc3_trace;
     p.cta = (bflow::g_tc3_cta != nullptr && bflow::g_tc3_cta_count++ == bflow::g_tc3_cta_nth) ? bflow::g_tc3_cta : nullptr;
@@ -829,4 +1269,77 @@ extern "C" int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* dp, const void* maps
         case 256: return bflow::launch_tc3<256, 2>(tm, d, w_tc, p, err, st);
         default: bflow::set_error("conv_tc3: bn must be 64, 128 or 256"); return BFLOW_ERR_INVALID;
     }
+}
+
+namespace bflow {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+}  // namespace bflow
+
+// Tiled (not im2col) tensor map over a split-fp16 NHWC plane: dims {C, W, H, N}, box {64 channels, box_w, box_h, 1}, SWIZZLE_128B,
+// out-of-bounds elements read as zero.  Used by bflow_conv2d_slab64 with box 8 x 18.
+extern "C" int bflow_tma_tile_map(void* map_out, const void* base, int N, int H, int W, int C, int ld_halves, int box_w, int box_h) {
+    BFLOW_REQUIRE(map_out != nullptr && base != nullptr, "tma_tile_map: null argument");
+    BFLOW_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= 64 && ld_halves >= C && ld_halves % 8 == 0, "tma_tile_map: bad shape (C <= 64, ld a multiple of 8 halves)");
+    BFLOW_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && box_w > 0 && box_w <= 256 && box_h > 0 && box_h <= 256, "tma_tile_map: alignment / box");
+    static bflow::EncodeTiledFn enc = nullptr;
+    if (enc == nullptr) {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            enc = reinterpret_cast<bflow::EncodeTiledFn>(fp);
+    }
+    BFLOW_REQUIRE(enc != nullptr, "tma_tile_map: cuTensorMapEncodeTiled not available from the driver");
+    alignas(64) CUtensorMap tm;
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)ld_halves * 2, (cuuint64_t)W * ld_halves * 2, (cuuint64_t)H * W * ld_halves * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        bflow::set_error("tma_tile_map: cuTensorMapEncodeTiled failed");
+        return BFLOW_ERR_CUDA;
+    }
+    memcpy(map_out, &tm, sizeof(tm));
+    return BFLOW_OK;
+}
+
+// 3x3 / stride 1 / pad 1 convolution, exactly 64 -> 64 channels, split-fp16 input (ResidualBlock convs of layer1, extractor.py:49-53).
+// maps: two 128-byte tensor maps {hi, lo} from bflow_tma_tile_map(..., box_w 8, box_h 18).  w_tc: the bflow_conv2d_nhwc_tc3 weight image for
+// bn = 64 (tap-major k-blocks).  Epilogue: bias, act1, split residual, act2 (none / relu), fp32 and / or split output, fused InstanceNorm sums.
+extern "C" int bflow_conv2d_slab64(const bflow_conv_desc* dp, const void* maps, const void* w_tc, float acc_scale, int* err, void* stream) {
+    BFLOW_REQUIRE(dp != nullptr && maps != nullptr && w_tc != nullptr, "conv_slab64: null argument");
+    const bflow_conv_desc& d = *dp;
+    BFLOW_REQUIRE(d.c0 == 64 && d.c1 == 0 && d.Cout == 64 && d.KH == 3 && d.KW == 3 && d.stride == 1 && d.pad_h == 1 && d.pad_w == 1, "conv_slab64: 3x3/1 64->64 only");
+    BFLOW_REQUIRE(d.N > 0 && d.H > 0 && d.W > 0 && d.W % 8 == 0 && d.Ho == d.H && d.Wo == d.W, "conv_slab64: W must be a multiple of 8");
+    BFLOW_REQUIRE(d.epi == BFLOW_EPI_STD && d.res == nullptr && d.act1 <= BFLOW_ACT_RELU && d.act2 <= BFLOW_ACT_RELU, "conv_slab64: standard epilogue, none / relu, split residual only");
+    BFLOW_REQUIRE((d.y == nullptr || (d.ldy >= 64 && d.ldy % 4 == 0 && bflow::aligned16(d.y))), "conv_slab64: fp32 output alignment");
+    BFLOW_REQUIRE(d.y16_hi == nullptr || (d.y16_lo != nullptr && d.ldy16 % 8 == 0 && bflow::aligned16(d.y16_hi) && bflow::aligned16(d.y16_lo)), "conv_slab64: split output alignment");
+    BFLOW_REQUIRE(d.stats == nullptr || (d.act1 == BFLOW_ACT_NONE && d.act2 == BFLOW_ACT_NONE && d.res16_hi == nullptr), "conv_slab64: fused statistics need the plain epilogue");
+    if (const char* msg = bflow::check_epilogue(d)) { bflow::set_error(msg); return BFLOW_ERR_INVALID; }
+    BFLOW_REQUIRE((reinterpret_cast<uintptr_t>(w_tc) & 15) == 0, "conv_slab64: weight alignment");
+    bflow::SlabParams p;
+    p.tiles_x = d.W / 8;
+    p.tiles_y = (d.H + 15) / 16;
+    const long long nt = (long long)d.N * p.tiles_x * p.tiles_y;
+    BFLOW_REQUIRE(nt < (1ll << 31), "conv_slab64: too large");
+    p.n_tiles = (int)nt;
+    p.acc_scale = acc_scale;
+    p.tl = bflow::timeline_next_slot("slab64");
+    constexpr int smem = bflow::SL_B_BYTES + bflow::SL_STAGES * bflow::SL_STAGE + 128 + 3 * 64 * 4 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(bflow::conv_slab64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            bflow::set_error(cudaGetErrorString(e));
+            return BFLOW_ERR_CUDA;
+        }
+        configured = true;
+    }
+    alignas(64) CUtensorMap tm[2];
+    memcpy(tm, maps, sizeof(tm));
+    const int grid = p.n_tiles < bflow::num_sms() ? p.n_tiles : bflow::num_sms();
+    bflow::conv_slab64_kernel<<<grid, bflow::T3_THREADS, smem, (cudaStream_t)stream>>>(tm[0], tm[1], d, reinterpret_cast<const uint8_t*>(w_tc), p, err);
+    return bflow::check_launch("bflow_conv2d_slab64");
 }

@@ -94,6 +94,21 @@ class S16Recorder:
             d.aux1_16_hi, d.aux1_16_lo, d.ld_aux1_16 = aux1_16[0].hi(aux1_16[1]), aux1_16[0].lo(aux1_16[1]), aux1_16[0].ld
         self.keep.append(d)
         M = N * Ho * Wo
+        import os
+        if (wt.kh == 3 and wt.kw == 3 and wt.stride == 1 and (ph, pw) == (1, 1) and c0 == 64 and c1 == 0 and wt.cout == 64 and W % 8 == 0 and
+                epi == 'std' and res is None and act1 in ('none', 'relu') and act2 in ('none', 'relu') and M >= 148 * 128 and
+                os.environ.get('BFLOW_SLAB', '1') != '0'):
+            # layer1 of the encoders: weights resident in shared memory + halo slabs (bflow_conv2d_slab64)
+            img, acc_scale = wt.tc3_image(64, c0)
+            maps = (C.c_uint8 * 256)()
+            src = srcs[0][0]
+            for j, base in enumerate((src.hi(srcs[0][1]), src.lo(srcs[0][1]))):
+                check(lib.bflow_tma_tile_map(C.addressof(maps) + 128 * j, base, N, H, W, 64, src.ld, 8, 18), 'tma_tile_map')
+            self.keep.append(maps)
+            self._add(lib.bflow_conv2d_slab64, C.byref(d), C.addressof(maps), img.data_ptr(), acc_scale, self.eng.err.data_ptr(),
+                      label=f'conv_slab64 64->64 3x3/1 M={M}', flops=2.0 * M * 64 * 9 * 64)
+            self.n_tc += 1
+            return Ho, Wo
         bn = choose_bn(wt.cout, (M + 127) // 128)
         img, acc_scale = wt.tc3_image(bn, c0)
         maps = self._maps(srcs, N, H, W, wt)

@@ -164,6 +164,18 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         check(_lib.lib().bflow_conv2d_nhwc_tc3(C.byref(d), C.addressof(maps), wtc.data_ptr(), bn, acc_scale, err.data_ptr(), _stream()), 'conv2d_tc3')
         if int(err.item()) != 0:
             raise RuntimeError('bflow_conv2d_nhwc_tc3: pipeline wait timed out inside the kernel')
+    elif backend == 'slab64':
+        x16 = split_f16(xh, 64)
+        maps = (C.c_uint8 * 256)()
+        L = _lib.lib()
+        for j in range(2):
+            check(L.bflow_tma_tile_map(C.addressof(maps) + 128 * j, x16[j].data_ptr(), N, H, W, 64, 64, 8, 18), 'tma_tile_map')
+        wtc, acc_scale = pack_conv_weight_tc(weight, 64, block_per_tap=True)
+        err = torch.zeros(1, device=x.device, dtype=torch.int32)
+        d.x0 = None
+        check(L.bflow_conv2d_slab64(C.byref(d), C.addressof(maps), wtc.data_ptr(), acc_scale, err.data_ptr(), _stream()), 'conv2d_slab64')
+        if int(err.item()) != 0:
+            raise RuntimeError('bflow_conv2d_slab64: pipeline wait timed out inside the kernel')
     elif backend == 'tc':
         wtc, acc_scale = pack_conv_weight_tc(weight, bn)
         err = torch.zeros(1, device=x.device, dtype=torch.int32)

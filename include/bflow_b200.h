@@ -118,6 +118,12 @@ int bflow_conv2d_tc_supported(const bflow_conv_desc* d);
 int bflow_tma_im2col_map(void* map_out_128B, const void* base_fp16, int N, int H, int W, int C, int ld_halves,
                          int KH, int KW, int stride, int pad_h, int pad_w);
 int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* d, const void* maps, const void* w_tc, int bn, float acc_scale, int* err, void* stream);
+/* Slab variant for 3x3 / stride 1 / pad 1, exactly 64 -> 64 channels, W % 8 == 0 (ResidualBlock convs of layer1, extractor.py:49-53):
+ * weights resident in shared memory, one 8 x 18 halo slab per filter column serves the three filter rows (4x less L2 -> SM traffic than
+ * the im2col kernel).  maps: {hi, lo} tensor maps from bflow_tma_tile_map(..., box_w 8, box_h 18); w_tc: the tc3 weight image for bn = 64.
+ * Standard epilogue only (none / relu, split residual, fp32 and / or split output, fused InstanceNorm sums). */
+int bflow_tma_tile_map(void* map_out_128B, const void* base_fp16, int N, int H, int W, int C, int ld_halves, int box_w, int box_h);
+int bflow_conv2d_slab64(const bflow_conv_desc* d, const void* maps, const void* w_tc, float acc_scale, int* err, void* stream);
 /* im2col of a channel window of an NCHW fp32 tensor straight into split-fp16 rows (the 7x7 stride-2 encoder stems on few input
  * channels, extractor.py:112: K = KH*KW*cin is too thin per tap for 64-channel TMA boxes, so the patch matrix is materialised
  * once and the stem becomes a 1x1 tensor-core GEMM).  out[row, (kh*KW+kw)*cin + c] = scale*src[n, c_off+c, oh*s-ph+kh, ow*s-pw+kw] + shift

@@ -61,6 +61,18 @@ def test_conv2d_tensor_core_matches_torch(N, Cin, H, W, Cout, k, s, p, act, bn):
     assert (out - ref).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize('N,H,W,act', [(1, 16, 8, 'none'), (2, 40, 24, 'relu'), (3, 37, 16, 'none'), (5, 120, 160, 'relu')])
+def test_conv2d_slab64_matches_torch(N, H, W, act):
+    """Slab kernel (weights resident, halo slabs): 3x3/1, 64 -> 64; ragged tile rows (H % 16 != 0), several images, multi-tile CTAs."""
+    x = torch.randn(N, 64, H, W, generator=g(1))
+    w = torch.randn(64, 64, 3, 3, generator=g(2)) / 24.0
+    b = torch.randn(64, generator=g(3))
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride=1, padding=1).float()
+    ref = torch.relu(ref) if act == 'relu' else ref
+    out = ops.conv2d(x.to(DEV), w.to(DEV), b.to(DEV), stride=1, padding=(1, 1), act=act, backend='slab64').cpu()
+    assert (out - ref).abs().max() < 1e-4
+
+
 def test_instance_norm_relu_variants():
     x = torch.randn(3, 96, 17, 23, generator=g(1)) * 3 + 1
     r = torch.randn(3, 96, 17, 23, generator=g(2))

@@ -48,7 +48,7 @@ def main():
         plan.load_inputs(vg, im, None)
         plan.launch_all()                      # eager warm-up, timeline off
         torch.cuda.synchronize()
-        cta = torch.zeros(148, 8, device=dev, dtype=torch.int64)
+        cta = torch.zeros(148, 16, device=dev, dtype=torch.int64)
         if a.cta_label:
             tc3l = [lab for (fn, _), (lab, _) in zip(plan.launches, plan.labels) if fn.__name__ == 'bflow_conv2d_nhwc_tc3']
             hits = [i for i, lab in enumerate(tc3l) if a.cta_label in lab]
@@ -76,7 +76,7 @@ def main():
     print(f'{a.preset} B={a.batch} {a.h}x{a.w} iters={a.iters}: graph replay {e0.elapsed_time(e1):.3f} ms; {n} instrumented launches of {plan.n_launches}; '
           f'span of instrumented launches {(int(t[:, 1].max()) - t0) / 1e6:.3f} ms')
     # label = instrumented launches in plan order (the plan's labels for those kernels)
-    inst = ('conv2d_nhwc_tc3', 'corr_lookup', 'conv2d_small_n', 'conv2d_thin7', 'conv2d_nhwc', 'instnorm_relu16', 'im2col_split16')
+    inst = ('conv2d_nhwc_tc3', 'conv2d_slab64', 'corr_lookup', 'conv2d_small_n', 'conv2d_thin7', 'conv2d_nhwc', 'instnorm_relu16', 'im2col_split16')
     labels = [lab for (fn, _), (lab, _) in zip(plan.launches, plan.labels) if fn.__name__.replace('bflow_', '') in inst]
     streams = [item[2] for item in plan.schedule if item[0] == 'launch' and plan.launches[item[1]][0].__name__.replace('bflow_', '') in inst]
     if len(labels) != n:
@@ -96,9 +96,11 @@ def main():
         print(f'per-CTA stamps of tc3 launch #{a.cta} ({tc3[a.cta] if a.cta < len(tc3) else "?"}), {c.shape[0]} CTAs, us from the first CTA start:')
         print('  cta   start prolog  1stTMA 1stfull lastMMA accrdy epidone    end')
         for i in range(c.shape[0]):
-            print(f'  {i:3d} ' + ' '.join(f'{(int(v) - c0) / 1e3:7.2f}' for v in c[i]))
-        cols = ['start', 'prolog', '1stTMA', '1stfull', 'lastMMA', 'accrdy', 'epidone', 'end']
+            print(f'  {i:3d} ' + ' '.join(f'{(int(v) - c0) / 1e3:7.2f}' for v in c[i] if int(v) > 0))
+        cols = ['start', 'prolog', '1stTMA', '1stfull', 'lastMMA', 'accrdy', 'epidone', 'end', 'tmem->reg', 'staged', 'batch0', 'batch1', 'batch2', 'batch3', 'batch4', '-']
         for j, nme in enumerate(cols):
+            if int(c[:, j].max()) == 0:
+                continue
             col = (c[:, j] - c0).double() / 1e3
             print(f'  {nme:8s} min {col.min():7.2f} median {col.median():7.2f} max {col.max():7.2f}')
     # per-label aggregate: in-kernel duration and the gap to the previous launch's end on the same stream
