@@ -101,7 +101,7 @@ class Engine:
         w1 = out['conv1']
         O, I, KH, KW = w1.oihw.shape
         if KH * KW * I <= 512:      # stem as a GEMM over the materialised patch matrix (engine_s16: 'im2col' stem)
-            kp = _ceil(KH * KW * I, 64)
+            kp = 256 if KH * KW * I <= 256 else _ceil(KH * KW * I, 64)      # bflow_conv2d_stem7 wants exactly 4 k-blocks
             wm = torch.zeros(O, kp, 1, 1, device=self.device, dtype=torch.float32)
             wm[:, :KH * KW * I, 0, 0] = w1.oihw.permute(0, 2, 3, 1).reshape(O, -1)
             wp, ldw = pack_conv_weight(wm)

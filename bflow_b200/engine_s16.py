@@ -146,6 +146,10 @@ class S16Recorder:
         from .engine import _ceil
         L, dev = self.eng.lib, self.eng.device
         shared = {} if shared is None else shared
+        import os
+        if 49 * cin <= 256 and W % 4 == 0 and os.environ.get('BFLOW_STEM7', '1') != '0':
+            # fused stem: input footprint -> patch matrix in shared memory -> tcgen05 (bflow_conv2d_stem7)
+            return dict(kind='stem7', src=src_nchw.data_ptr(), C_total=C_total, c_off=c_off, cin=cin, ns=ns, scale=scale, shift=shift)
         if 49 * cin <= 512:
             if 'buf' not in shared:      # one patch-matrix buffer per encoder call, reused window after window (same stream)
                 shared['buf'] = _S16(ns * (H // 2) * (W // 2), _ceil(49 * cin, 64), dev)
@@ -190,7 +194,24 @@ class S16Recorder:
         #   'tma'     cin >= 16 at an 8-aligned channel offset of a split-fp16 NHWC input: 7x7 im2col-TMA convolution
         #   'simt'    fp32 NHWC input on CUDA cores
         def stem(win, n0, ns, y=None, y16=None, act='none', stats=None):
-            if win['kind'] == 'im2col':
+            if win['kind'] == 'stem7':
+                wm = E['conv1_mat']
+                img, acc_scale = wm.tc3_image(64, wm.cin)
+                d = ConvDesc()
+                d.x0, d.c0, d.c1, d.bias = win['src'], win['cin'], 0, wm.b.data_ptr()
+                d.y, d.ldy = y, 64
+                d.N, d.H, d.W, d.Ho, d.Wo, d.Cout = ns, H, W, H2, W2, 64
+                d.KH, d.KW, d.stride, d.pad_h, d.pad_w = 7, 7, 2, 3, 3
+                d.act1, d.act2, d.scale, d.epi = ACT[act], 0, 1.0, 0
+                if y16 is not None:
+                    d.y16_hi, d.y16_lo, d.ldy16 = y16[0].hi(y16[1]), y16[0].lo(y16[1]), y16[0].ld
+                d.stats, d.stats_hw = stats, H2 * W2
+                self.keep.append(d)
+                self._add(L.bflow_conv2d_stem7, C.byref(d), img.data_ptr(), win['C_total'], win['c_off'],
+                          win.get('scale', 1.0), win.get('shift', 0.0), acc_scale, self.eng.err.data_ptr(),
+                          label=f'conv_stem7 {win["cin"]}->64 7x7/2 M={ns * H2 * W2}', flops=2.0 * ns * H2 * W2 * 64 * 49 * win['cin'])
+                self.n_tc += 1
+            elif win['kind'] == 'im2col':
                 wm = E['conv1_mat']
                 buf = win['buf']
                 self._add(L.bflow_im2col_split16, win['src'], win['C_total'], win['c_off'], win['cin'], ns, H, W, 7, 7, 2, 3, 3, win.get('scale', 1.0),

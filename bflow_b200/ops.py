@@ -164,6 +164,18 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         check(_lib.lib().bflow_conv2d_nhwc_tc3(C.byref(d), C.addressof(maps), wtc.data_ptr(), bn, acc_scale, err.data_ptr(), _stream()), 'conv2d_tc3')
         if int(err.item()) != 0:
             raise RuntimeError('bflow_conv2d_nhwc_tc3: pipeline wait timed out inside the kernel')
+    elif backend == 'stem7':
+        # x stays NCHW fp32; `scale` doubles as the input map x -> in_scale * x + in_shift via the `stem_affine` attribute of this function
+        in_scale, in_shift = getattr(conv2d, 'stem_affine', (1.0, 0.0))
+        L = _lib.lib()
+        wm = torch.zeros(O, 256, 1, 1, device=x.device, dtype=torch.float32)
+        wm[:, :KH * KW * Cin, 0, 0] = _f32c(weight, 'weight').permute(0, 2, 3, 1).reshape(O, -1)
+        wtc, acc_scale = pack_conv_weight_tc(wm, 64, block_per_tap=True)
+        err = torch.zeros(1, device=x.device, dtype=torch.int32)
+        d.x0 = x.data_ptr()
+        check(L.bflow_conv2d_stem7(C.byref(d), wtc.data_ptr(), Cin, 0, in_scale, in_shift, acc_scale, err.data_ptr(), _stream()), 'conv2d_stem7')
+        if int(err.item()) != 0:
+            raise RuntimeError('bflow_conv2d_stem7: pipeline wait timed out inside the kernel')
     elif backend == 'slab64':
         x16 = split_f16(xh, 64)
         maps = (C.c_uint8 * 256)()

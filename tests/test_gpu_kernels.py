@@ -73,6 +73,22 @@ def test_conv2d_slab64_matches_torch(N, H, W, act):
     assert (out - ref).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize('N,Cin,H,W,affine', [(1, 5, 32, 16, None), (2, 5, 96, 160, None), (2, 3, 64, 48, (2.0 / 255.0, -1.0)), (3, 4, 40, 24, None)])
+def test_conv2d_stem7_matches_torch(N, Cin, H, W, affine):
+    """Fused stem (TMA footprint -> patch matrix in shared memory -> tcgen05): 7x7/2, thin input; the affine input map must leave the padding at zero."""
+    x = torch.randn(N, Cin, H, W, generator=g(1)) if affine is None else torch.randint(0, 256, (N, Cin, H, W), generator=g(1)).float()
+    w = torch.randn(64, Cin, 7, 7, generator=g(2)) / (49 * Cin) ** 0.5
+    b = torch.randn(64, generator=g(3))
+    xin = x if affine is None else x * affine[0] + affine[1]
+    ref = torch.relu(F.conv2d(xin.double(), w.double(), b.double(), stride=2, padding=3).float())
+    ops.conv2d.stem_affine = affine or (1.0, 0.0)
+    try:
+        out = ops.conv2d(x.to(DEV), w.to(DEV), b.to(DEV), stride=2, padding=(3, 3), act='relu', backend='stem7').cpu()
+    finally:
+        ops.conv2d.stem_affine = (1.0, 0.0)
+    assert (out - ref).abs().max() < 1e-4
+
+
 def test_instance_norm_relu_variants():
     x = torch.randn(3, 96, 17, 23, generator=g(1)) * 3 + 1
     r = torch.randn(3, 96, 17, 23, generator=g(2))

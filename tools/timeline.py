@@ -76,7 +76,7 @@ def main():
     print(f'{a.preset} B={a.batch} {a.h}x{a.w} iters={a.iters}: graph replay {e0.elapsed_time(e1):.3f} ms; {n} instrumented launches of {plan.n_launches}; '
           f'span of instrumented launches {(int(t[:, 1].max()) - t0) / 1e6:.3f} ms')
     # label = instrumented launches in plan order (the plan's labels for those kernels)
-    inst = ('conv2d_nhwc_tc3', 'conv2d_slab64', 'corr_lookup', 'conv2d_small_n', 'conv2d_thin7', 'conv2d_nhwc', 'instnorm_relu16', 'im2col_split16')
+    inst = ('conv2d_nhwc_tc3', 'conv2d_slab64', 'conv2d_stem7', 'corr_lookup', 'conv2d_small_n', 'conv2d_thin7', 'conv2d_nhwc', 'instnorm_relu16', 'im2col_split16')
     labels = [lab for (fn, _), (lab, _) in zip(plan.launches, plan.labels) if fn.__name__.replace('bflow_', '') in inst]
     streams = [item[2] for item in plan.schedule if item[0] == 'launch' and plan.launches[item[1]][0].__name__.replace('bflow_', '') in inst]
     if len(labels) != n:
