@@ -83,6 +83,17 @@ class ClockSampler:
         return out
 
 
+def lookup_traffic(batch: int):
+    """DRAM bytes (read + write) of ONE in-step lookup launch from the committed ncu --set full capture (profiles/lookup_traffic.json,
+    written from the .ncu-rep by tools/ncu_summary.py); None when the capture is for another batch size."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'lookup_traffic.json')) as f:
+            t = json.load(f)
+        return float(t['dram_bytes_per_launch']) if int(t.get('batch', 1)) == batch else None
+    except Exception:
+        return None
+
+
 def lookup_bytes(B: int, h: int, w: int, slots: int, targets: int) -> int:
     """Algorithmic bytes of one lookup launch: 400 B read + 324 B written per (pixel, slot),
     + 8 B of centre coordinates per (pixel, target)."""
@@ -307,7 +318,7 @@ def main():
                 'ms_per_step': e2e_ms / K, 'api': 'RAFTSpline.forward(voxel_grid=pinned host tensor .to(cuda)) -> BezierCurves.cpu()'},
         'gpu_launches': plan.n_launches * K,
         'roofline': {'kernel': 'corr_lookup_tiled_kernel (bflow_corr_lookup, granule-tiled volume)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                     'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src, 'bytes_per_launch': lk_bytes,
+                     'frac': achieved / peak, 'traffic': lookup_traffic(Bp), 'peak_source': peak_src, 'bytes_per_launch': lk_bytes,
                      'us_per_launch': lk_ms * 1e3, 'us_per_launch_isolated_event_pair': lk_iso_ms * 1e3, 'us_per_launch_burst_of_12': lk_burst_ms * 1e3,
                      'launches_timed': len(lk),
                      'note': 'achieved = algorithmic bytes / mean launch duration of the 12 lookup launches of a step, CUDA events on the launch '

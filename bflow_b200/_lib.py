@@ -67,7 +67,7 @@ _SIGNATURES = {
     'bflow_conv2d_nhwc_tc3': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     'bflow_tma_tile_map': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7),
     'bflow_conv2d_slab64': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
-    'bflow_conv2d_stem7': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    'bflow_conv2d_stem7': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     'bflow_im2col_split16': (C.c_int, [C.c_void_p] + [C.c_int] * 11 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'bflow_split_f16': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
     'bflow_pack_b_tc': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),

@@ -1004,7 +1004,8 @@ constexpr int ST_B_BYTES = ST_NKB * 2 * SL_BN * 128;// 65536
 constexpr int ST_PATCH_BYTES = ST_MAXC * ST_PH * ST_PW * 4;   // 28416
 
 struct StemParams {
-    int tiles_x, tiles_y, n_tiles, cin, c_total, c_off, K;
+    int tiles_x, tiles_y, n_tiles, cin, c_total, K;
+    int n_win, ns, c_off[8];      // image n = window * ns + sample: channels [c_off[window], +cin) of input sample `sample`
     float acc_scale, in_scale, in_shift;
     unsigned long long* tl;
 };
@@ -1061,7 +1062,8 @@ conv_stem7_kernel(const bflow_conv_desc d, const uint8_t* __restrict__ wtc, cons
         const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
         const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
         const int gx0 = tx * 16 - 4, gy0 = ty * 32 - 3;
-        const float* src0 = d.x0 + ((size_t)n * p.c_total + p.c_off) * d.H * d.W;
+        const int win = n / p.ns, nl = n - win * p.ns;
+        const float* src0 = d.x0 + ((size_t)nl * p.c_total + p.c_off[win]) * d.H * d.W;
         const int total = p.cin * ST_PH * (ST_PW / 4);
         for (int i = etid_; i < total; i += 256) {
             const int x4 = i % (ST_PW / 4);
@@ -1638,15 +1640,16 @@ extern "C" int bflow_conv2d_slab64(const bflow_conv_desc* dp, const void* maps, 
 // Fused stem: 7x7 / stride 2 / pad 3, channels [c_off, c_off + cin) of an fp32 NCHW input (49 * cin <= 256) -> 64 channels, input mapped
 // x -> in_scale * x + in_shift first (raft.py:134).  d carries the output side (N, H, W, Ho, Wo, Cout = 64, bias, act1, y / y16, stats);
 // x0: the fp32 NCHW input; w_tc: tc3 weight image (bn 64) of the [64][256] matrix with K = (kh*7+kw)*cin + c.
-extern "C" int bflow_conv2d_stem7(const bflow_conv_desc* dp, const void* w_tc, int c_total, int c_off, float in_scale, float in_shift,
-                                  float acc_scale, int* err, void* stream) {
+extern "C" int bflow_conv2d_stem7(const bflow_conv_desc* dp, const void* w_tc, int c_total, const int* c_offs, int n_windows, float in_scale,
+                                  float in_shift, float acc_scale, int* err, void* stream) {
     BFLOW_REQUIRE(dp != nullptr && w_tc != nullptr, "conv_stem7: null argument");
     BFLOW_REQUIRE(dp->x0 != nullptr && bflow::aligned16(dp->x0) && dp->W % 4 == 0, "conv_stem7: x0 = 16-byte aligned fp32 NCHW input, W % 4 == 0");
     const bflow_conv_desc& d = *dp;
     BFLOW_REQUIRE(d.c0 > 0 && d.c0 <= bflow::ST_MAXC && 49 * d.c0 <= 256 && d.c1 == 0 && d.Cout == 64, "conv_stem7: cin <= 5, Cout == 64");
     BFLOW_REQUIRE(d.KH == 7 && d.KW == 7 && d.stride == 2 && d.pad_h == 3 && d.pad_w == 3, "conv_stem7: 7x7 / 2 / pad 3 only");
     BFLOW_REQUIRE(d.N > 0 && d.H > 0 && d.W > 0 && d.Ho == (d.H - 1) / 2 + 1 && d.Wo == (d.W - 1) / 2 + 1, "conv_stem7: Ho/Wo mismatch");
-    BFLOW_REQUIRE(c_off >= 0 && c_off + d.c0 <= c_total, "conv_stem7: channel window");
+    BFLOW_REQUIRE(c_offs != nullptr && n_windows >= 1 && n_windows <= 8 && d.N % n_windows == 0, "conv_stem7: 1..8 channel windows, N = windows * samples");
+    for (int i = 0; i < n_windows; ++i) BFLOW_REQUIRE(c_offs[i] >= 0 && c_offs[i] + d.c0 <= c_total, "conv_stem7: channel window");
     BFLOW_REQUIRE(d.epi == BFLOW_EPI_STD && d.res == nullptr && d.res16_hi == nullptr && d.act1 <= BFLOW_ACT_RELU && d.act2 == BFLOW_ACT_NONE, "conv_stem7: plain epilogue (none / relu)");
     BFLOW_REQUIRE((d.y == nullptr || (d.ldy >= 64 && d.ldy % 4 == 0 && bflow::aligned16(d.y))), "conv_stem7: fp32 output alignment");
     BFLOW_REQUIRE(d.y16_hi == nullptr || (d.y16_lo != nullptr && d.ldy16 % 8 == 0 && bflow::aligned16(d.y16_hi) && bflow::aligned16(d.y16_lo)), "conv_stem7: split output alignment");
@@ -1660,7 +1663,9 @@ extern "C" int bflow_conv2d_stem7(const bflow_conv_desc* dp, const void* w_tc, i
     p.n_tiles = (int)nt;
     p.cin = d.c0;
     p.c_total = c_total;
-    p.c_off = c_off;
+    p.n_win = n_windows;
+    p.ns = d.N / n_windows;
+    for (int i = 0; i < 8; ++i) p.c_off[i] = i < n_windows ? c_offs[i] : 0;
     p.K = 49 * d.c0;
     p.acc_scale = acc_scale;
     p.in_scale = in_scale;

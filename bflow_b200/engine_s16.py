@@ -189,12 +189,28 @@ class S16Recorder:
         H2, W2 = H // 2, W // 2
         rows = Np * H2 * W2
         w1 = E['conv1']
+        # consecutive fused-stem windows over the same source tensor (same sample count) collapse into one launch
+        merged = []
+        for win in windows:
+            last = merged[-1] if merged else None
+            if (last is not None and win['kind'] == 'stem7' and last['kind'] == 'stem7' and last['src'] == win['src'] and last['ns'] == win['ns'] and
+                    last['cin'] == win['cin'] and len(last['group']) < 8):
+                last['group'].append(win)
+            elif win['kind'] == 'stem7':
+                merged.append(dict(win, group=[win]))
+            else:
+                merged.append(win)
+        windows = [dict(w_, ns=sum(g_['ns'] for g_ in w_['group'])) if w_.get('group') else w_ for w_ in merged]
         # stem: 7x7 stride-2 conv (extractor.py:112), one launch group per input window.  Three forms:
         #   'im2col'  few input channels (K = 49*cin <= 512): patch matrix in split-fp16 + 1x1 tensor-core GEMM
         #   'tma'     cin >= 16 at an 8-aligned channel offset of a split-fp16 NHWC input: 7x7 im2col-TMA convolution
         #   'simt'    fp32 NHWC input on CUDA cores
         def stem(win, n0, ns, y=None, y16=None, act='none', stats=None):
             if win['kind'] == 'stem7':
+                wins = win.get('group', [win])           # several channel windows of the same input tensor: one launch
+                offs = (C.c_int * len(wins))(*[w_['c_off'] for w_ in wins])
+                self.keep.append(offs)
+                ns = sum(w_['ns'] for w_ in wins)
                 wm = E['conv1_mat']
                 img, acc_scale = wm.tc3_image(64, wm.cin)
                 d = ConvDesc()
@@ -207,7 +223,7 @@ class S16Recorder:
                     d.y16_hi, d.y16_lo, d.ldy16 = y16[0].hi(y16[1]), y16[0].lo(y16[1]), y16[0].ld
                 d.stats, d.stats_hw = stats, H2 * W2
                 self.keep.append(d)
-                self._add(L.bflow_conv2d_stem7, C.byref(d), img.data_ptr(), win['C_total'], win['c_off'],
+                self._add(L.bflow_conv2d_stem7, C.byref(d), img.data_ptr(), win['C_total'], offs, len(wins),
                           win.get('scale', 1.0), win.get('shift', 0.0), acc_scale, self.eng.err.data_ptr(),
                           label=f'conv_stem7 {win["cin"]}->64 7x7/2 M={ns * H2 * W2}', flops=2.0 * ns * H2 * W2 * 64 * 49 * win['cin'])
                 self.n_tc += 1

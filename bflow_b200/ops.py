@@ -173,7 +173,7 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         wtc, acc_scale = pack_conv_weight_tc(wm, 64, block_per_tap=True)
         err = torch.zeros(1, device=x.device, dtype=torch.int32)
         d.x0 = x.data_ptr()
-        check(L.bflow_conv2d_stem7(C.byref(d), wtc.data_ptr(), Cin, 0, in_scale, in_shift, acc_scale, err.data_ptr(), _stream()), 'conv2d_stem7')
+        check(L.bflow_conv2d_stem7(C.byref(d), wtc.data_ptr(), Cin, (C.c_int * 1)(0), 1, in_scale, in_shift, acc_scale, err.data_ptr(), _stream()), 'conv2d_stem7')
         if int(err.item()) != 0:
             raise RuntimeError('bflow_conv2d_stem7: pipeline wait timed out inside the kernel')
     elif backend == 'slab64':

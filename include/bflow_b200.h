@@ -124,12 +124,14 @@ int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* d, const void* maps, const void
  * Standard epilogue only (none / relu, split residual, fp32 and / or split output, fused InstanceNorm sums). */
 int bflow_tma_tile_map(void* map_out_128B, const void* base_fp16, int N, int H, int W, int C, int ld_halves, int box_w, int box_h);
 int bflow_conv2d_slab64(const bflow_conv_desc* d, const void* maps, const void* w_tc, float acc_scale, int* err, void* stream);
-/* Fused encoder stem (extractor.py:112): 7x7 / stride 2 / pad 3 over channels [c_off, c_off + cin) of an fp32 NCHW input (cin <= 5, W % 4 == 0),
+/* Fused encoder stem (extractor.py:112): 7x7 / stride 2 / pad 3 over n_windows (<= 8) channel windows [c_offs[i], c_offs[i] + cin) of an fp32
+ * NCHW input of N / n_windows samples (cin <= 5, W % 4 == 0; output image i * samples + s = window i of sample s: the torch.cat of
+ * extractor.py:106-110),
  * input first mapped x -> in_scale * x + in_shift (raft.py:134), 64 output channels.  The patch matrix is built in shared memory from the
  * input footprint of each 8 x 16 output tile and multiplied on tcgen05 against the resident weights (w_tc: tc3 image, bn 64, of the
  * [64][256] matrix, K = (kh*7+kw)*cin + c).  d: x0 = the NCHW input, c0 = cin, N/H/W/Ho/Wo, Cout = 64, bias, act1, y / y16, stats; plain
  * epilogue (none / relu, fp32 and / or split output, fused InstanceNorm sums). */
-int bflow_conv2d_stem7(const bflow_conv_desc* d, const void* w_tc, int c_total, int c_off, float in_scale, float in_shift,
+int bflow_conv2d_stem7(const bflow_conv_desc* d, const void* w_tc, int c_total, const int* c_offs, int n_windows, float in_scale, float in_shift,
                        float acc_scale, int* err, void* stream);
 /* im2col of a channel window of an NCHW fp32 tensor straight into split-fp16 rows (the 7x7 stride-2 encoder stems on few input
  * channels, extractor.py:112: K = KH*KW*cin is too thin per tap for 64-channel TMA boxes, so the patch matrix is materialised
