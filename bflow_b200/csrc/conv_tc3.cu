@@ -352,7 +352,53 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
             if (warp == 2 && lane == 0) T3_CTA(5);
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_COLS + (uint32_t)(chalf * HALF);
             const int nb0 = n0 + chalf * HALF;
-            if (p.staged == 2) {
+            if (p.staged == 3) {
+                // Multi-tile CTAs with a plain fp32 store epilogue (the all-pairs correlation GEMM, corr.py:264-272: 1444 tiles of 64 KB): the
+                // direct path below stores 16 bytes per row per instruction and was measured LSU-bound (~7 us per tile against a 2 us main
+                // loop).  Here the pipeline runs with one stage less and the freed shared memory is a [128][BN + 4] fp32 staging tile: the
+                // epilogue warps park the tile there and one cp.async.bulk per row streams it out while the next tile's MMAs run.
+                constexpr int PITCH = BN + 4;
+                float* S = reinterpret_cast<float*>(smem_raw + (smem_base - t3_smem_u32(smem_raw)) + STAGES * STAGE_BYTES);
+                const int mt0 = m_tile * T3_BM;
+                const int ncols = min(BN, d.Cout - n0);
+                if (etid < T3_BM) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // previous tile's rows have left the staging tile
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                {
+                    float* trow = S + (quad * 32 + lane) * PITCH + chalf * HALF;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < HALF; c0 += 32) {
+                        float v[32];
+                        t3_tmem_ld16_nowait(taddr + (uint32_t)c0, v);
+                        t3_tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), v + 16);
+                        if (STACK) {
+                            float u[32];
+                            t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0), u);
+                            t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0 + 16), u + 16);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) v[c] += u[c];
+                        } else {
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        }
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + chalf * HALF + c0 + c);
+                            *reinterpret_cast<float4*>(trow + c0 + c) =
+                                make_float4(fmaxf(post * fmaf(v[c], p.acc_scale, b4.x), lo1), fmaxf(post * fmaf(v[c + 1], p.acc_scale, b4.y), lo1),
+                                            fmaxf(post * fmaf(v[c + 2], p.acc_scale, b4.z), lo1), fmaxf(post * fmaf(v[c + 3], p.acc_scale, b4.w), lo1));
+                        }
+                    }
+                }
+                t3_fence_before();
+                __syncwarp();
+                if (lane == 0) t3_mbar_arrive(tempty_bar(acc));
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (etid < T3_BM && mt0 + etid < p.M) {
+                    t3_bulk_s2g(d.y + (size_t)(mt0 + etid) * d.ldy + n0, t3_smem_u32(S + etid * PITCH), (uint32_t)ncols * 4u);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else if (p.staged == 2) {
                 // Bulk-copy epilogue of a single-tile CTA.  Measured (tools/timeline.py --cta-label): ordinary loads / stores issued by the 8
                 // epilogue warps move ~9 bytes per clock per SM -- a 128x128 GRU epilogue took 13 us, longer than its main loop.  The
                 // pipeline stages are idle once tmem_full has fired, so: (1) one thread per tile row fetches the row of every per-element
@@ -725,6 +771,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
             if (warp == 2 && lane == 0) T3_CTA(6);
         }
         if (d.stats != nullptr) flush_stats(cur_img, stat_n0);
+        if (p.staged == 3) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     if (tid == 0) T3_TRACE(4, 255);              // CTA end
@@ -1549,6 +1596,15 @@ extern "C" int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* dp, const void* maps
             bulk = bulk && bflow::T3_BM * (bn + 4) * 4 + regions * bflow::T3_BM * bn * 4 <= bflow::t3_area_bytes(bn, 0);
         }
         if (bulk) p.staged = 2;
+        // multi-tile bulk-store epilogue: plain fp32 output only, bn = 128 (runs the <128, 2> instantiation: the third stage's memory is the staging tile)
+        static int mstore_on = -1;
+        if (mstore_on < 0) {
+            const char* e = getenv("BFLOW_TC3_MSTORE");
+            mstore_on = (e != nullptr && e[0] == '0') ? 0 : 1;
+        }
+        if (mstore_on && !single && bn == 128 && d.epi == BFLOW_EPI_STD && d.stats == nullptr && d.res == nullptr && d.res16_hi == nullptr &&
+            d.y16_hi == nullptr && d.y != nullptr && a16(d.y) && d.ldy % 4 == 0 && d.Cout % 4 == 0 && d.act1 <= BFLOW_ACT_RELU && d.act2 == BFLOW_ACT_NONE)
+            p.staged = 3;
     }
     p.trace = bflow::g_tc3_trace;
     p.cta = (bflow::g_tc3_cta != nullptr && bflow::g_tc3_cta_count++ == bflow::g_tc3_cta_nth) ? bflow::g_tc3_cta : nullptr;
@@ -1558,7 +1614,7 @@ extern "C" int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* dp, const void* maps
     cudaStream_t st = (cudaStream_t)stream;
     switch (bn) {
         case 64: return bflow::launch_tc3<64, 4>(tm, d, w_tc, p, err, st);
-        case 128: return bflow::launch_tc3<128, 3>(tm, d, w_tc, p, err, st);
+        case 128: return p.staged == 3 ? bflow::launch_tc3<128, 2>(tm, d, w_tc, p, err, st) : bflow::launch_tc3<128, 3>(tm, d, w_tc, p, err, st);
         case 256: return bflow::launch_tc3<256, 2>(tm, d, w_tc, p, err, st);
         default: bflow::set_error("conv_tc3: bn must be 64, 128 or 256"); return BFLOW_ERR_INVALID;
     }

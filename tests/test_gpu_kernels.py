@@ -61,6 +61,25 @@ def test_conv2d_tensor_core_matches_torch(N, Cin, H, W, Cout, k, s, p, act, bn):
     assert (out - ref).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize('N,Cin,H,W,Cout,k,s,p,act,bn', [
+    (1, 64, 160, 128, 256, (1, 1), 1, (0, 0), 'none', 128),    # 320 tiles: multi-tile CTAs, bulk row stores from the staging tile
+    (1, 64, 150, 129, 200, (1, 1), 1, (0, 0), 'relu', 128),    # the same with ragged M and Cout
+    (2, 64, 96, 100, 64, (3, 3), 1, (1, 1), 'relu', 64),       # multi-tile, direct stores
+    (1, 256, 60, 80, 124, (3, 3), 1, (1, 1), 'relu', 64),      # single-tile, ragged Cout
+    (1, 256, 60, 80, 256, (1, 5), 1, (0, 2), 'sigmoid', 128),  # single-tile bulk-copy epilogue, bn 128
+    (1, 128, 60, 80, 64, (3, 3), 1, (1, 1), 'tanh', 64),
+])
+def test_conv2d_tc3_matches_torch(N, Cin, H, W, Cout, k, s, p, act, bn):
+    """TMA-fed kernel and its epilogue variants (single-tile bulk copy, multi-tile bulk row stores, direct stores, ragged Cout)."""
+    x = torch.randn(N, Cin, H, W, generator=g(1))
+    w = torch.randn(Cout, Cin, *k, generator=g(2)) / (Cin * k[0] * k[1]) ** 0.5
+    b = torch.randn(Cout, generator=g(3))
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride=s, padding=p).float()
+    ref = {'none': lambda t: t, 'relu': torch.relu, 'sigmoid': torch.sigmoid, 'tanh': torch.tanh}[act](ref)
+    out = ops.conv2d(x.to(DEV), w.to(DEV), b.to(DEV), stride=s, padding=p, act=act, backend='tc3', bn=bn).cpu()
+    assert (out - ref).abs().max() < 1e-4
+
+
 @pytest.mark.parametrize('N,H,W,act', [(1, 16, 8, 'none'), (2, 40, 24, 'relu'), (3, 37, 16, 'none'), (5, 120, 160, 'relu')])
 def test_conv2d_slab64_matches_torch(N, H, W, act):
     """Slab kernel (weights resident, halo slabs): 3x3/1, 64 -> 64; ragged tile rows (H % 16 != 0), several images, multi-tile CTAs."""
