@@ -535,6 +535,13 @@ __global__ void __launch_bounds__(256) conv_thin7_kernel(const bflow_conv_desc d
     const int n = bid / tiles_y;
     const int oy0 = ty * TH_ROWS, ox0 = tx * TH_COLS;
     tl_begin(tl);
+    __shared__ __align__(8) unsigned long long wbar_storage;
+    const uint32_t wbar = (uint32_t)__cvta_generic_to_shared(&wbar_storage);
+    uint32_t wphase = 0;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(wbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -542,14 +549,18 @@ __global__ void __launch_bounds__(256) conv_thin7_kernel(const bflow_conv_desc d
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     for (int c0 = 0; c0 < d.c0; c0 += 4) {
         __syncthreads();
-        // weights of this channel chunk: rows (tap*Cin + c0 + ch) of the packed [K][ldw] matrix
-        for (int i = tid; i < TH_K * TH_K * 4 * (TH_CO / 4); i += 256) {
-            const int row = i >> 5, c4 = i & 31;             // row = tap*4 + ch
-            const int tap = row >> 2, ch = row & 3;
-            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<float4*>(s_w) + i);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(d.w + (size_t)(tap * d.c0 + c0 + ch) * d.ldw + c4 * 4) : "memory");
+        // weights of this channel chunk: rows (tap*Cin + c0 + ch) of the packed [K][ldw] matrix -- per tap 4 consecutive rows (2 KB), one
+        // cp.async.bulk each (per-lane copies of the 100 KB cost ~5 us of LSU time per CTA)
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic reads of s_w (previous chunk) are ordered before the refill
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar), "r"(TH_K * TH_K * 4 * TH_CO * 4) : "memory");
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (tid < TH_K * TH_K) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_w + tid * 4 * TH_CO);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "l"(d.w + (size_t)(tid * d.c0 + c0) * d.ldw), "r"(4 * TH_CO * 4), "r"(wbar)
+                         : "memory");
+        }
         for (int i = tid; i < TH_PR * TH_PC; i += 256) {
             const int yy = i / TH_PC, xx = i - yy * TH_PC;
             const int iy = oy0 + yy - 3, ix = ox0 + xx - 3;
@@ -560,7 +571,19 @@ __global__ void __launch_bounds__(256) conv_thin7_kernel(const bflow_conv_desc d
             s_x[2 * TH_PR * TH_PC + i] = v.z;
             s_x[3 * TH_PR * TH_PC + i] = v.w;
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        {
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(ok)
+                    : "r"(wbar), "r"(wphase)
+                    : "memory");
+            }
+            wphase ^= 1u;
+        }
         __syncthreads();
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
@@ -606,7 +629,7 @@ extern "C" int bflow_conv2d_thin7(const bflow_conv_desc* dp, void* stream) {
     BFLOW_REQUIRE(d.x0 != nullptr && d.w != nullptr, "conv_thin7: null tensor");
     BFLOW_REQUIRE(d.c1 == 0 && d.c0 > 0 && d.c0 % 4 == 0 && d.ld0 % 4 == 0 && bflow::aligned16(d.x0), "conv_thin7: one aligned source, Cin % 4 == 0");
     BFLOW_REQUIRE(d.KH == 7 && d.KW == 7 && d.stride == 1 && d.pad_h == 3 && d.pad_w == 3 && d.Ho == d.H && d.Wo == d.W, "conv_thin7: 7x7, stride 1, pad 3");
-    BFLOW_REQUIRE(d.Cout == bflow::TH_CO && d.ldw % 4 == 0 && d.ldw >= d.Cout && bflow::aligned16(d.w), "conv_thin7: Cout == 128, packed weights");
+    BFLOW_REQUIRE(d.Cout == bflow::TH_CO && d.ldw == bflow::TH_CO && bflow::aligned16(d.w), "conv_thin7: Cout == 128, packed weights with ldw == 128");
     BFLOW_REQUIRE(d.bias == nullptr || bflow::aligned16(d.bias), "conv_thin7: bias alignment");
     BFLOW_REQUIRE(d.epi == BFLOW_EPI_STD, "conv_thin7: standard epilogue only");
     BFLOW_REQUIRE((d.y == nullptr || d.ldy >= d.Cout) && (d.res == nullptr || d.ldr >= d.Cout), "conv_thin7: bad output stride");

@@ -176,6 +176,14 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
 
     if (tid == 0) T3_TRACE(5, 255);              // CTA start
     if (tid == 0) T3_CTA(0);
+    if (tid == 32) {                             // descriptor fetch overlaps barrier init / TMEM allocation
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map0h)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map0l)) : "memory");
+        if (p.ncb1 > 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map1h)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map1l)) : "memory");
+        }
+    }
     tl_begin(p.tl);
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -1589,7 +1597,12 @@ extern "C" int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* dp, const void* maps
             bulk = bulk && d.y != nullptr && a16(d.aux0) && d.ld_aux0 % 4 == 0 && d.aux1 == nullptr && d.aux1_16_hi != nullptr && a16(d.aux1_16_hi) &&
                    a16(d.aux1_16_lo) && d.ld_aux1_16 % 8 == 0 && (d.Cout / 2) % bn == 0;
         } else {
-            bulk = bulk && d.y != nullptr && a16(d.aux0) && d.ld_aux0 % 4 == 0 && (d.y16_hi == nullptr || (a16(d.y16_hi) && a16(d.y16_lo) && d.ldy16 % 8 == 0));
+            static int bulk_q = -1;
+            if (bulk_q < 0) {
+                const char* e = getenv("BFLOW_TC3_BULK_Q");
+                bulk_q = (e != nullptr && e[0] == '1') ? 1 : 0;      // measured: three operand rows in + three out per tile row cost more in bulk-copy issue than the batched loads (22.8 vs 17.1 us)
+            }
+            bulk = bulk && bulk_q && d.y != nullptr && a16(d.aux0) && d.ld_aux0 % 4 == 0 && (d.y16_hi == nullptr || (a16(d.y16_hi) && a16(d.y16_lo) && d.ldy16 % 8 == 0));
         }
         {   // the fp32 tile plus the operand / output tiles must fit the data area
             const int regions = d.epi == BFLOW_EPI_GRU_Q ? 3 : (d.epi == BFLOW_EPI_GRU_ZR ? 2 : 1);

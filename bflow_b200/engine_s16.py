@@ -464,15 +464,16 @@ class S16Recorder:
         for itr in range(self.iters):
             if itr == 1:
                 self.iter_len = len(self.launches) - self.iter_start
-            # motion encoder (update.py:88-97): the Bezier branch (convf1 -> convf2) runs beside lookup -> convc1 -> convc2
+            # motion encoder (update.py:88-97): the Bezier branch (convf1 -> convf2) runs beside lookup -> convc1 -> convc2.  (Forking after
+            # the lookup instead was measured: the lookup drops from 21 to 15 us, but convc1 then starts ~10 us late behind the fork and
+            # convc2 shares SMs with convf2: no net gain.)
             self._fork()
             thin = U['convf1'].cout == 128 and (2 * deg) % 4 == 0 and poff % 4 == 0
             self._conv_simt16(U['convf1'], hx + poff * 4, 2 * deg, gw, B, h, w, y16=(f1_16, 0), act1='relu', kernel='thin7' if thin else 'auto')
             self._conv3(U['convf2'], [(f1_16, 0, 128)], B, h, w, y16=(cb16, 192), act1='relu')
             self._main()
             self._add(L.bflow_corr_lookup, C.byref(ld))
-            self._conv3(U['convc1'], [(self.corr16, 0, eng.ldc)], B, h, w, y16=(c1_16, 0), act1='relu')
-            self._conv3(U['convc2'], [(c1_16, 0, 256)], B, h, w, y16=(cb16, 0), act1='relu')
+            self._conv3(U['convc1'], [(self.corr16, 0, eng.ldc)], B, h, w, y16=(c1_16, 0), act1='relu')            self._conv3(U['convc2'], [(c1_16, 0, 256)], B, h, w, y16=(cb16, 0), act1='relu')
             self._join()
             self._conv3(U['conv'], [(cb16, 0, 256)], B, h, w, y16=(hx16, hd + cd), act1='relu')
             # SepConvGRU (update.py:33-48) with the iteration-invariant inp part hoisted and the gate arithmetic in the epilogues
