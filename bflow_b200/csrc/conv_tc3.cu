@@ -133,12 +133,21 @@ __device__ __forceinline__ void t3_bulk_s2g(void* dst, uint32_t src, uint32_t by
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 
+__device__ __forceinline__ void sl_tma_tile(uint32_t dst, const CUtensorMap* map, int c, int x, int y, int n, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(x), "r"(y), "r"(n)
+                 : "memory");
+}
+
 struct T3Params {
     int M, n_mtiles, n_ntiles, ntaps, ncb0, ncb1, nkb;
     float acc_scale;
     long long* trace;
     unsigned long long* tl;
     unsigned long long* cta;   // development (bflow_tc3_cta_trace): [gridDim.x][16] globaltimer stamps of ONE chosen launch
+    // slab mode (stride-1 3x3 / 1x5 / 5x1): an output tile is an 8 x 16 pixel patch and one halo slab per slow filter index serves all taps
+    // along the other axis (see conv_slab64_kernel).  1: slab rows = (y, x) with x fastest (taps along y), 2: rows = (x, y) (taps along x).
+    int slab, tiles_x, tiles_y, n_slabs, tps;
     int staged;   // every CTA owns exactly one tile: the epilogue goes through shared memory (coalesced, batched global accesses)
     int dbg;      // development switches (bflow_tc3_debug): 1 no TMA loads, 2 no MMA, 4 no epilogue stores, 8 one MMA per k-step
 };
@@ -168,6 +177,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
     auto tempty_bar = [&](int a) { return bars + 80u + 8u * (uint32_t)a; };
     const uint32_t tmem_slot = bars + 96u;
     const uint32_t ebar = bars + 104u;          // bulk-copy epilogue: operand tiles have landed
+    constexpr int SL_NSA = 3, SL_NSB = BN <= 64 ? 4 : 3;                 // slab mode: halo-slab ring and weight-tile ring
+    constexpr int SL_SLAB_MAX = 2 * 8 * 20 * 128;                        // hi + lo planes of an 8 x (16 + 4) slab
+    const uint32_t sl_bars = bars + 128u + 3u * BN * 4u;                 // [afull 3][aempty 3]
+    auto afull_bar = [&](int s_) { return sl_bars + 8u * (uint32_t)s_; };
+    auto aempty_bar = [&](int s_) { return sl_bars + 24u + 8u * (uint32_t)s_; };
+    const uint32_t sl_bring = smem_base + SL_NSA * SL_SLAB_MAX;          // weight-tile ring behind the slab ring
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -186,9 +201,13 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
     }
     tl_begin(p.tl);
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < 4; ++s) {
             t3_mbar_init(full_bar(s), 1);      // the producer's arrive.expect_tx (+ TMA bytes)
             t3_mbar_init(empty_bar(s), 1);     // one tcgen05.commit
+        }
+        for (int s = 0; s < SL_NSA; ++s) {
+            t3_mbar_init(afull_bar(s), 1);
+            t3_mbar_init(aempty_bar(s), 1);
         }
         t3_mbar_init(ebar, 1);
         for (int a = 0; a < 2; ++a) {
@@ -215,7 +234,41 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer ------------------------------------------------
-        if (lane == 0) {
+        if (lane == 0 && p.slab) {
+            // slab mode: per 64-channel block and slow filter index one halo slab (hi, lo), then the weight tiles of its taps
+            uint32_t ia = 0, ib = 0;
+            const int tiles_per_img = p.tiles_x * p.tiles_y;
+            const uint32_t slab_plane = (uint32_t)(8 * (16 + p.tps - 1) * 128);
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m_tile = tile / p.n_ntiles, n_tile = tile - m_tile * p.n_ntiles;
+                const int n = m_tile / tiles_per_img, r = m_tile - n * tiles_per_img;
+                const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+                const int x0 = tx * (p.slab == 1 ? 8 : 16) - d.pad_w, y0 = ty * (p.slab == 1 ? 16 : 8) - d.pad_h;
+                const uint8_t* wt = wtc + (size_t)n_tile * p.nkb * (2 * B_BYTES);
+                const int ncb = p.ncb0 + p.ncb1;
+                for (int cb = 0; cb < ncb; ++cb) {
+                    const bool src0 = cb < p.ncb0;
+                    const int cc = (src0 ? cb : cb - p.ncb0) * 64;
+                    for (int sl = 0; sl < p.n_slabs; ++sl, ++ia) {
+                        const int sa = (int)(ia % SL_NSA);
+                        t3_mbar_wait(aempty_bar(sa), ((ia / SL_NSA) & 1u) ^ 1u, err);
+                        const uint32_t dst = smem_base + (uint32_t)sa * SL_SLAB_MAX;
+                        t3_mbar_arrive_expect_tx(afull_bar(sa), 2u * slab_plane);
+                        // slab == 1: map dims {C, W, H, N}, slabs indexed by kw; slab == 2: map dims {C, H, W, N}, slabs indexed by kh
+                        const int c1_ = p.slab == 1 ? x0 + sl : y0 + sl, c2_ = p.slab == 1 ? y0 : x0;
+                        sl_tma_tile(dst, src0 ? &map0h : &map1h, cc, c1_, c2_, n, afull_bar(sa));
+                        sl_tma_tile(dst + slab_plane, src0 ? &map0l : &map1l, cc, c1_, c2_, n, afull_bar(sa));
+                        for (int t = 0; t < p.tps; ++t, ++ib) {
+                            const int sb = (int)(ib % SL_NSB);
+                            t3_mbar_wait(empty_bar(sb), ((ib / SL_NSB) & 1u) ^ 1u, err);
+                            const int tap = p.slab == 1 ? t * d.KW + sl : sl * d.KW + t;
+                            t3_mbar_arrive_expect_tx(full_bar(sb), 2 * B_BYTES);
+                            t3_bulk_g2s(sl_bring + (uint32_t)sb * (2 * B_BYTES), wt + (size_t)(tap * ncb + cb) * (2 * B_BYTES), 2 * B_BYTES, full_bar(sb));
+                        }
+                    }
+                }
+            }
+        } else if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int m_tile = tile / p.n_ntiles, n_tile = tile - m_tile * p.n_ntiles;
@@ -256,12 +309,50 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
         // fp16 x fp16 -> fp32, K-major, M 128, N = BN (idesc) or 2 BN (idesc2)
         const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
         const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
-        uint32_t it = 0, lt = 0;
+        uint32_t it = 0, lt = 0, ia = 0, ib = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
             const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
             t3_mbar_wait(tempty_bar(acc), aph ^ 1u, err);          // epilogue has drained this accumulator
             t3_fence_after();
             const uint32_t tacc = tmem_base + acc * ACC_COLS;
+            if (p.slab) {
+                if (STACK) {
+                    const int ncb = p.ncb0 + p.ncb1;
+                    const uint32_t slab_plane = (uint32_t)(8 * (16 + p.tps - 1) * 128);
+                    uint32_t first = 1u;
+                    for (int cb = 0; cb < ncb; ++cb) {
+                        for (int sl = 0; sl < p.n_slabs; ++sl, ++ia) {
+                            const int sa = (int)(ia % SL_NSA);
+                            t3_mbar_wait(afull_bar(sa), (ia / SL_NSA) & 1u, err);
+                            const uint32_t a_hi0 = smem_base + (uint32_t)sa * SL_SLAB_MAX, a_lo0 = a_hi0 + slab_plane;
+                            for (int t = 0; t < p.tps; ++t, ++ib) {
+                                const int sb = (int)(ib % SL_NSB);
+                                t3_mbar_wait(full_bar(sb), (ib / SL_NSB) & 1u, err);
+                                t3_fence_after();
+                                if (lane == 0) {
+                                    const uint32_t b_hi = sl_bring + (uint32_t)sb * (2 * B_BYTES);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const uint32_t ko = (uint32_t)k * 32u + (uint32_t)t * 1024u;      // tap t = the slab advanced by 8 rows
+                                        const uint64_t dbh = t3_umma_desc(b_hi + (uint32_t)k * 32u);
+                                        t3_umma(tacc, t3_umma_desc(a_hi0 + ko), dbh, idesc2, first ? 0u : 1u);
+                                        t3_umma(tacc, t3_umma_desc(a_lo0 + ko), dbh, idesc, 1u);
+                                        first = 0u;
+                                    }
+                                    t3_commit(empty_bar(sb));
+                                    if (t == p.tps - 1) t3_commit(aempty_bar(sa));
+                                    if (t == p.tps - 1 && sl == p.n_slabs - 1 && cb == ncb - 1) {
+                                        t3_commit(tfull_bar(acc));
+                                        T3_CTA(4);
+                                    }
+                                }
+                                __syncwarp();
+                            }
+                        }
+                    }
+                }
+                continue;
+            }
             for (int kb = 0; kb < p.nkb; ++kb, ++it) {
                 const int s = (int)(it % STAGES);
                 const uint32_t ph = (it / STAGES) & 1u;
@@ -337,7 +428,29 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
         if (d.stats != nullptr) flush_stats(-1, 0);
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
             const int m_tile = tile / p.n_ntiles, n_tile = tile - m_tile * p.n_ntiles;
-            const int m = m_tile * T3_BM + quad * 32 + lane;
+            // tile row -> output pixel.  im2col mode: 128 consecutive pixels; slab mode: an 8 x 16 patch of image t_n at (t_y0, t_x0)
+            int t_n = 0, t_y0 = 0, t_x0 = 0;
+            if (p.slab) {
+                const int tpi = p.tiles_x * p.tiles_y;
+                t_n = m_tile / tpi;
+                const int r_ = m_tile - t_n * tpi;
+                const int ty_ = r_ / p.tiles_x;
+                t_y0 = ty_ * (p.slab == 1 ? 16 : 8);
+                t_x0 = (r_ - ty_ * p.tiles_x) * (p.slab == 1 ? 8 : 16);
+            }
+            auto row_m = [&](int row, bool& ok) -> int {
+                if (!p.slab) {
+                    const int mm_ = m_tile * T3_BM + row;
+                    ok = mm_ < p.M;
+                    return mm_;
+                }
+                const int yy = p.slab == 1 ? (row >> 3) : (row & 7), xx = p.slab == 1 ? (row & 7) : (row >> 3);
+                const int y = t_y0 + yy, x = t_x0 + xx;
+                ok = y < d.Ho && x < d.Wo;
+                return (t_n * d.Ho + y) * d.Wo + x;
+            };
+            bool m_ok;
+            const int m = row_m(quad * 32 + lane, m_ok);
             const int n0 = n_tile * BN;
             if (n_tile != bias_tile) {               // uniform over the epilogue warps
                 asm volatile("bar.sync 1, 256;" ::: "memory");      // everyone is done with the previous slice
@@ -346,7 +459,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 bias_tile = n_tile;
             }
             if (d.stats != nullptr) {
-                const int tile_img = (m_tile * T3_BM) / shw;
+                const int tile_img = p.slab ? t_n : (m_tile * T3_BM) / shw;
                 if (tile_img != cur_img || n0 != stat_n0) {
                     flush_stats(cur_img, stat_n0);
                     cur_img = tile_img;
@@ -402,8 +515,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 if (lane == 0) t3_mbar_arrive(tempty_bar(acc));
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (etid < T3_BM && mt0 + etid < p.M) {
-                    t3_bulk_s2g(d.y + (size_t)(mt0 + etid) * d.ldy + n0, t3_smem_u32(S + etid * PITCH), (uint32_t)ncols * 4u);
+                bool row_ok = false;
+                const int row_mm = etid < T3_BM ? row_m(etid, row_ok) : 0;
+                if (etid < T3_BM && row_ok) {
+                    t3_bulk_s2g(d.y + (size_t)row_mm * d.ldy + n0, t3_smem_u32(S + etid * PITCH), (uint32_t)ncols * 4u);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             } else if (p.staged == 2) {
@@ -432,13 +547,17 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 const bool out16 = is_zr ? r_tile : d.y16_hi != nullptr;
                 float* Og = is_q ? Yg : Rg;
                 const int ncols = min(BN, d.Cout - n0);
-                const int vrows = min(T3_BM, p.M - mt0);
+                int vrows;                                  // number of tile rows that are output pixels
+                if (!p.slab) vrows = min(T3_BM, p.M - mt0);
+                else vrows = min(p.slab == 1 ? 16 : 8, d.Ho - t_y0) * min(p.slab == 1 ? 8 : 16, d.Wo - t_x0);
+                bool row_ok = false;
+                const int row_mm = etid < T3_BM ? row_m(etid, row_ok) : 0;
                 if (etid == 0) {
                     const uint32_t per_row = (uint32_t)ncols * 4u * ((hasR ? 1u : 0u) + (hasA ? 1u : 0u) + (hasY ? 1u : 0u));
                     t3_mbar_arrive_expect_tx(ebar, per_row * (uint32_t)vrows);
                 }
-                if (etid < vrows) {
-                    const size_t mm = (size_t)(mt0 + etid);
+                if (etid < T3_BM && row_ok) {
+                    const size_t mm = (size_t)row_mm;
                     const uint32_t nb = (uint32_t)ncols * 4u;
                     if (hasR) t3_bulk_g2s(t3_smem_u32(Rg + etid * BN), d.res + mm * d.ldr + n0, nb, ebar);
                     if (hasA) t3_bulk_g2s(t3_smem_u32(Ag + etid * BN), d.aux0 + mm * d.ld_aux0 + (is_zr ? n0 - Cg : n0), nb, ebar);
@@ -532,8 +651,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the bulk-copy engine
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (etid < vrows) {
-                    const size_t mm = (size_t)(mt0 + etid);
+                if (etid < T3_BM && row_ok) {
+                    const size_t mm = (size_t)row_mm;
                     if (out32) t3_bulk_s2g(d.y + mm * d.ldy + n0, t3_smem_u32(Og + etid * BN), (uint32_t)ncols * 4u);
                     if (out16) {
                         const int b = etid / RPB, rr = etid - b * RPB;
@@ -600,12 +719,15 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                     EpiPre pre[EPI_BATCH];
                     float4 val[EPI_BATCH];
                     bool ok[EPI_BATCH], vec[EPI_BATCH];
+                    int mrow[EPI_BATCH];
 #pragma unroll
                     for (int u = 0; u < EPI_BATCH; ++u) {
                         const int idx = base + u * 256;
                         const int row = idx / C4, c = (idx - row * C4) * 4;
-                        const int mm = mt0 + row, nn = n0 + c;
-                        ok[u] = idx < T3_BM * C4 && mm < p.M && nn < d.Cout;
+                        bool rok = false;
+                        const int mm = idx < T3_BM * C4 ? row_m(row, rok) : 0, nn = n0 + c;
+                        mrow[u] = mm;
+                        ok[u] = idx < T3_BM * C4 && rok && nn < d.Cout;
                         vec[u] = aligned && nn + 3 < d.Cout;
                         if (ok[u]) {
                             val[u] = *reinterpret_cast<const float4*>(T + row * PITCH + c);
@@ -618,7 +740,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                         const int row = idx / C4, c = (idx - row * C4) * 4;
                         if (ok[u]) {
                             float t4[4] = {val[u].x, val[u].y, val[u].z, val[u].w};
-                            conv_epilogue4_finish(d, mt0 + row, n0 + c, t4, vec[u], pre[u]);
+                            conv_epilogue4_finish(d, mrow[u], n0 + c, t4, vec[u], pre[u]);
                         }
                     }
                     if (warp == 2 && lane == 0 && base < 256 * EPI_BATCH * 5) T3_CTA(10 + base / (256 * EPI_BATCH));
@@ -647,9 +769,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 if (d.stats != nullptr) {
                     // butterfly transpose-reduce over the warp's 32 rows, 16 columns at a time; lanes with the low bit clear then own one
                     // column's (sum, sum of squares) and add it to the CTA's shared accumulators
-                    const int m_first = m_tile * T3_BM + quad * 32;
+                    const int m_first = p.slab ? t_n * shw : m_tile * T3_BM + quad * 32;      // slab mode: any pixel of image t_n
                     const int m_last = min(m_first + 31, p.M - 1);
-                    const bool uniform = m_first < p.M && (m_first / shw) == (m_last / shw);       // warp-uniform
+                    const bool uniform = p.slab ? true : (m_first < p.M && (m_first / shw) == (m_last / shw));       // warp-uniform
 #pragma unroll
                     for (int c = 0; c < HALF; c += 16) {
                         const int nb = nb0 + c;
@@ -658,7 +780,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const float b = s_bias[chalf * HALF + c + j];
-                            const float x = m < p.M ? post * fmaf(v[c + j], p.acc_scale, b) : 0.f;
+                            const float x = m_ok ? post * fmaf(v[c + j], p.acc_scale, b) : 0.f;
                             sv[j] = x;
                             sq[j] = x * x;
                         }
@@ -687,7 +809,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                                     atomicAdd(st + 1, (double)tq);
                                 }
                             }
-                        } else if (m < p.M) {
+                        } else if (m_ok) {
                             double* st = d.stats + ((size_t)(m / shw) * d.Cout + nb) * 2;
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
@@ -697,7 +819,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                         }
                     }
                 }
-                if (m < p.M) {
+                if (m_ok) {
 #pragma unroll
                     for (int c = 0; c < HALF; c += 16) {
                         const int nb = nb0 + c;
@@ -814,12 +936,6 @@ struct SlabParams {
     float acc_scale;
     unsigned long long* tl;
 };
-
-__device__ __forceinline__ void sl_tma_tile(uint32_t dst, const CUtensorMap* map, int c, int x, int y, int n, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-                 "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(x), "r"(y), "r"(n)
-                 : "memory");
-}
 
 __global__ void __launch_bounds__(T3_THREADS, 1)
 conv_slab64_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const bflow_conv_desc d,
@@ -1370,7 +1486,7 @@ static int g_tc3_cta_nth = -1, g_tc3_cta_count = 0;
 
 template <int BN, int STAGES>
 static int launch_tc3(const CUtensorMap* maps, const bflow_conv_desc& d, const void* wtc, const T3Params& p, int* err, cudaStream_t stream) {
-    constexpr int smem = t3_area_bytes(BN, STAGES) + 128 + 3 * BN * 4 + 1024;
+    constexpr int smem = t3_area_bytes(BN, STAGES) + 128 + 3 * BN * 4 + 64 + 1024;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1545,9 +1661,14 @@ extern "C" int bflow_tma_im2col_map(void* map_out, const void* base, int N, int 
     return BFLOW_OK;
 }
 
-extern "C" int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* dp, const void* maps, const void* w_tc, int bn, float acc_scale, int* err, void* stream) {
+static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* w_tc, int bn, float acc_scale, int slab, int* err, void* stream) {
     BFLOW_REQUIRE(dp != nullptr && maps != nullptr && w_tc != nullptr, "conv_tc3: null argument");
     const bflow_conv_desc& d = *dp;
+    if (slab) {
+        BFLOW_REQUIRE(slab == 1 || slab == 2, "conv_tc3s: orientation must be 1 (taps along y) or 2 (taps along x)");
+        BFLOW_REQUIRE(d.stride == 1 && d.pad_h == d.KH / 2 && d.pad_w == d.KW / 2 && (d.KH & 1) && (d.KW & 1), "conv_tc3s: stride 1, odd window, 'same' padding");
+        BFLOW_REQUIRE((slab == 1 ? d.KH : d.KW) <= 5 && bn <= 128, "conv_tc3s: at most 5 taps along the slab axis, bn <= 128");
+    }
     // channel counts are free (the TMA unit zero-fills channels beyond C); a second source must start on a 64-channel block
     BFLOW_REQUIRE(d.c0 > 0 && d.c1 >= 0 && (d.c1 == 0 || d.c0 % 64 == 0), "conv_tc3: channel counts");
     BFLOW_REQUIRE(d.N > 0 && d.H > 0 && d.W > 0 && d.Cout > 0 && d.KH > 0 && d.KW > 0 && d.stride > 0, "conv_tc3: bad shape");
@@ -1563,6 +1684,17 @@ extern "C" int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* dp, const void* maps
     bflow::T3Params p;
     p.M = (int)Mll;
     p.n_mtiles = (p.M + bflow::T3_BM - 1) / bflow::T3_BM;
+    p.slab = slab;
+    p.tiles_x = p.tiles_y = p.n_slabs = p.tps = 0;
+    if (slab) {
+        p.tiles_x = (d.Wo + (slab == 1 ? 8 : 16) - 1) / (slab == 1 ? 8 : 16);
+        p.tiles_y = (d.Ho + (slab == 1 ? 16 : 8) - 1) / (slab == 1 ? 16 : 8);
+        p.n_slabs = slab == 1 ? d.KW : d.KH;
+        p.tps = slab == 1 ? d.KH : d.KW;
+        const long long nm = (long long)d.N * p.tiles_x * p.tiles_y;
+        BFLOW_REQUIRE(nm < (1ll << 31), "conv_tc3s: too large");
+        p.n_mtiles = (int)nm;
+    }
     p.n_ntiles = (d.Cout + bn - 1) / bn;
     p.ntaps = d.KH * d.KW;
     p.ncb0 = (d.c0 + 63) / 64;
@@ -1615,7 +1747,7 @@ extern "C" int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* dp, const void* maps
             const char* e = getenv("BFLOW_TC3_MSTORE");
             mstore_on = (e != nullptr && e[0] == '0') ? 0 : 1;
         }
-        if (mstore_on && !single && bn == 128 && d.epi == BFLOW_EPI_STD && d.stats == nullptr && d.res == nullptr && d.res16_hi == nullptr &&
+        if (mstore_on && !slab && !single && bn == 128 && d.epi == BFLOW_EPI_STD && d.stats == nullptr && d.res == nullptr && d.res16_hi == nullptr &&
             d.y16_hi == nullptr && d.y != nullptr && a16(d.y) && d.ldy % 4 == 0 && d.Cout % 4 == 0 && d.act1 <= BFLOW_ACT_RELU && d.act2 == BFLOW_ACT_NONE)
             p.staged = 3;
     }
@@ -1633,6 +1765,17 @@ extern "C" int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* dp, const void* maps
     }
 }
 
+extern "C" int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* d, const void* maps, const void* w_tc, int bn, float acc_scale, int* err, void* stream) {
+    return tc3_entry(d, maps, w_tc, bn, acc_scale, 0, err, stream);
+}
+
+// Slab mode of the same kernel for stride-1 3x3 / 5x1 (orientation 1) and 1x5 / 3x3 (orientation 2) convolutions: `maps` are TILED tensor
+// maps from bflow_tma_tile_map (box 8 x (16 + taps - 1), transposed for orientation 2) instead of im2col maps; everything else as above.
+extern "C" int bflow_conv2d_nhwc_tc3s(const bflow_conv_desc* d, const void* maps, const void* w_tc, int bn, float acc_scale, int orientation, int* err,
+                                      void* stream) {
+    return tc3_entry(d, maps, w_tc, bn, acc_scale, orientation, err, stream);
+}
+
 namespace bflow {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1640,9 +1783,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 // Tiled (not im2col) tensor map over a split-fp16 NHWC plane: dims {C, W, H, N}, box {64 channels, box_w, box_h, 1}, SWIZZLE_128B,
 // out-of-bounds elements read as zero.  Used by bflow_conv2d_slab64 with box 8 x 18.
-extern "C" int bflow_tma_tile_map(void* map_out, const void* base, int N, int H, int W, int C, int ld_halves, int box_w, int box_h) {
+extern "C" int bflow_tma_tile_map(void* map_out, const void* base, int N, int H, int W, int C, int ld_halves, int box_w, int box_h, int transposed) {
     BFLOW_REQUIRE(map_out != nullptr && base != nullptr, "tma_tile_map: null argument");
-    BFLOW_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= 64 && ld_halves >= C && ld_halves % 8 == 0, "tma_tile_map: bad shape (C <= 64, ld a multiple of 8 halves)");
+    BFLOW_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && ld_halves >= C && ld_halves % 8 == 0, "tma_tile_map: bad shape (ld a multiple of 8 halves)");
     BFLOW_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && box_w > 0 && box_w <= 256 && box_h > 0 && box_h <= 256, "tma_tile_map: alignment / box");
     static bflow::EncodeTiledFn enc = nullptr;
     if (enc == nullptr) {
@@ -1653,9 +1796,15 @@ extern "C" int bflow_tma_tile_map(void* map_out, const void* base, int N, int H,
     }
     BFLOW_REQUIRE(enc != nullptr, "tma_tile_map: cuTensorMapEncodeTiled not available from the driver");
     alignas(64) CUtensorMap tm;
-    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    const cuuint64_t strides[3] = {(cuuint64_t)ld_halves * 2, (cuuint64_t)W * ld_halves * 2, (cuuint64_t)H * W * ld_halves * 2};
-    const cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    // transposed: dimension 1 is y and dimension 2 is x, so the box is stored y-fastest (slab rows = (x, y)); box_w / box_h keep their meaning
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)ld_halves * 2, (cuuint64_t)W * ld_halves * 2, (cuuint64_t)H * W * ld_halves * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    if (transposed) {
+        dims[1] = (cuuint64_t)H; dims[2] = (cuuint64_t)W;
+        strides[0] = (cuuint64_t)W * ld_halves * 2; strides[1] = (cuuint64_t)ld_halves * 2;
+        box[1] = (cuuint32_t)box_h; box[2] = (cuuint32_t)box_w;
+    }
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

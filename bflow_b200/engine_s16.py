@@ -9,6 +9,7 @@ volume.  The structure of the forward pass is the same as in ``engine._Plan._rec
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -103,7 +104,7 @@ class S16Recorder:
             maps = (C.c_uint8 * 256)()
             src = srcs[0][0]
             for j, base in enumerate((src.hi(srcs[0][1]), src.lo(srcs[0][1]))):
-                check(lib.bflow_tma_tile_map(C.addressof(maps) + 128 * j, base, N, H, W, 64, src.ld, 8, 18), 'tma_tile_map')
+                check(lib.bflow_tma_tile_map(C.addressof(maps) + 128 * j, base, N, H, W, 64, src.ld, 8, 18, 0), 'tma_tile_map')
             self.keep.append(maps)
             self._add(lib.bflow_conv2d_slab64, C.byref(d), C.addressof(maps), img.data_ptr(), acc_scale, self.eng.err.data_ptr(),
                       label=f'conv_slab64 64->64 3x3/1 M={M}', flops=2.0 * M * 64 * 9 * 64)
@@ -111,6 +112,20 @@ class S16Recorder:
             return Ho, Wo
         bn = choose_bn(wt.cout, (M + 127) // 128)
         img, acc_scale = wt.tc3_image(bn, c0)
+        orient = {(3, 3): 1, (5, 1): 1, (1, 5): 2}.get((wt.kh, wt.kw), 0)
+        if (orient and wt.stride == 1 and (ph, pw) == (wt.kh // 2, wt.kw // 2) and bn <= 128 and os.environ.get('BFLOW_TC3_SLAB', '1') != '0'):
+            # halo slabs instead of im2col rows: A traffic / 2.7 (3x3) ... / 4 (1x5, 5x1)
+            taps = wt.kh if orient == 1 else wt.kw
+            bw, bh = (8, 16 + taps - 1) if orient == 1 else (16 + taps - 1, 8)
+            maps = (C.c_uint8 * 512)()
+            for i, (s_, c_off, cc) in enumerate(srcs):
+                for j, base in enumerate((s_.hi(c_off), s_.lo(c_off))):
+                    check(lib.bflow_tma_tile_map(C.addressof(maps) + 128 * (2 * i + j), base, N, H, W, cc, s_.ld, bw, bh, 1 if orient == 2 else 0), 'tma_tile_map')
+            self.keep.append(maps)
+            self._add(lib.bflow_conv2d_nhwc_tc3s, C.byref(d), C.addressof(maps), img.data_ptr(), bn, acc_scale, orient, self.eng.err.data_ptr(),
+                      label=f'conv_tc3s_{bn} {c0 + c1}->{wt.cout} {wt.kh}x{wt.kw}/{wt.stride} M={M}', flops=2.0 * M * wt.cout * wt.kh * wt.kw * (c0 + c1))
+            self.n_tc += 1
+            return Ho, Wo
         maps = self._maps(srcs, N, H, W, wt)
         self._add(lib.bflow_conv2d_nhwc_tc3, C.byref(d), C.addressof(maps), img.data_ptr(), bn, acc_scale, self.eng.err.data_ptr(),
                   label=f'conv_tc3_{bn} {c0 + c1}->{wt.cout} {wt.kh}x{wt.kw}/{wt.stride} M={M}', flops=2.0 * M * wt.cout * wt.kh * wt.kw * (c0 + c1))
@@ -473,7 +488,8 @@ class S16Recorder:
             self._conv3(U['convf2'], [(f1_16, 0, 128)], B, h, w, y16=(cb16, 192), act1='relu')
             self._main()
             self._add(L.bflow_corr_lookup, C.byref(ld))
-            self._conv3(U['convc1'], [(self.corr16, 0, eng.ldc)], B, h, w, y16=(c1_16, 0), act1='relu')            self._conv3(U['convc2'], [(c1_16, 0, 256)], B, h, w, y16=(cb16, 0), act1='relu')
+            self._conv3(U['convc1'], [(self.corr16, 0, eng.ldc)], B, h, w, y16=(c1_16, 0), act1='relu')
+            self._conv3(U['convc2'], [(c1_16, 0, 256)], B, h, w, y16=(cb16, 0), act1='relu')
             self._join()
             self._conv3(U['conv'], [(cb16, 0, 256)], B, h, w, y16=(hx16, hd + cd), act1='relu')
             # SepConvGRU (update.py:33-48) with the iteration-invariant inp part hoisted and the gate arithmetic in the epilogues

@@ -153,7 +153,23 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     d.N, d.H, d.W, d.Ho, d.Wo, d.Cout = N, H, W, Ho, Wo, O
     d.KH, d.KW, d.stride, d.pad_h, d.pad_w = KH, KW, stride, ph, pw
     d.act1, d.act2, d.scale = ACT[act], 0, scale
-    if backend == 'tc3':
+    if backend == 'tc3s':
+        orient = {(3, 3): 1, (5, 1): 1, (1, 5): 2}[(KH, KW)]
+        ld16 = (Cin + 7) // 8 * 8
+        x16 = split_f16(xh, ld16)
+        taps = KH if orient == 1 else KW
+        bw, bh = (8, 16 + taps - 1) if orient == 1 else (16 + taps - 1, 8)
+        maps = (C.c_uint8 * 512)()
+        L = _lib.lib()
+        for j in range(2):
+            check(L.bflow_tma_tile_map(C.addressof(maps) + 128 * j, x16[j].data_ptr(), N, H, W, Cin, ld16, bw, bh, 1 if orient == 2 else 0), 'tma_tile_map')
+        wtc, acc_scale = pack_conv_weight_tc(weight, bn, block_per_tap=True)
+        err = torch.zeros(1, device=x.device, dtype=torch.int32)
+        d.x0 = None
+        check(L.bflow_conv2d_nhwc_tc3s(C.byref(d), C.addressof(maps), wtc.data_ptr(), bn, acc_scale, orient, err.data_ptr(), _stream()), 'conv2d_tc3s')
+        if int(err.item()) != 0:
+            raise RuntimeError('bflow_conv2d_nhwc_tc3s: pipeline wait timed out inside the kernel')
+    elif backend == 'tc3':
         x16 = split_f16(xh, (Cin + 7) // 8 * 8)
         m = tma_im2col_maps(x16, N, H, W, Cin, KH, KW, stride, ph, pw)
         maps = (C.c_uint8 * 512)()
@@ -181,7 +197,7 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         maps = (C.c_uint8 * 256)()
         L = _lib.lib()
         for j in range(2):
-            check(L.bflow_tma_tile_map(C.addressof(maps) + 128 * j, x16[j].data_ptr(), N, H, W, 64, 64, 8, 18), 'tma_tile_map')
+            check(L.bflow_tma_tile_map(C.addressof(maps) + 128 * j, x16[j].data_ptr(), N, H, W, 64, 64, 8, 18, 0), 'tma_tile_map')
         wtc, acc_scale = pack_conv_weight_tc(weight, 64, block_per_tap=True)
         err = torch.zeros(1, device=x.device, dtype=torch.int32)
         d.x0 = None

@@ -122,7 +122,11 @@ int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* d, const void* maps, const void
  * weights resident in shared memory, one 8 x 18 halo slab per filter column serves the three filter rows (4x less L2 -> SM traffic than
  * the im2col kernel).  maps: {hi, lo} tensor maps from bflow_tma_tile_map(..., box_w 8, box_h 18); w_tc: the tc3 weight image for bn = 64.
  * Standard epilogue only (none / relu, split residual, fp32 and / or split output, fused InstanceNorm sums). */
-int bflow_tma_tile_map(void* map_out_128B, const void* base_fp16, int N, int H, int W, int C, int ld_halves, int box_w, int box_h);
+int bflow_tma_tile_map(void* map_out_128B, const void* base_fp16, int N, int H, int W, int C, int ld_halves, int box_w, int box_h, int transposed);
+/* bflow_conv2d_nhwc_tc3 in slab mode (stride-1 3x3, 5x1: orientation 1; 1x5, 3x3: orientation 2): output tiles are 8 x 16 pixel patches and one halo
+ * slab per slow filter index serves all taps along the other axis; `maps` = tiled maps (bflow_tma_tile_map, box 8 x (16 + taps - 1) pixels,
+ * transposed = orientation 2) in the same {source0 hi, source0 lo, source1 hi, source1 lo} order.  Same weights, epilogues and outputs. */
+int bflow_conv2d_nhwc_tc3s(const bflow_conv_desc* d, const void* maps, const void* w_tc, int bn, float acc_scale, int orientation, int* err, void* stream);
 int bflow_conv2d_slab64(const bflow_conv_desc* d, const void* maps, const void* w_tc, float acc_scale, int* err, void* stream);
 /* Fused encoder stem (extractor.py:112): 7x7 / stride 2 / pad 3 over n_windows (<= 8) channel windows [c_offs[i], c_offs[i] + cin) of an fp32
  * NCHW input of N / n_windows samples (cin <= 5, W % 4 == 0; output image i * samples + s = window i of sample s: the torch.cat of

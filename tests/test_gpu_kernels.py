@@ -80,6 +80,26 @@ def test_conv2d_tc3_matches_torch(N, Cin, H, W, Cout, k, s, p, act, bn):
     assert (out - ref).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize('N,Cin,H,W,Cout,k,p,act,bn', [
+    (1, 64, 16, 8, 64, (3, 3), (1, 1), 'none', 64),            # one tile
+    (1, 256, 60, 80, 192, (3, 3), (1, 1), 'relu', 64),         # convc2 shape: 40 x 3 single-tile CTAs, ragged tile rows (60 = 3.75 x 16)
+    (1, 256, 60, 80, 256, (1, 5), (0, 2), 'sigmoid', 128),     # GRU horizontal pass: transposed slabs
+    (1, 256, 60, 80, 128, (5, 1), (2, 0), 'tanh', 64),         # GRU vertical pass
+    (2, 96, 50, 44, 96, (3, 3), (1, 1), 'relu', 128),          # channels beyond C zero-filled, ragged both ways, 2 images
+    (5, 128, 60, 80, 128, (3, 3), (1, 1), 'none', 128),        # multi-tile CTAs (200 tiles)
+    (1, 128, 13, 21, 124, (3, 3), (1, 1), 'relu', 64),         # ragged Cout
+])
+def test_conv2d_tc3_slab_mode_matches_torch(N, Cin, H, W, Cout, k, p, act, bn):
+    """Slab mode of the TMA-fed kernel (8 x 16 pixel tiles, halo slabs, both orientations) through every epilogue it can meet."""
+    x = torch.randn(N, Cin, H, W, generator=g(1))
+    w = torch.randn(Cout, Cin, *k, generator=g(2)) / (Cin * k[0] * k[1]) ** 0.5
+    b = torch.randn(Cout, generator=g(3))
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride=1, padding=p).float()
+    ref = {'none': lambda t: t, 'relu': torch.relu, 'sigmoid': torch.sigmoid, 'tanh': torch.tanh}[act](ref)
+    out = ops.conv2d(x.to(DEV), w.to(DEV), b.to(DEV), stride=1, padding=p, act=act, backend='tc3s', bn=bn).cpu()
+    assert (out - ref).abs().max() < 1e-4
+
+
 @pytest.mark.parametrize('N,H,W,act', [(1, 16, 8, 'none'), (2, 40, 24, 'relu'), (3, 37, 16, 'none'), (5, 120, 160, 'relu')])
 def test_conv2d_slab64_matches_torch(N, H, W, act):
     """Slab kernel (weights resident, halo slabs): 3x3/1, 64 -> 64; ragged tile rows (H % 16 != 0), several images, multi-tile CTAs."""
