@@ -269,7 +269,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 }
             }
         } else if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t it = 0, ps_ = 0, pph = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int m_tile = tile / p.n_ntiles, n_tile = tile - m_tile * p.n_ntiles;
                 const int m0 = m_tile * T3_BM;
@@ -283,10 +283,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 for (int tap = 0; tap < p.ntaps; ++tap) {
                     const int kh = tap / d.KW, kw = tap - kh * d.KW;
                     for (int cb = 0; cb < p.ncb0 + p.ncb1; ++cb, ++kb, ++it) {
-                        const int s = (int)(it % STAGES);
-                        const uint32_t ph = (it / STAGES) & 1u;
-                        t3_mbar_wait(empty_bar(s), ph ^ 1u, err);
-                        T3_TRACE(0, it);
+                        const int s = (int)ps_;
+                        t3_mbar_wait(empty_bar(s), pph ^ 1u, err);
+                        if (++ps_ == STAGES) {
+                            ps_ = 0;
+                            pph ^= 1u;
+                        }
                         if (it == 0) T3_CTA(2);
                         const uint32_t stage = smem_base + (uint32_t)s * STAGE_BYTES;
                         const uint32_t bar = full_bar(s);
@@ -309,7 +311,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
         // fp16 x fp16 -> fp32, K-major, M 128, N = BN (idesc) or 2 BN (idesc2)
         const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
         const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
-        uint32_t it = 0, lt = 0, ia = 0, ib = 0;
+        uint32_t lt = 0, ia = 0, ib = 0, ms = 0, mph = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
             const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
             t3_mbar_wait(tempty_bar(acc), aph ^ 1u, err);          // epilogue has drained this accumulator
@@ -353,41 +355,39 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 }
                 continue;
             }
-            for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-                const int s = (int)(it % STAGES);
-                const uint32_t ph = (it / STAGES) & 1u;
-                t3_mbar_wait(full_bar(s), ph, err);
-                t3_fence_after();
-                if (lane == 0) T3_TRACE(1, it);
-                if (lane == 0 && it == 0) T3_CTA(3);
-                if (lane == 0) {
-                    const uint32_t a_hi = smem_base + (uint32_t)s * STAGE_BYTES;
-                    const uint32_t a_lo = a_hi + T3_A_BYTES;
-                    const uint32_t b_hi = a_hi + 2 * T3_A_BYTES;
-                    const uint32_t b_lo = b_hi + B_BYTES;
+            // The single issuing thread is the bottleneck of the narrow (bn 64) tiles -- ~70 cycles per tcgen05.mma, so everything else in this
+            // loop is kept off its path: stage index and phase are carried, not divided out; descriptors advance by adding to a per-stage base.
+            if (lane == 0) {
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    t3_mbar_wait(full_bar(ms), mph, err);
+                    t3_fence_after();
+                    const uint32_t a_hi = smem_base + (uint32_t)ms * STAGE_BYTES;
+                    const uint64_t dah0 = t3_umma_desc(a_hi);
+                    const uint64_t dal0 = dah0 + (uint64_t)(T3_A_BYTES >> 4);
+                    const uint64_t dbh0 = dah0 + (uint64_t)((2 * T3_A_BYTES) >> 4);
+                    const uint64_t dbl0 = dbh0 + (uint64_t)(B_BYTES >> 4);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if ((p.dbg & 2) && (kb > 0 || k > 0)) break;      // development: one MMA per tile (load path alone)
-                        const uint32_t ko = (uint32_t)k * 32u;
-                        const uint64_t dah = t3_umma_desc(a_hi + ko), dal = t3_umma_desc(a_lo + ko);
-                        const uint64_t dbh = t3_umma_desc(b_hi + ko);
+                        const uint64_t ko = (uint64_t)(k * 2);             // 32 bytes along K, in 16-byte descriptor units
                         if (STACK) {
-                            t3_umma(tacc, dah, dbh, idesc2, (kb > 0 || k > 0) ? 1u : 0u);      // hi*hi | hi*lo
-                            t3_umma(tacc, dal, dbh, idesc, 1u);                               // lo*hi
+                            t3_umma(tacc, dah0 + ko, dbh0 + ko, idesc2, (kb > 0 || k > 0) ? 1u : 0u);      // hi*hi | hi*lo
+                            t3_umma(tacc, dal0 + ko, dbh0 + ko, idesc, 1u);                               // lo*hi
                         } else {
-                            const uint64_t dbl = t3_umma_desc(b_lo + ko);
-                            t3_umma(tacc, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                            t3_umma(tacc, dah, dbl, idesc, 1u);
-                            t3_umma(tacc, dal, dbh, idesc, 1u);
+                            t3_umma(tacc, dah0 + ko, dbh0 + ko, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            t3_umma(tacc, dah0 + ko, dbl0 + ko, idesc, 1u);
+                            t3_umma(tacc, dal0 + ko, dbh0 + ko, idesc, 1u);
                         }
                     }
-                    t3_commit(empty_bar(s));
-                    if (kb == p.nkb - 1) t3_commit(tfull_bar(acc));
-                    if (kb == p.nkb - 1) T3_CTA(4);
-                    T3_TRACE(2, it);
+                    t3_commit(empty_bar(ms));
+                    if (++ms == STAGES) {
+                        ms = 0;
+                        mph ^= 1u;
+                    }
                 }
-                __syncwarp();
+                t3_commit(tfull_bar(acc));
+                T3_CTA(4);
             }
+            __syncwarp();
         }
         t3_fence_before();
     } else {

@@ -113,8 +113,9 @@ class S16Recorder:
         bn = choose_bn(wt.cout, (M + 127) // 128)
         img, acc_scale = wt.tc3_image(bn, c0)
         orient = {(3, 3): 1, (5, 1): 1, (1, 5): 2}.get((wt.kh, wt.kw), 0)
-        if (orient and wt.stride == 1 and (ph, pw) == (wt.kh // 2, wt.kw // 2) and bn <= 128 and os.environ.get('BFLOW_TC3_SLAB', '1') != '0'):
-            # halo slabs instead of im2col rows: A traffic / 2.7 (3x3) ... / 4 (1x5, 5x1)
+        if (orient and wt.stride == 1 and (ph, pw) == (wt.kh // 2, wt.kw // 2) and bn <= 128 and os.environ.get('BFLOW_TC3_SLAB', '0') == '1'):
+            # halo slabs instead of im2col rows: A traffic / 2.7 (3x3) ... / 4 (1x5, 5x1).  Opt-in: measured on B200 it buys nothing here -- the
+            # main loops of these layers are bound by the tensor pipe (bn 128) or by MMA issue (bn 64), not by L2 -> SM traffic
             taps = wt.kh if orient == 1 else wt.kw
             bw, bh = (8, 16 + taps - 1) if orient == 1 else (16 + taps - 1, 8)
             maps = (C.c_uint8 * 512)()
