@@ -426,6 +426,34 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
         };
         int stat_n0 = 0;
         if (d.stats != nullptr) flush_stats(-1, 0);
+        // column sums of 16 consecutive channels over the warp's 32 tile rows (all of one image): butterfly transpose-reduce, then the lanes with
+        // the low bit clear own one column each and add (sum, sum of squares) to the CTA's shared accumulators
+        auto stat16 = [&](const float* x, int col0) {
+            float sv[16], sq[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                sv[j] = x[j];
+                sq[j] = x[j] * x[j];
+            }
+#pragma unroll
+            for (int width = 8, bit = 16; width >= 1; width >>= 1, bit >>= 1) {
+                const bool upper = (lane & bit) != 0;
+#pragma unroll
+                for (int i = 0; i < width; ++i) {
+                    const float keep_s = upper ? sv[width + i] : sv[i], send_s = upper ? sv[i] : sv[width + i];
+                    const float keep_q = upper ? sq[width + i] : sq[i], send_q = upper ? sq[i] : sq[width + i];
+                    sv[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
+                    sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
+                }
+            }
+            const float ts = sv[0] + __shfl_xor_sync(0xffffffffu, sv[0], 1);
+            const float tq = sq[0] + __shfl_xor_sync(0xffffffffu, sq[0], 1);
+            if ((lane & 1) == 0) {
+                const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                atomicAdd(s_stat + col0 + col, ts);
+                atomicAdd(s_stat + BN + col0 + col, tq);
+            }
+        };
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
             const int m_tile = tile / p.n_ntiles, n_tile = tile - m_tile * p.n_ntiles;
             // tile row -> output pixel.  im2col mode: 128 consecutive pixels; slab mode: an 8 x 16 patch of image t_n at (t_y0, t_x0)
@@ -504,9 +532,21 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
 #pragma unroll
                         for (int c = 0; c < 32; c += 4) {
                             const float4 b4 = *reinterpret_cast<const float4*>(s_bias + chalf * HALF + c0 + c);
-                            *reinterpret_cast<float4*>(trow + c0 + c) =
-                                make_float4(fmaxf(post * fmaf(v[c], p.acc_scale, b4.x), lo1), fmaxf(post * fmaf(v[c + 1], p.acc_scale, b4.y), lo1),
-                                            fmaxf(post * fmaf(v[c + 2], p.acc_scale, b4.z), lo1), fmaxf(post * fmaf(v[c + 3], p.acc_scale, b4.w), lo1));
+                            v[c] = fmaxf(post * fmaf(v[c], p.acc_scale, b4.x), lo1);
+                            v[c + 1] = fmaxf(post * fmaf(v[c + 1], p.acc_scale, b4.y), lo1);
+                            v[c + 2] = fmaxf(post * fmaf(v[c + 2], p.acc_scale, b4.z), lo1);
+                            v[c + 3] = fmaxf(post * fmaf(v[c + 3], p.acc_scale, b4.w), lo1);
+                            *reinterpret_cast<float4*>(trow + c0 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                        }
+                        if (d.stats != nullptr) {          // host contract: no activation with statistics, every tile inside one image
+                            bool rok_;
+                            (void)row_m(quad * 32 + lane, rok_);
+                            if (!rok_) {
+#pragma unroll
+                                for (int c = 0; c < 32; ++c) v[c] = 0.f;
+                            }
+                            if (nb0 + c0 + 15 < d.Cout) stat16(v, chalf * HALF + c0);
+                            if (nb0 + c0 + 31 < d.Cout) stat16(v + 16, chalf * HALF + c0 + 16);
                         }
                     }
                 }
@@ -1747,7 +1787,11 @@ static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* w_
             const char* e = getenv("BFLOW_TC3_MSTORE");
             mstore_on = (e != nullptr && e[0] == '0') ? 0 : 1;
         }
-        if (mstore_on && !slab && !single && bn == 128 && d.epi == BFLOW_EPI_STD && d.stats == nullptr && d.res == nullptr && d.res16_hi == nullptr &&
+        const long long shw_ = d.stats_hw > 0 ? d.stats_hw : (long long)d.Ho * d.Wo;
+        // with fused statistics: a tile must not straddle two images, and only short main loops (<= 12 k-blocks) are epilogue-bound enough to
+        // pay for the lost pipeline stage (measured: 64->96 3x3/2 80 -> 61 us, 1x1/2 59 -> 38 us, but 96->96 3x3 85 -> 90 us)
+        const bool stats_ok = d.stats == nullptr || (shw_ % bflow::T3_BM == 0 && d.Cout % 16 == 0 && p.nkb <= 12);
+        if (mstore_on && !slab && !single && bn == 128 && d.epi == BFLOW_EPI_STD && stats_ok && d.res == nullptr && d.res16_hi == nullptr &&
             d.y16_hi == nullptr && d.y != nullptr && a16(d.y) && d.ldy % 4 == 0 && d.Cout % 4 == 0 && d.act1 <= BFLOW_ACT_RELU && d.act2 == BFLOW_ACT_NONE)
             p.staged = 3;
     }

@@ -1,14 +1,16 @@
 # Round-end evidence: GPU tests, bench (both arms), in-graph timeline, ncu launch list of one eager step, ncu --set full captures of the
-# roofline kernel and the three tensor-core kernels.  Everything lands in gpurun_out/ (copy what should be judged into profiles/).
+# roofline kernel and the tensor-core kernels.  Everything lands in gpurun_out/ (copy what should be judged into profiles/).
 mkdir -p gpurun_out
 timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/pytest_gpu.txt
 timeout 400 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
 timeout 200 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
+timeout 200 python bench.py --batch-per-gpu 4 --no-cpu-baseline --no-sweep > gpurun_out/bench_b4.json 2> gpurun_out/bench_b4.err
 timeout 120 python tools/timeline.py --raw > gpurun_out/timeline_final.txt 2>&1
+timeout 120 python tools/timeline.py --preset E_I_LU5_BD10 --batch 4 --h 384 --w 512 > gpurun_out/timeline_configM.txt 2>&1
 timeout 120 python tools/step_profile.py --all > gpurun_out/step_profile_final.txt 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:bflow:: --launch-skip 211 -c 211 --csv --log-file gpurun_out/launches_step_final.csv python tools/one_step.py > gpurun_out/ncu1.log 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:corr_lookup --launch-skip 14 -c 1 -f -o gpurun_out/lookup_instep_final python tools/one_step.py > gpurun_out/ncu2.log 2>&1
-timeout 200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:conv_slab64 --launch-skip 9 -c 1 -f -o gpurun_out/slab64_final python tools/one_step.py > gpurun_out/ncu3.log 2>&1
+timeout 200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:conv_slab64 --launch-skip 4 -c 1 -f -o gpurun_out/slab64_final python tools/one_step.py > gpurun_out/ncu3.log 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:conv_stem7 --launch-skip 2 -c 1 -f -o gpurun_out/stem7_final python tools/one_step.py > gpurun_out/ncu4.log 2>&1
-timeout 200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:conv_tc3_kernel --launch-skip 300 -c 2 -f -o gpurun_out/tc3_update_final python tools/one_step.py > gpurun_out/ncu5.log 2>&1
-ls -la gpurun_out | tail -20
+timeout 200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:conv_tc3_kernel --launch-skip 200 -c 4 -f -o gpurun_out/tc3_update_final python tools/one_step.py > gpurun_out/ncu5.log 2>&1
+ls -la gpurun_out | tail -24
