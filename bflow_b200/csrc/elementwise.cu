@@ -129,22 +129,24 @@ __global__ void __launch_bounds__(256) instnorm_relu16_kernel(const float* __res
     __shared__ float mu_a[IN_MAXC], rs_a[IN_MAXC], mu_r[IN_MAXC], rs_r[IN_MAXC];
     const int n = blockIdx.y;
     tl_begin(tl);
+    const double inv_hw = 1.0 / (double)HW;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        // fp64 only where cancellation needs it (E[x^2] - E[x]^2): no fp64 divide / sqrt (slow on this part and paid by every CTA)
         double s = sums_a[((size_t)n * C + c) * 2], ss = sums_a[((size_t)n * C + c) * 2 + 1];
-        double m = s / HW;
-        double var = ss / HW - m * m;
+        double m = s * inv_hw;
+        double var = ss * inv_hw - m * m;
         if (var < 0.0) var = 0.0;
         mu_a[c] = (float)m;
-        rs_a[c] = (float)(1.0 / sqrt(var + (double)eps));
+        rs_a[c] = rsqrtf((float)(var + (double)eps));
         mu_r[c] = 0.f;
         rs_r[c] = 1.f;
         if (sums_r != nullptr) {
             s = sums_r[((size_t)n * C + c) * 2]; ss = sums_r[((size_t)n * C + c) * 2 + 1];
-            m = s / HW;
-            var = ss / HW - m * m;
+            m = s * inv_hw;
+            var = ss * inv_hw - m * m;
             if (var < 0.0) var = 0.0;
             mu_r[c] = (float)m;
-            rs_r[c] = (float)(1.0 / sqrt(var + (double)eps));
+            rs_r[c] = rsqrtf((float)(var + (double)eps));
         }
     }
     __syncthreads();
