@@ -67,6 +67,18 @@ __device__ __forceinline__ void t3_mbar_wait(uint32_t bar, uint32_t parity, int*
         if (t3_mbar_try_wait(bar, parity)) return;
     if (err != nullptr) atomicExch(err, 1);
 }
+// one lane of a CONVERGED warp (elect.sync): the branch it guards is the idiom under which nvcc keeps warp-uniform operands in uniform
+// registers and issues UTCHMMA / UTCBAR directly.  Under `if (lane == 0)` it wraps every tcgen05.mma in an ELECT + 5 x R2UR + loop
+// "waterfall" -- ~70 cycles per instruction on the one thread that feeds the tensor pipe (measured: 576 of 1094 cycles per k-block).
+__device__ __forceinline__ bool t3_elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void t3_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void t3_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -185,7 +197,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
     const uint32_t sl_bring = smem_base + SL_NSA * SL_SLAB_MAX;          // weight-tile ring behind the slab ring
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5;
+    // warp index through a shuffle: nvcc then treats it (and every branch on it) as warp-uniform, which is what lets the role loops below keep
+    // their operands in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int lane = tid & 31;
     const int n_tiles = p.n_mtiles * p.n_ntiles;
 
@@ -284,8 +298,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                     const int kh = tap / d.KW, kw = tap - kh * d.KW;
                     for (int cb = 0; cb < p.ncb0 + p.ncb1; ++cb, ++kb, ++it) {
                         const int s = (int)ps_;
-                        t3_mbar_wait(empty_bar(s), pph ^ 1u, err);
-                        if (++ps_ == STAGES) {
+                        if (p.dbg & 256) {
+                            while (!t3_mbar_test_wait(empty_bar(s), pph ^ 1u)) {}
+                        } else {
+                            t3_mbar_wait(empty_bar(s), pph ^ 1u, err);
+                        }
+                        if (++ps_ == ((p.dbg & 512) ? 2u : (uint32_t)STAGES)) {
                             ps_ = 0;
                             pph ^= 1u;
                         }
@@ -355,17 +373,18 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 }
                 continue;
             }
-            // The single issuing thread is the bottleneck of the narrow (bn 64) tiles -- ~70 cycles per tcgen05.mma, so everything else in this
-            // loop is kept off its path: stage index and phase are carried, not divided out; descriptors advance by adding to a per-stage base.
-            if (lane == 0) {
-                for (int kb = 0; kb < p.nkb; ++kb) {
-                    t3_mbar_wait(full_bar(ms), mph, err);
-                    t3_fence_after();
-                    const uint32_t a_hi = smem_base + (uint32_t)ms * STAGE_BYTES;
-                    const uint64_t dah0 = t3_umma_desc(a_hi);
-                    const uint64_t dal0 = dah0 + (uint64_t)(T3_A_BYTES >> 4);
-                    const uint64_t dbh0 = dah0 + (uint64_t)((2 * T3_A_BYTES) >> 4);
-                    const uint64_t dbl0 = dbh0 + (uint64_t)(B_BYTES >> 4);
+            // The issuing thread is the bottleneck of this kernel's main loop, so the loop runs warp-converged (every lane waits on the barrier,
+            // stage index and phase are carried, descriptors are base + constant) and only the MMA / commit instructions sit under elect.sync.
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                t3_mbar_wait(full_bar(ms), mph, err);
+                t3_fence_after();
+                const uint32_t a_hi = smem_base + ms * (uint32_t)STAGE_BYTES;
+                const uint64_t dah0 = t3_umma_desc(a_hi);
+                const uint64_t dal0 = dah0 + (uint64_t)(T3_A_BYTES >> 4);
+                const uint64_t dbh0 = dah0 + (uint64_t)((2 * T3_A_BYTES) >> 4);
+                const uint64_t dbl0 = dbh0 + (uint64_t)(B_BYTES >> 4);
+                const uint32_t ebar_s = empty_bar(ms);
+                if (t3_elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t ko = (uint64_t)(k * 2);             // 32 bytes along K, in 16-byte descriptor units
@@ -378,16 +397,18 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                             t3_umma(tacc, dal0 + ko, dbh0 + ko, idesc, 1u);
                         }
                     }
-                    t3_commit(empty_bar(ms));
-                    if (++ms == STAGES) {
-                        ms = 0;
-                        mph ^= 1u;
+                    t3_commit(ebar_s);
+                    if (kb == p.nkb - 1) {
+                        t3_commit(tfull_bar(acc));
+                        T3_CTA(4);
                     }
                 }
-                t3_commit(tfull_bar(acc));
-                T3_CTA(4);
+                __syncwarp();
+                if (++ms == (uint32_t)STAGES) {
+                    ms = 0;
+                    mph ^= 1u;
+                }
             }
-            __syncwarp();
         }
         t3_fence_before();
     } else {
@@ -993,7 +1014,7 @@ conv_slab64_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     auto tempty_bar = [&](int a) { return bars + 80u + 8u * (uint32_t)a; };
     const uint32_t tmem_slot = bars + 96u;
     const uint32_t wbar = bars + 104u;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;      // warp-uniform role index (see conv_tc3_kernel)
     tl_begin(p.tl);
     if (tid == 0) {
         for (int s = 0; s < SL_STAGES; ++s) {
@@ -1239,7 +1260,7 @@ conv_stem7_kernel(const bflow_conv_desc d, const uint8_t* __restrict__ wtc, cons
     int* koff = reinterpret_cast<int*>(gen + ST_A_BYTES + ST_B_BYTES + ST_PATCH_BYTES + 64);       // [256] patch offset of k, -1 beyond K
     float* s_bias = reinterpret_cast<float*>(koff + 256);                                           // [64]
     float* s_stat = s_bias + SL_BN;                                                                  // [2][64]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;      // warp-uniform role index (see conv_tc3_kernel)
     tl_begin(p.tl);
     if (tid == 0) {
         t3_mbar_init(a_full, 256);

@@ -77,6 +77,9 @@ def main():
         names = ['prod:empty-ok', 'mma:full-ok', 'mma:committed', 'epi:tfull-ok', 'epi:tmem-released', 'epi:tile-done']
         print('cta start', int(tr[5, 255]) - t0, 'prologue done', int(tr[3, 255]) - t0, 'cta end', int(tr[4, 255]) - t0, '(SM cycles)')
         tr[5, 255] = 0; tr[3, 255] = 0; tr[4, 255] = 0
+        for nm, r in (('mma:before-wait', 3), ('mma:issued', 4)):
+            print(f'{nm:18s}', [int(v) - t0 for v in tr[r, 100:140] if int(v) > 0])
+        tr[3, 100:] = 0; tr[4, 100:] = 0
         for r in range(6):
             vals = [int(v) - t0 for v in tr[r] if int(v) > 0][:40]
             print(f'{names[r]:18s}', vals)
