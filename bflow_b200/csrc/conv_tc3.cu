@@ -282,7 +282,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                     }
                 }
             }
-        } else if (lane == 0) {
+        } else if (!p.slab) {
+            // converged warp: every lane waits on the stage barrier, one elected lane issues (operands stay in uniform registers)
             uint32_t it = 0, ps_ = 0, pph = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int m_tile = tile / p.n_ntiles, n_tile = tile - m_tile * p.n_ntiles;
@@ -307,19 +308,22 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                             ps_ = 0;
                             pph ^= 1u;
                         }
-                        if (it == 0) T3_CTA(2);
+                        if (it == 0 && lane == 0) T3_CTA(2);
                         const uint32_t stage = smem_base + (uint32_t)s * STAGE_BYTES;
                         const uint32_t bar = full_bar(s);
-                        if (p.dbg & 1) {                 // development: no loads (MMA + epilogue path alone)
-                            t3_mbar_arrive(bar);
-                            continue;
-                        }
-                        t3_mbar_arrive_expect_tx(bar, TX_BYTES);
                         const bool src0 = cb < p.ncb0;
                         const int cc = (src0 ? cb : cb - p.ncb0) * 64;
-                        t3_tma_im2col(stage, src0 ? &map0h : &map1h, cc, cw, ch, n, (uint16_t)kw, (uint16_t)kh, bar);
-                        t3_tma_im2col(stage + T3_A_BYTES, src0 ? &map0l : &map1l, cc, cw, ch, n, (uint16_t)kw, (uint16_t)kh, bar);
-                        t3_bulk_g2s(stage + 2 * T3_A_BYTES, wt + (size_t)kb * (2 * B_BYTES), 2 * B_BYTES, bar);
+                        if (t3_elect_one()) {
+                            if (p.dbg & 1) {                 // development: no loads (MMA + epilogue path alone)
+                                t3_mbar_arrive(bar);
+                            } else {
+                                t3_mbar_arrive_expect_tx(bar, TX_BYTES);
+                                t3_tma_im2col(stage, src0 ? &map0h : &map1h, cc, cw, ch, n, (uint16_t)kw, (uint16_t)kh, bar);
+                                t3_tma_im2col(stage + T3_A_BYTES, src0 ? &map0l : &map1l, cc, cw, ch, n, (uint16_t)kw, (uint16_t)kh, bar);
+                                t3_bulk_g2s(stage + 2 * T3_A_BYTES, wt + (size_t)kb * (2 * B_BYTES), 2 * B_BYTES, bar);
+                            }
+                        }
+                        __syncwarp();
                     }
                 }
             }
@@ -349,7 +353,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                                 const int sb = (int)(ib % SL_NSB);
                                 t3_mbar_wait(full_bar(sb), (ib / SL_NSB) & 1u, err);
                                 t3_fence_after();
-                                if (lane == 0) {
+                                if (t3_elect_one()) {
                                     const uint32_t b_hi = sl_bring + (uint32_t)sb * (2 * B_BYTES);
 #pragma unroll
                                     for (int k = 0; k < 4; ++k) {
@@ -1040,23 +1044,27 @@ conv_slab64_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     const int tiles_per_img = p.tiles_x * p.tiles_y;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (t3_elect_one()) {
             t3_mbar_arrive_expect_tx(wbar, SL_B_BYTES);
             for (int t = 0; t < 9; ++t) t3_bulk_g2s(bres + (uint32_t)t * (2 * SL_BN * 128), wtc + (size_t)t * (2 * SL_BN * 128), 2 * SL_BN * 128, wbar);
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
-                const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-                const int x0 = tx * 8, y0 = ty * 16;
-                for (int kw = 0; kw < 3; ++kw, ++it) {
-                    const int s = (int)(it % SL_STAGES);
-                    const uint32_t ph = (it / SL_STAGES) & 1u;
-                    t3_mbar_wait(empty_bar(s), ph ^ 1u, err);
-                    const uint32_t st = stage0 + (uint32_t)s * SL_STAGE;
+        }
+        __syncwarp();
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
+            const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+            const int x0 = tx * 8, y0 = ty * 16;
+            for (int kw = 0; kw < 3; ++kw, ++it) {
+                const int s = (int)(it % SL_STAGES);
+                const uint32_t ph = (it / SL_STAGES) & 1u;
+                t3_mbar_wait(empty_bar(s), ph ^ 1u, err);
+                const uint32_t st = stage0 + (uint32_t)s * SL_STAGE;
+                if (t3_elect_one()) {
                     t3_mbar_arrive_expect_tx(full_bar(s), SL_STAGE);
                     sl_tma_tile(st, &map_hi, 0, x0 + kw - 1, y0 - 1, n, full_bar(s));
                     sl_tma_tile(st + SL_PLANE, &map_lo, 0, x0 + kw - 1, y0 - 1, n, full_bar(s));
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
@@ -1074,7 +1082,7 @@ conv_slab64_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
                 const uint32_t ph = (it / SL_STAGES) & 1u;
                 t3_mbar_wait(full_bar(s), ph, err);
                 t3_fence_after();
-                if (lane == 0) {
+                if (t3_elect_one()) {
                     const uint32_t a_hi = stage0 + (uint32_t)s * SL_STAGE, a_lo = a_hi + SL_PLANE;
 #pragma unroll
                     for (int kh = 0; kh < 3; ++kh) {
@@ -1322,7 +1330,7 @@ conv_stem7_kernel(const bflow_conv_desc d, const uint8_t* __restrict__ wtc, cons
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
             t3_mbar_wait(a_full, lt & 1u, err);
             t3_fence_after();
-            if (lane == 0) {
+            if (t3_elect_one()) {
                 const uint32_t tacc = tmem_base + (lt & 1u) * ACC_COLS;
 #pragma unroll
                 for (int kb = 0; kb < ST_NKB; ++kb) {
