@@ -206,7 +206,6 @@ def main():
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if sampler else None
 
         # ---------------- end to end through the public API with host buffers ----------------
         for _ in range(2):
@@ -218,6 +217,9 @@ def main():
             up_h, low_h = up_c.cpu(), low_c.cpu()          # what the reference's @to_cpu does with the result
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
+        # the sampler (nvidia-smi at 100 ms) ran across both timed regions (device-resident and end-to-end): at 4 ms per step the first one
+        # alone is shorter than one sampling period
+        clocks = sampler.stop() if sampler else None
         barrier()
     t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
