@@ -66,6 +66,8 @@ _SIGNATURES = {
     'bflow_tma_im2col_map': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 10),
     'bflow_conv2d_nhwc_tc3': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     'bflow_tma_tile_map': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 8),
+    'bflow_tma_out_map': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int]),
+    'bflow_conv2d_nhwc_tc3o': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     'bflow_conv2d_nhwc_tc3s': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
     'bflow_conv2d_slab64': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     'bflow_conv2d_stem7': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),

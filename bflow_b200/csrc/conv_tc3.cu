@@ -151,6 +151,12 @@ __device__ __forceinline__ void sl_tma_tile(uint32_t dst, const CUtensorMap* map
                  : "memory");
 }
 
+__device__ __forceinline__ void t3_tma_store2d(const CUtensorMap* map, uint32_t src, int c, int r) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c),
+                 "r"(r)
+                 : "memory");
+}
+
 struct T3Params {
     int M, n_mtiles, n_ntiles, ntaps, ncb0, ncb1, nkb;
     float acc_scale;
@@ -167,7 +173,8 @@ struct T3Params {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant__ CUtensorMap map0l, const __grid_constant__ CUtensorMap map1h,
-                const __grid_constant__ CUtensorMap map1l, const bflow_conv_desc d, const uint8_t* __restrict__ wtc, const T3Params p, int* err) {
+                const __grid_constant__ CUtensorMap map1l, const __grid_constant__ CUtensorMap omap_hi, const __grid_constant__ CUtensorMap omap_lo,
+                const __grid_constant__ CUtensorMap omap32, const bflow_conv_desc d, const uint8_t* __restrict__ wtc, const T3Params p, int* err) {
     constexpr int B_BYTES = BN * 128;
     constexpr int STAGE_BYTES = 2 * T3_A_BYTES + 2 * B_BYTES;
     constexpr uint32_t TX_BYTES = 2 * T3_A_BYTES + 2 * B_BYTES;
@@ -526,7 +533,94 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
             if (warp == 2 && lane == 0) T3_CTA(5);
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_COLS + (uint32_t)(chalf * HALF);
             const int nb0 = n0 + chalf * HALF;
-            if (p.staged == 3) {
+            if (p.staged == 4) {
+                // Single-tile CTA, plain epilogue (bias, scale, none / relu), outputs through 2-D tensor-map stores: each thread converts its row
+                // straight from the accumulator into SWIZZLE_128B boxes in the idle pipeline stages ([128 rows][128 bytes] per 64 halves / 32
+                // floats of width; chunk j of row r sits at j ^ (r & 7), so the 16-byte stores of a quarter-warp hit 8 different bank groups), and
+                // ONE thread issues a cp.async.bulk.tensor per box.  Rows beyond M and channels beyond Cout are clipped by the tensor map.
+                // (The per-row bulk-copy variant below spent 2.3 us issuing 256 row copies and 1.7 us in a separate conversion pass.)
+                uint8_t* sb = smem_raw + (smem_base - t3_smem_u32(smem_raw));
+                constexpr int NB16 = (BN + 63) / 64, NB32 = (BN + 31) / 32;          // boxes per plane
+                uint8_t* s_hi = sb;
+                uint8_t* s_lo = sb + NB16 * 16384;
+                uint8_t* s_32 = sb + 2 * NB16 * 16384;
+                const bool o16 = d.y16_hi != nullptr, o32 = d.y != nullptr;
+                const int row = quad * 32 + lane;
+                const int colbase = chalf * HALF;
+#pragma unroll 1
+                for (int c0 = 0; c0 < HALF; c0 += 32) {
+                    float v[32];
+                    t3_tmem_ld16_nowait(taddr + (uint32_t)c0, v);
+                    t3_tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), v + 16);
+                    if (STACK) {
+                        float u[32];
+                        t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0), u);
+                        t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0 + 16), u + 16);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] += u[c];
+                    } else {
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    }
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + colbase + c0 + c);
+                        v[c] = fmaxf(fmaxf(post * fmaf(v[c], p.acc_scale, b4.x), lo1), lo2);
+                        v[c + 1] = fmaxf(fmaxf(post * fmaf(v[c + 1], p.acc_scale, b4.y), lo1), lo2);
+                        v[c + 2] = fmaxf(fmaxf(post * fmaf(v[c + 2], p.acc_scale, b4.z), lo1), lo2);
+                        v[c + 3] = fmaxf(fmaxf(post * fmaf(v[c + 3], p.acc_scale, b4.w), lo1), lo2);
+                    }
+                    const int col = colbase + c0;                  // first of these 32 columns inside the tile
+                    if (o16) {
+                        uint8_t* bh = s_hi + (col >> 6) * 16384 + row * 128;
+                        uint8_t* bl = s_lo + (col >> 6) * 16384 + row * 128;
+#pragma unroll
+                        for (int c = 0; c < 32; c += 8) {
+                            uint4 h4, l4;
+                            split2(v[c], v[c + 1], h4.x, l4.x);
+                            split2(v[c + 2], v[c + 3], h4.y, l4.y);
+                            split2(v[c + 4], v[c + 5], h4.z, l4.z);
+                            split2(v[c + 6], v[c + 7], h4.w, l4.w);
+                            const int chunk = (((col & 63) + c) >> 3) ^ (row & 7);
+                            *reinterpret_cast<uint4*>(bh + (chunk << 4)) = h4;
+                            *reinterpret_cast<uint4*>(bl + (chunk << 4)) = l4;
+                        }
+                    }
+                    if (o32) {
+                        uint8_t* b3 = s_32 + (col >> 5) * 16384 + row * 128;
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) {
+                            const int chunk = (c >> 2) ^ (row & 7);
+                            *reinterpret_cast<float4*>(b3 + (chunk << 4)) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                        }
+                    }
+                }
+                if (warp == 2 && lane == 0) T3_CTA(8);
+                t3_fence_before();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (warp == 2 && t3_elect_one()) {
+                    const int mt0 = m_tile * T3_BM;
+                    if (o16) {
+#pragma unroll
+                        for (int b = 0; b < NB16; ++b) {
+                            if (n0 + b * 64 < d.Cout) {
+                                t3_tma_store2d(&omap_hi, t3_smem_u32(s_hi + b * 16384), n0 + b * 64, mt0);
+                                t3_tma_store2d(&omap_lo, t3_smem_u32(s_lo + b * 16384), n0 + b * 64, mt0);
+                            }
+                        }
+                    }
+                    if (o32) {
+#pragma unroll
+                        for (int b = 0; b < NB32; ++b)
+                            if (n0 + b * 32 < d.Cout) t3_tma_store2d(&omap32, t3_smem_u32(s_32 + b * 16384), n0 + b * 32, mt0);
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                }
+                __syncwarp();
+                if (lane == 0) t3_mbar_arrive(tempty_bar(acc));
+            } else if (p.staged == 3) {
                 // Multi-tile CTAs with a plain fp32 store epilogue (the all-pairs correlation GEMM, corr.py:264-272: 1444 tiles of 64 KB): the
                 // direct path below stores 16 bytes per row per instruction and was measured LSU-bound (~7 us per tile against a 2 us main
                 // loop).  Here the pipeline runs with one stage less and the freed shared memory is a [128][BN + 4] fp32 staging tile: the
@@ -1527,6 +1621,9 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                    CUtensorMapFloatOOBfill);
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
 static EncodeIm2colFn get_encode_im2col() {
     static EncodeIm2colFn fn = nullptr;
     if (fn == nullptr) {
@@ -1554,7 +1651,7 @@ static unsigned long long* g_tc3_cta = nullptr;
 static int g_tc3_cta_nth = -1, g_tc3_cta_count = 0;
 
 template <int BN, int STAGES>
-static int launch_tc3(const CUtensorMap* maps, const bflow_conv_desc& d, const void* wtc, const T3Params& p, int* err, cudaStream_t stream) {
+static int launch_tc3(const CUtensorMap* maps, const bflow_conv_desc& d, const void* wtc, const T3Params& p, int* err, cudaStream_t stream) {      // maps: 4 input + 3 output
     constexpr int smem = t3_area_bytes(BN, STAGES) + 128 + 3 * BN * 4 + 64 + 1024;
     static bool configured = false;
     if (!configured) {
@@ -1567,8 +1664,8 @@ static int launch_tc3(const CUtensorMap* maps, const bflow_conv_desc& d, const v
     }
     const int n_tiles = p.n_mtiles * p.n_ntiles;
     const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
-    cudaError_t le = launch_pdl(conv_tc3_kernel<BN, STAGES>, dim3(grid), dim3(T3_THREADS), smem, stream, maps[0], maps[1], maps[2], maps[3], d,
-                                reinterpret_cast<const uint8_t*>(wtc), p, err);
+    cudaError_t le = launch_pdl(conv_tc3_kernel<BN, STAGES>, dim3(grid), dim3(T3_THREADS), smem, stream, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
+                                maps[6], d, reinterpret_cast<const uint8_t*>(wtc), p, err);
     if (le != cudaSuccess) {
         set_error(cudaGetErrorString(le));
         return BFLOW_ERR_CUDA;
@@ -1730,7 +1827,8 @@ extern "C" int bflow_tma_im2col_map(void* map_out, const void* base, int N, int 
     return BFLOW_OK;
 }
 
-static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* w_tc, int bn, float acc_scale, int slab, int* err, void* stream) {
+static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* omaps, const void* w_tc, int bn, float acc_scale, int slab, int* err,
+                     void* stream) {
     BFLOW_REQUIRE(dp != nullptr && maps != nullptr && w_tc != nullptr, "conv_tc3: null argument");
     const bflow_conv_desc& d = *dp;
     if (slab) {
@@ -1827,8 +1925,24 @@ static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* w_
     p.trace = bflow::g_tc3_trace;
     p.cta = (bflow::g_tc3_cta != nullptr && bflow::g_tc3_cta_count++ == bflow::g_tc3_cta_nth) ? bflow::g_tc3_cta : nullptr;
     p.tl = bflow::timeline_next_slot(bn == 64 ? "tc3_64" : bn == 128 ? "tc3_128" : "tc3_256");
-    alignas(64) CUtensorMap tm[4];
-    memcpy(tm, maps, sizeof(tm));
+    alignas(64) CUtensorMap tm[7];
+    memset(tm, 0, sizeof(tm));
+    memcpy(tm, maps, 4 * sizeof(CUtensorMap));
+    if (omaps != nullptr) {
+        memcpy(tm + 4, omaps, 3 * sizeof(CUtensorMap));
+        // tensor-map store epilogue: single-tile CTAs, plain epilogue (none / relu), no residual / statistics
+        static int ostore_on = -1;
+        if (ostore_on < 0) {
+            const char* e = getenv("BFLOW_TC3_OSTORE");
+            ostore_on = (e != nullptr && e[0] == '0') ? 0 : 1;
+        }
+        const bool single1 = d.stats == nullptr && p.n_mtiles * p.n_ntiles <= bflow::num_sms();
+        // Cout % 8: measured on B200, a tensor-map store whose box is clipped inside a 16-byte chunk still writes the whole chunk (it
+        // overwrote the 4 Bezier-parameter channels behind the motion encoder's 124) -- ragged widths stay on the per-row bulk-copy path
+        if (ostore_on && single1 && !slab && bn <= 128 && d.Cout % 8 == 0 && d.epi == BFLOW_EPI_STD && d.res == nullptr && d.res16_hi == nullptr && d.act1 <= BFLOW_ACT_RELU &&
+            d.act2 <= BFLOW_ACT_RELU)
+            p.staged = 4;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     switch (bn) {
         case 64: return bflow::launch_tc3<64, 4>(tm, d, w_tc, p, err, st);
@@ -1839,20 +1953,52 @@ static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* w_
 }
 
 extern "C" int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* d, const void* maps, const void* w_tc, int bn, float acc_scale, int* err, void* stream) {
-    return tc3_entry(d, maps, w_tc, bn, acc_scale, 0, err, stream);
+    return tc3_entry(d, maps, nullptr, w_tc, bn, acc_scale, 0, err, stream);
+}
+
+// The same with tensor maps for the OUTPUTS: omaps = three 128-byte maps {y16 hi plane, y16 lo plane, y fp32} from bflow_tma_out_map (zeroed
+// entries for outputs the descriptor does not have).  Single-tile launches with a plain epilogue then store through cp.async.bulk.tensor.
+extern "C" int bflow_conv2d_nhwc_tc3o(const bflow_conv_desc* d, const void* maps, const void* omaps, const void* w_tc, int bn, float acc_scale, int* err,
+                                      void* stream) {
+    return tc3_entry(d, maps, omaps, w_tc, bn, acc_scale, 0, err, stream);
+}
+
+// 2-D tensor map over an output tensor [rows][cols] (row stride ld elements; elem_bytes 2 = one split-fp16 plane, 4 = fp32), box = 128 rows x
+// 128 bytes, SWIZZLE_128B: what the store epilogue of bflow_conv2d_nhwc_tc3o writes.
+extern "C" int bflow_tma_out_map(void* map_out, const void* base, long long rows, int cols, int ld_elems, int elem_bytes) {
+    BFLOW_REQUIRE(map_out != nullptr && base != nullptr, "tma_out_map: null argument");
+    BFLOW_REQUIRE(rows > 0 && cols > 0 && ld_elems >= cols && (elem_bytes == 2 || elem_bytes == 4), "tma_out_map: bad shape");
+    BFLOW_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && ((long long)ld_elems * elem_bytes) % 16 == 0, "tma_out_map: 16-byte aligned base and row stride");
+    static bflow::EncodeTiledFn enc = nullptr;
+    if (enc == nullptr) {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            enc = reinterpret_cast<bflow::EncodeTiledFn>(fp);
+    }
+    BFLOW_REQUIRE(enc != nullptr, "tma_out_map: cuTensorMapEncodeTiled not available from the driver");
+    alignas(64) CUtensorMap tm;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld_elems * elem_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), 128};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        bflow::set_error("tma_out_map: cuTensorMapEncodeTiled failed");
+        return BFLOW_ERR_CUDA;
+    }
+    memcpy(map_out, &tm, sizeof(tm));
+    return BFLOW_OK;
 }
 
 // Slab mode of the same kernel for stride-1 3x3 / 5x1 (orientation 1) and 1x5 / 3x3 (orientation 2) convolutions: `maps` are TILED tensor
 // maps from bflow_tma_tile_map (box 8 x (16 + taps - 1), transposed for orientation 2) instead of im2col maps; everything else as above.
 extern "C" int bflow_conv2d_nhwc_tc3s(const bflow_conv_desc* d, const void* maps, const void* w_tc, int bn, float acc_scale, int orientation, int* err,
                                       void* stream) {
-    return tc3_entry(d, maps, w_tc, bn, acc_scale, orientation, err, stream);
+    return tc3_entry(d, maps, nullptr, w_tc, bn, acc_scale, orientation, err, stream);
 }
 
-namespace bflow {
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-}  // namespace bflow
 
 // Tiled (not im2col) tensor map over a split-fp16 NHWC plane: dims {C, W, H, N}, box {64 channels, box_w, box_h, 1}, SWIZZLE_128B,
 // out-of-bounds elements read as zero.  Used by bflow_conv2d_slab64 with box 8 x 18.

@@ -128,6 +128,21 @@ class S16Recorder:
             self.n_tc += 1
             return Ho, Wo
         maps = self._maps(srcs, N, H, W, wt)
+        if (epi == 'std' and res is None and res16 is None and stats is None and act1 in ('none', 'relu') and act2 in ('none', 'relu') and
+                (M + 127) // 128 * ((wt.cout + bn - 1) // bn) <= 148 and wt.cout % 8 == 0 and os.environ.get('BFLOW_TC3_OSTORE', '1') != '0'):
+            # single-tile launch with a plain epilogue: outputs leave through tensor-map stores
+            omaps = (C.c_uint8 * 384)()
+            if y16 is not None and y16[0].ld % 8 == 0:
+                for j, base in enumerate((y16[0].hi(y16[1]), y16[0].lo(y16[1]))):
+                    check(lib.bflow_tma_out_map(C.addressof(omaps) + 128 * j, base, M, wt.cout, y16[0].ld, 2), 'tma_out_map')
+            if y is not None and ldy % 4 == 0:
+                check(lib.bflow_tma_out_map(C.addressof(omaps) + 256, y, M, wt.cout, ldy, 4), 'tma_out_map')
+            if (y16 is None or y16[0].ld % 8 == 0) and (y is None or ldy % 4 == 0):
+                self.keep.append(omaps)
+                self._add(lib.bflow_conv2d_nhwc_tc3o, C.byref(d), C.addressof(maps), C.addressof(omaps), img.data_ptr(), bn, acc_scale, self.eng.err.data_ptr(),
+                          label=f'conv_tc3_{bn} {c0 + c1}->{wt.cout} {wt.kh}x{wt.kw}/{wt.stride} M={M}', flops=2.0 * M * wt.cout * wt.kh * wt.kw * (c0 + c1))
+                self.n_tc += 1
+                return Ho, Wo
         self._add(lib.bflow_conv2d_nhwc_tc3, C.byref(d), C.addressof(maps), img.data_ptr(), bn, acc_scale, self.eng.err.data_ptr(),
                   label=f'conv_tc3_{bn} {c0 + c1}->{wt.cout} {wt.kh}x{wt.kw}/{wt.stride} M={M}', flops=2.0 * M * wt.cout * wt.kh * wt.kw * (c0 + c1))
         self.n_tc += 1

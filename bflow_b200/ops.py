@@ -177,7 +177,19 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         wtc, acc_scale = pack_conv_weight_tc(weight, bn, block_per_tap=True)
         err = torch.zeros(1, device=x.device, dtype=torch.int32)
         d.x0 = None
-        check(_lib.lib().bflow_conv2d_nhwc_tc3(C.byref(d), C.addressof(maps), wtc.data_ptr(), bn, acc_scale, err.data_ptr(), _stream()), 'conv2d_tc3')
+        if getattr(conv2d, 'tma_out', False):
+            # outputs through tensor-map stores (bflow_conv2d_nhwc_tc3o): fp32 y and a split-fp16 copy that is checked against it
+            L = _lib.lib()
+            y16 = torch.zeros(2, N * Ho * Wo, (O + 7) // 8 * 8, device=x.device, dtype=torch.float16)
+            d.y16_hi, d.y16_lo, d.ldy16 = y16[0].data_ptr(), y16[1].data_ptr(), y16.shape[-1]
+            omaps = (C.c_uint8 * 384)()
+            for j in range(2):
+                check(L.bflow_tma_out_map(C.addressof(omaps) + 128 * j, y16[j].data_ptr(), N * Ho * Wo, O, y16.shape[-1], 2), 'tma_out_map')
+            check(L.bflow_tma_out_map(C.addressof(omaps) + 256, y.data_ptr(), N * Ho * Wo, O, O, 4), 'tma_out_map')
+            check(L.bflow_conv2d_nhwc_tc3o(C.byref(d), C.addressof(maps), C.addressof(omaps), wtc.data_ptr(), bn, acc_scale, err.data_ptr(), _stream()), 'conv2d_tc3o')
+            conv2d.last_y16 = (y16[0].float() + y16[1].float())[:, :O].reshape(N, Ho, Wo, O).permute(0, 3, 1, 2)
+        else:
+            check(_lib.lib().bflow_conv2d_nhwc_tc3(C.byref(d), C.addressof(maps), wtc.data_ptr(), bn, acc_scale, err.data_ptr(), _stream()), 'conv2d_tc3')
         if int(err.item()) != 0:
             raise RuntimeError('bflow_conv2d_nhwc_tc3: pipeline wait timed out inside the kernel')
     elif backend == 'stem7':

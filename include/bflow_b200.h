@@ -126,6 +126,11 @@ int bflow_tma_tile_map(void* map_out_128B, const void* base_fp16, int N, int H, 
 /* bflow_conv2d_nhwc_tc3 in slab mode (stride-1 3x3, 5x1: orientation 1; 1x5, 3x3: orientation 2): output tiles are 8 x 16 pixel patches and one halo
  * slab per slow filter index serves all taps along the other axis; `maps` = tiled maps (bflow_tma_tile_map, box 8 x (16 + taps - 1) pixels,
  * transposed = orientation 2) in the same {source0 hi, source0 lo, source1 hi, source1 lo} order.  Same weights, epilogues and outputs. */
+/* bflow_conv2d_nhwc_tc3 with tensor maps for the OUTPUTS: omaps = three 128-byte maps {y16 hi plane, y16 lo plane, y fp32} from
+ * bflow_tma_out_map (zero bytes for outputs the descriptor does not have).  Single-tile launches with a plain epilogue (none / relu, no
+ * residual, no statistics) then leave through cp.async.bulk.tensor stores of SWIZZLE_128B boxes; every other case behaves like _tc3. */
+int bflow_tma_out_map(void* map_out_128B, const void* base, long long rows, int cols, int ld_elems, int elem_bytes);
+int bflow_conv2d_nhwc_tc3o(const bflow_conv_desc* d, const void* maps, const void* omaps, const void* w_tc, int bn, float acc_scale, int* err, void* stream);
 int bflow_conv2d_nhwc_tc3s(const bflow_conv_desc* d, const void* maps, const void* w_tc, int bn, float acc_scale, int orientation, int* err, void* stream);
 int bflow_conv2d_slab64(const bflow_conv_desc* d, const void* maps, const void* w_tc, float acc_scale, int* err, void* stream);
 /* Fused encoder stem (extractor.py:112): 7x7 / stride 2 / pad 3 over n_windows (<= 8) channel windows [c_offs[i], c_offs[i] + cin) of an fp32

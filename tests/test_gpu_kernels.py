@@ -100,6 +100,31 @@ def test_conv2d_tc3_slab_mode_matches_torch(N, Cin, H, W, Cout, k, p, act, bn):
     assert (out - ref).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize('N,Cin,H,W,Cout,k,p,act,bn', [
+    (1, 576, 60, 80, 256, (1, 1), (0, 0), 'relu', 128),        # convc1 shape
+    (1, 256, 60, 80, 192, (3, 3), (1, 1), 'relu', 64),         # convc2 shape
+    (1, 256, 60, 80, 120, (3, 3), (1, 1), 'relu', 64),         # ragged Cout (multiple of 8): the tensor map clips the last box
+    (1, 256, 60, 80, 124, (3, 3), (1, 1), 'relu', 64),         # Cout % 8 != 0: falls back to the per-row bulk-copy epilogue
+    (1, 128, 37, 50, 256, (3, 3), (1, 1), 'none', 128),        # ragged M: rows beyond M clipped
+    (1, 64, 9, 13, 40, (1, 1), (0, 0), 'relu', 64),            # one partial tile
+])
+def test_conv2d_tc3_tensor_map_store_epilogue(N, Cin, H, W, Cout, k, p, act, bn):
+    """Single-tile launches whose outputs (fp32 and both split-fp16 planes) leave through cp.async.bulk.tensor stores of swizzled boxes."""
+    x = torch.randn(N, Cin, H, W, generator=g(1))
+    w = torch.randn(Cout, Cin, *k, generator=g(2)) / (Cin * k[0] * k[1]) ** 0.5
+    b = torch.randn(Cout, generator=g(3))
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride=1, padding=p).float()
+    ref = torch.relu(ref) if act == 'relu' else ref
+    ops.conv2d.tma_out = True
+    try:
+        out = ops.conv2d(x.to(DEV), w.to(DEV), b.to(DEV), stride=1, padding=p, act=act, backend='tc3', bn=bn).cpu()
+        out16 = ops.conv2d.last_y16.cpu()
+    finally:
+        ops.conv2d.tma_out = False
+    assert (out - ref).abs().max() < 1e-4
+    assert (out16 - ref).abs().max() < 1e-4
+
+
 @pytest.mark.parametrize('N,H,W,act', [(1, 16, 8, 'none'), (2, 40, 24, 'relu'), (3, 37, 16, 'none'), (5, 120, 160, 'relu')])
 def test_conv2d_slab64_matches_torch(N, H, W, act):
     """Slab kernel (weights resident, halo slabs): 3x3/1, 64 -> 64; ragged tile rows (H % 16 != 0), several images, multi-tile CTAs."""
