@@ -618,6 +618,18 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
                 }
+                // Cout % 8 == 4: the fp16 maps cover Cout - 4 channels (a box clipped inside a 16-byte chunk would write the whole chunk); the last
+                // four channels of each row go out as one 8-byte store per plane
+                const int c8 = d.Cout & ~7;
+                if (o16 && c8 < d.Cout && c8 >= n0 && c8 < n0 + BN && etid < T3_BM) {
+                    const int mm = m_tile * T3_BM + etid;
+                    if (mm < p.M) {
+                        const int lc = c8 - n0;
+                        const int off = (lc >> 6) * 16384 + etid * 128 + ((((lc & 63) >> 3) ^ (etid & 7)) << 4);
+                        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(d.y16_hi) + (size_t)mm * d.ldy16 + c8) = *reinterpret_cast<const uint2*>(s_hi + off);
+                        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(d.y16_lo) + (size_t)mm * d.ldy16 + c8) = *reinterpret_cast<const uint2*>(s_lo + off);
+                    }
+                }
                 __syncwarp();
                 if (lane == 0) t3_mbar_arrive(tempty_bar(acc));
             } else if (p.staged == 3) {
@@ -1938,8 +1950,9 @@ static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* om
         }
         const bool single1 = d.stats == nullptr && p.n_mtiles * p.n_ntiles <= bflow::num_sms();
         // Cout % 8: measured on B200, a tensor-map store whose box is clipped inside a 16-byte chunk still writes the whole chunk (it
-        // overwrote the 4 Bezier-parameter channels behind the motion encoder's 124) -- ragged widths stay on the per-row bulk-copy path
-        if (ostore_on && single1 && !slab && bn <= 128 && d.Cout % 8 == 0 && d.epi == BFLOW_EPI_STD && d.res == nullptr && d.res16_hi == nullptr && d.act1 <= BFLOW_ACT_RELU &&
+        // overwrote the 4 Bezier-parameter channels behind the motion encoder's 124) -- so the caller's fp16 maps must cover only Cout & ~7 channels;
+        // the kernel writes a 4-channel tail itself
+        if (ostore_on && single1 && !slab && bn <= 128 && d.Cout % 4 == 0 && d.epi == BFLOW_EPI_STD && d.res == nullptr && d.res16_hi == nullptr && d.act1 <= BFLOW_ACT_RELU &&
             d.act2 <= BFLOW_ACT_RELU)
             p.staged = 4;
     }

@@ -129,12 +129,12 @@ class S16Recorder:
             return Ho, Wo
         maps = self._maps(srcs, N, H, W, wt)
         if (epi == 'std' and res is None and res16 is None and stats is None and act1 in ('none', 'relu') and act2 in ('none', 'relu') and
-                (M + 127) // 128 * ((wt.cout + bn - 1) // bn) <= 148 and wt.cout % 8 == 0 and os.environ.get('BFLOW_TC3_OSTORE', '1') != '0'):
+                (M + 127) // 128 * ((wt.cout + bn - 1) // bn) <= 148 and wt.cout % 4 == 0 and os.environ.get('BFLOW_TC3_OSTORE', '1') != '0'):
             # single-tile launch with a plain epilogue: outputs leave through tensor-map stores
             omaps = (C.c_uint8 * 384)()
             if y16 is not None and y16[0].ld % 8 == 0:
                 for j, base in enumerate((y16[0].hi(y16[1]), y16[0].lo(y16[1]))):
-                    check(lib.bflow_tma_out_map(C.addressof(omaps) + 128 * j, base, M, wt.cout, y16[0].ld, 2), 'tma_out_map')
+                    check(lib.bflow_tma_out_map(C.addressof(omaps) + 128 * j, base, M, wt.cout & ~7, y16[0].ld, 2), 'tma_out_map')      # a 4-channel tail is the kernel's
             if y is not None and ldy % 4 == 0:
                 check(lib.bflow_tma_out_map(C.addressof(omaps) + 256, y, M, wt.cout, ldy, 4), 'tma_out_map')
             if (y16 is None or y16[0].ld % 8 == 0) and (y is None or ldy % 4 == 0):

@@ -184,10 +184,11 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
             d.y16_hi, d.y16_lo, d.ldy16 = y16[0].data_ptr(), y16[1].data_ptr(), y16.shape[-1]
             omaps = (C.c_uint8 * 384)()
             for j in range(2):
-                check(L.bflow_tma_out_map(C.addressof(omaps) + 128 * j, y16[j].data_ptr(), N * Ho * Wo, O, y16.shape[-1], 2), 'tma_out_map')
+                check(L.bflow_tma_out_map(C.addressof(omaps) + 128 * j, y16[j].data_ptr(), N * Ho * Wo, O & ~7, y16.shape[-1], 2), 'tma_out_map')
             check(L.bflow_tma_out_map(C.addressof(omaps) + 256, y.data_ptr(), N * Ho * Wo, O, O, 4), 'tma_out_map')
             check(L.bflow_conv2d_nhwc_tc3o(C.byref(d), C.addressof(maps), C.addressof(omaps), wtc.data_ptr(), bn, acc_scale, err.data_ptr(), _stream()), 'conv2d_tc3o')
             conv2d.last_y16 = (y16[0].float() + y16[1].float())[:, :O].reshape(N, Ho, Wo, O).permute(0, 3, 1, 2)
+            conv2d.last_y16_pad = y16[:, :, O:].clone()          # channels behind Cout must stay untouched
         else:
             check(_lib.lib().bflow_conv2d_nhwc_tc3(C.byref(d), C.addressof(maps), wtc.data_ptr(), bn, acc_scale, err.data_ptr(), _stream()), 'conv2d_tc3')
         if int(err.item()) != 0:

@@ -104,7 +104,7 @@ def test_conv2d_tc3_slab_mode_matches_torch(N, Cin, H, W, Cout, k, p, act, bn):
     (1, 576, 60, 80, 256, (1, 1), (0, 0), 'relu', 128),        # convc1 shape
     (1, 256, 60, 80, 192, (3, 3), (1, 1), 'relu', 64),         # convc2 shape
     (1, 256, 60, 80, 120, (3, 3), (1, 1), 'relu', 64),         # ragged Cout (multiple of 8): the tensor map clips the last box
-    (1, 256, 60, 80, 124, (3, 3), (1, 1), 'relu', 64),         # Cout % 8 != 0: falls back to the per-row bulk-copy epilogue
+    (1, 256, 60, 80, 124, (3, 3), (1, 1), 'relu', 64),         # Cout % 8 == 4: maps cover 120 channels, the kernel stores the 4-channel tail
     (1, 128, 37, 50, 256, (3, 3), (1, 1), 'none', 128),        # ragged M: rows beyond M clipped
     (1, 64, 9, 13, 40, (1, 1), (0, 0), 'relu', 64),            # one partial tile
 ])
@@ -123,6 +123,7 @@ def test_conv2d_tc3_tensor_map_store_epilogue(N, Cin, H, W, Cout, k, p, act, bn)
         ops.conv2d.tma_out = False
     assert (out - ref).abs().max() < 1e-4
     assert (out16 - ref).abs().max() < 1e-4
+    assert float(ops.conv2d.last_y16_pad.abs().sum()) == 0.0, 'the store epilogue wrote behind the last output channel'
 
 
 @pytest.mark.parametrize('N,H,W,act', [(1, 16, 8, 'none'), (2, 40, 24, 'relu'), (3, 37, 16, 'none'), (5, 120, 160, 'relu')])

@@ -50,7 +50,7 @@ def main():
         torch.cuda.synchronize()
         cta = torch.zeros(148, 16, device=dev, dtype=torch.int64)
         if a.cta_label:
-            tc3l = [lab for (fn, _), (lab, _) in zip(plan.launches, plan.labels) if fn.__name__ in ('bflow_conv2d_nhwc_tc3', 'bflow_conv2d_nhwc_tc3s')]
+            tc3l = [lab for (fn, _), (lab, _) in zip(plan.launches, plan.labels) if fn.__name__ in ('bflow_conv2d_nhwc_tc3', 'bflow_conv2d_nhwc_tc3o', 'bflow_conv2d_nhwc_tc3s')]
             hits = [i for i, lab in enumerate(tc3l) if a.cta_label in lab]
             a.cta = hits[min(a.cta_occ, len(hits) - 1)]
         if a.cta >= 0:
@@ -76,7 +76,7 @@ def main():
     print(f'{a.preset} B={a.batch} {a.h}x{a.w} iters={a.iters}: graph replay {e0.elapsed_time(e1):.3f} ms; {n} instrumented launches of {plan.n_launches}; '
           f'span of instrumented launches {(int(t[:, 1].max()) - t0) / 1e6:.3f} ms')
     # label = instrumented launches in plan order (the plan's labels for those kernels)
-    inst = ('conv2d_nhwc_tc3', 'conv2d_nhwc_tc3s', 'conv2d_slab64', 'conv2d_stem7', 'corr_lookup', 'conv2d_small_n', 'conv2d_thin7', 'conv2d_nhwc', 'instnorm_relu16', 'im2col_split16')
+    inst = ('conv2d_nhwc_tc3', 'conv2d_nhwc_tc3o', 'conv2d_nhwc_tc3s', 'conv2d_slab64', 'conv2d_stem7', 'corr_lookup', 'conv2d_small_n', 'conv2d_thin7', 'conv2d_nhwc', 'instnorm_relu16', 'im2col_split16')
     labels = [lab for (fn, _), (lab, _) in zip(plan.launches, plan.labels) if fn.__name__.replace('bflow_', '') in inst]
     streams = [item[2] for item in plan.schedule if item[0] == 'launch' and plan.launches[item[1]][0].__name__.replace('bflow_', '') in inst]
     if len(labels) != n:
@@ -89,7 +89,7 @@ def main():
         for s, e, lab, st in rows:
             print(f'{s / 1e3:9.2f} {e / 1e3:9.2f}  {(e - s) / 1e3:7.2f} us  s{st} {lab}')
     if a.cta >= 0:
-        tc3 = [lab for (fn, _), (lab, _) in zip(plan.launches, plan.labels) if fn.__name__ in ('bflow_conv2d_nhwc_tc3', 'bflow_conv2d_nhwc_tc3s')]
+        tc3 = [lab for (fn, _), (lab, _) in zip(plan.launches, plan.labels) if fn.__name__ in ('bflow_conv2d_nhwc_tc3', 'bflow_conv2d_nhwc_tc3o', 'bflow_conv2d_nhwc_tc3s')]
         c = cta.cpu()
         c = c[c[:, 0] > 0]
         c0 = int(c[:, 0].min())
