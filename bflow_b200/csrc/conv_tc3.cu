@@ -157,6 +157,12 @@ __device__ __forceinline__ void t3_tma_store2d(const CUtensorMap* map, uint32_t 
                  : "memory");
 }
 
+__device__ __forceinline__ void t3_tma_load2d(uint32_t dst, const CUtensorMap* map, int c, int r, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(r)
+                 : "memory");
+}
+
 struct T3Params {
     int M, n_mtiles, n_ntiles, ntaps, ncb0, ncb1, nkb;
     float acc_scale;
@@ -174,7 +180,8 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant__ CUtensorMap map0l, const __grid_constant__ CUtensorMap map1h,
                 const __grid_constant__ CUtensorMap map1l, const __grid_constant__ CUtensorMap omap_hi, const __grid_constant__ CUtensorMap omap_lo,
-                const __grid_constant__ CUtensorMap omap32, const bflow_conv_desc d, const uint8_t* __restrict__ wtc, const T3Params p, int* err) {
+                const __grid_constant__ CUtensorMap omap32, const __grid_constant__ CUtensorMap rmap, const __grid_constant__ CUtensorMap amap,
+                const bflow_conv_desc d, const uint8_t* __restrict__ wtc, const T3Params p, int* err) {
     constexpr int B_BYTES = BN * 128;
     constexpr int STAGE_BYTES = 2 * T3_A_BYTES + 2 * B_BYTES;
     constexpr uint32_t TX_BYTES = 2 * T3_A_BYTES + 2 * B_BYTES;
@@ -533,7 +540,126 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
             if (warp == 2 && lane == 0) T3_CTA(5);
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_COLS + (uint32_t)(chalf * HALF);
             const int nb0 = n0 + chalf * HALF;
-            if (p.staged == 4) {
+            if (p.staged == 5) {
+                // GRU gate epilogues of a single-tile CTA on tensor maps (update.py:36-45).  One elected thread fetches the tile of every
+                // per-element operand (hoisted term `res`; h for the r gate / z for the candidate; the state h itself for the candidate) as
+                // SWIZZLE_128B boxes of 32 floats into the idle pipeline stages while the accumulator is being unloaded; each thread then
+                // finishes ITS row out of shared memory (chunk j of row r sits at j ^ (r & 7): conflict-free for the 16-byte accesses of a
+                // quarter-warp), writes the fp32 result in place of an operand and the split-fp16 planes next to it, and one thread stores
+                // the boxes.  No per-lane global access, no staging pass.  (Per-row bulk copies: 7.4 us per 128x128 tile; batched loads: 10.8.)
+                uint8_t* sb = smem_raw + (smem_base - t3_smem_u32(smem_raw));
+                constexpr int NB16 = (BN + 63) / 64, NB32 = (BN + 31) / 32;
+                const int Cg = d.Cout >> 1;
+                const bool is_zr = d.epi == BFLOW_EPI_GRU_ZR;
+                const bool r_tile = is_zr && n0 >= Cg;
+                const bool hasR = d.res != nullptr, hasA = r_tile || !is_zr, hasY = !is_zr;
+                const bool out16 = is_zr ? r_tile : d.y16_hi != nullptr;
+                uint8_t* s_R = sb;                                   // res, then (GRU_ZR) the fp32 gates in place
+                uint8_t* s_A = sb + NB32 * 16384;                    // h (r gate) / z (candidate)
+                uint8_t* s_Y = sb + 2 * NB32 * 16384;                // candidate: h in, h out
+                uint8_t* s_hi = sb + 3 * NB32 * 16384;
+                uint8_t* s_lo = s_hi + NB16 * 16384;
+                uint8_t* s_O = is_zr ? s_R : s_Y;
+                const int mt0 = m_tile * T3_BM;
+                const int acol0 = is_zr ? n0 - Cg : n0;              // column of the aux0 / fp16 tile
+                if (warp == 2 && t3_elect_one()) {
+                    const uint32_t nbox = (uint32_t)NB32 * ((hasR ? 1u : 0u) + (hasA ? 1u : 0u) + (hasY ? 1u : 0u));
+                    t3_mbar_arrive_expect_tx(ebar, nbox * 16384u);
+#pragma unroll
+                    for (int b = 0; b < NB32; ++b) {
+                        if (hasR) t3_tma_load2d(t3_smem_u32(s_R + b * 16384), &rmap, n0 + b * 32, mt0, ebar);
+                        if (hasA) t3_tma_load2d(t3_smem_u32(s_A + b * 16384), &amap, acol0 + b * 32, mt0, ebar);
+                        if (hasY) t3_tma_load2d(t3_smem_u32(s_Y + b * 16384), &omap32, n0 + b * 32, mt0, ebar);
+                    }
+                }
+                __syncwarp();
+                const int row = quad * 32 + lane;
+                const int colbase = chalf * HALF;
+                bool waited = false;
+#pragma unroll 1
+                for (int c0 = 0; c0 < HALF; c0 += 32) {
+                    float v[32];
+                    t3_tmem_ld16_nowait(taddr + (uint32_t)c0, v);
+                    t3_tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), v + 16);
+                    if (STACK) {
+                        float u[32];
+                        t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0), u);
+                        t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0 + 16), u + 16);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] += u[c];
+                    } else {
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    }
+                    if (!waited) {
+                        t3_mbar_wait(ebar, 0u, err);
+                        waited = true;
+                    }
+                    const int col = colbase + c0;
+                    const int boff = (col >> 5) * 16384 + row * 128;          // this thread's 128-byte row inside the fp32 box of these 32 columns
+                    float h[32];
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) {
+                        const int ch = ((c >> 2) ^ (row & 7)) << 4;
+                        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + colbase + c0 + c);
+                        float o[4] = {post * fmaf(v[c], p.acc_scale, b4.x), post * fmaf(v[c + 1], p.acc_scale, b4.y), post * fmaf(v[c + 2], p.acc_scale, b4.z),
+                                      post * fmaf(v[c + 3], p.acc_scale, b4.w)};
+                        if (hasR) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(s_R + boff + ch);
+                            o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+                        }
+                        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (hasA) a4 = *reinterpret_cast<const float4*>(s_A + boff + ch);
+                        if (is_zr) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) o[j] = fast_sigmoid(o[j]);
+                            h[c] = o[0] * a4.x; h[c + 1] = o[1] * a4.y; h[c + 2] = o[2] * a4.z; h[c + 3] = o[3] * a4.w;
+                        } else {
+                            const float4 y4 = *reinterpret_cast<const float4*>(s_Y + boff + ch);
+                            o[0] = (1.f - a4.x) * y4.x + a4.x * fast_tanh(o[0]);
+                            o[1] = (1.f - a4.y) * y4.y + a4.y * fast_tanh(o[1]);
+                            o[2] = (1.f - a4.z) * y4.z + a4.z * fast_tanh(o[2]);
+                            o[3] = (1.f - a4.w) * y4.w + a4.w * fast_tanh(o[3]);
+                            h[c] = o[0]; h[c + 1] = o[1]; h[c + 2] = o[2]; h[c + 3] = o[3];
+                        }
+                        *reinterpret_cast<float4*>(s_O + boff + ch) = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                    if (out16) {
+                        uint8_t* bh = s_hi + (col >> 6) * 16384 + row * 128;
+                        uint8_t* bl = s_lo + (col >> 6) * 16384 + row * 128;
+#pragma unroll
+                        for (int c = 0; c < 32; c += 8) {
+                            uint4 h4, l4;
+                            split2(h[c], h[c + 1], h4.x, l4.x);
+                            split2(h[c + 2], h[c + 3], h4.y, l4.y);
+                            split2(h[c + 4], h[c + 5], h4.z, l4.z);
+                            split2(h[c + 6], h[c + 7], h4.w, l4.w);
+                            const int chunk = (((col & 63) + c) >> 3) ^ (row & 7);
+                            *reinterpret_cast<uint4*>(bh + (chunk << 4)) = h4;
+                            *reinterpret_cast<uint4*>(bl + (chunk << 4)) = l4;
+                        }
+                    }
+                }
+                if (warp == 2 && lane == 0) T3_CTA(8);
+                t3_fence_before();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (warp == 2 && t3_elect_one()) {
+#pragma unroll
+                    for (int b = 0; b < NB32; ++b) t3_tma_store2d(&omap32, t3_smem_u32(s_O + b * 16384), n0 + b * 32, mt0);
+                    if (out16) {
+#pragma unroll
+                        for (int b = 0; b < NB16; ++b) {
+                            t3_tma_store2d(&omap_hi, t3_smem_u32(s_hi + b * 16384), acol0 + b * 64, mt0);
+                            t3_tma_store2d(&omap_lo, t3_smem_u32(s_lo + b * 16384), acol0 + b * 64, mt0);
+                        }
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                }
+                __syncwarp();
+                if (lane == 0) t3_mbar_arrive(tempty_bar(acc));
+            } else if (p.staged == 4) {
                 // Single-tile CTA, plain epilogue (bias, scale, none / relu), outputs through 2-D tensor-map stores: each thread converts its row
                 // straight from the accumulator into SWIZZLE_128B boxes in the idle pipeline stages ([128 rows][128 bytes] per 64 halves / 32
                 // floats of width; chunk j of row r sits at j ^ (r & 7), so the 16-byte stores of a quarter-warp hit 8 different bank groups), and
@@ -1677,7 +1803,7 @@ static int launch_tc3(const CUtensorMap* maps, const bflow_conv_desc& d, const v
     const int n_tiles = p.n_mtiles * p.n_ntiles;
     const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
     cudaError_t le = launch_pdl(conv_tc3_kernel<BN, STAGES>, dim3(grid), dim3(T3_THREADS), smem, stream, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
-                                maps[6], d, reinterpret_cast<const uint8_t*>(wtc), p, err);
+                                maps[6], maps[7], maps[8], d, reinterpret_cast<const uint8_t*>(wtc), p, err);
     if (le != cudaSuccess) {
         set_error(cudaGetErrorString(le));
         return BFLOW_ERR_CUDA;
@@ -1937,11 +2063,11 @@ static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* om
     p.trace = bflow::g_tc3_trace;
     p.cta = (bflow::g_tc3_cta != nullptr && bflow::g_tc3_cta_count++ == bflow::g_tc3_cta_nth) ? bflow::g_tc3_cta : nullptr;
     p.tl = bflow::timeline_next_slot(bn == 64 ? "tc3_64" : bn == 128 ? "tc3_128" : "tc3_256");
-    alignas(64) CUtensorMap tm[7];
+    alignas(64) CUtensorMap tm[9];
     memset(tm, 0, sizeof(tm));
     memcpy(tm, maps, 4 * sizeof(CUtensorMap));
     if (omaps != nullptr) {
-        memcpy(tm + 4, omaps, 3 * sizeof(CUtensorMap));
+        memcpy(tm + 4, omaps, 5 * sizeof(CUtensorMap));
         // tensor-map store epilogue: single-tile CTAs, plain epilogue (none / relu), no residual / statistics
         static int ostore_on = -1;
         if (ostore_on < 0) {
@@ -1955,6 +2081,18 @@ static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* om
         if (ostore_on && single1 && !slab && bn <= 128 && d.Cout % 4 == 0 && d.epi == BFLOW_EPI_STD && d.res == nullptr && d.res16_hi == nullptr && d.act1 <= BFLOW_ACT_RELU &&
             d.act2 <= BFLOW_ACT_RELU)
             p.staged = 4;
+        // GRU gate epilogues on tensor maps: omaps = {fp16 hi, fp16 lo (aux1_16 for the z|r launch, y16 for the candidate), y fp32, res, aux0};
+        // every tile must be full width (Cout a multiple of bn, the z|r boundary on a tile boundary)
+        static int gru_tma = -1;
+        if (gru_tma < 0) {
+            const char* e = getenv("BFLOW_TC3_GRU_TMA");
+            gru_tma = (e != nullptr && e[0] == '0') ? 0 : 1;
+        }
+        const int regions = d.epi == BFLOW_EPI_GRU_Q ? 3 : 2;
+        if (gru_tma && ostore_on && single1 && !slab && bn <= 128 && d.epi != BFLOW_EPI_STD && d.Cout % bn == 0 && d.y != nullptr && d.res != nullptr &&
+            (d.epi == BFLOW_EPI_GRU_Q ? d.y16_hi != nullptr : ((d.Cout / 2) % bn == 0 && d.aux1 == nullptr && d.aux1_16_hi != nullptr)) &&
+            (regions * ((bn + 31) / 32) + 2 * ((bn + 63) / 64)) * 16384 <= bflow::t3_area_bytes(bn, 0))
+            p.staged = 5;
     }
     cudaStream_t st = (cudaStream_t)stream;
     switch (bn) {
@@ -1971,7 +2109,7 @@ extern "C" int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* d, const void* maps,
 
 // The same with tensor maps for the OUTPUTS: omaps = three 128-byte maps {y16 hi plane, y16 lo plane, y fp32} from bflow_tma_out_map (zeroed
 // entries for outputs the descriptor does not have).  Single-tile launches with a plain epilogue then store through cp.async.bulk.tensor.
-extern "C" int bflow_conv2d_nhwc_tc3o(const bflow_conv_desc* d, const void* maps, const void* omaps, const void* w_tc, int bn, float acc_scale, int* err,
+extern "C" int bflow_conv2d_nhwc_tc3o(const bflow_conv_desc* d, const void* maps, const void* omaps /* 5 x 128 bytes */, const void* w_tc, int bn, float acc_scale, int* err,
                                       void* stream) {
     return tc3_entry(d, maps, omaps, w_tc, bn, acc_scale, 0, err, stream);
 }
