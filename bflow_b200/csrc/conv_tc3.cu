@@ -226,6 +226,17 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map1h)) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map1l)) : "memory");
         }
+        if (p.staged >= 4) {                     // tensor-map epilogues: their descriptors too (a cold descriptor costs ~1 us at first use)
+            if (d.y16_hi != nullptr || d.aux1_16_hi != nullptr) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&omap_hi)) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&omap_lo)) : "memory");
+            }
+            if (d.y != nullptr) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&omap32)) : "memory");
+            if (p.staged == 5) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&rmap)) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&amap)) : "memory");
+            }
+        }
     }
     tl_begin(p.tl);
     if (tid == 0) {
@@ -557,7 +568,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 uint8_t* s_R = sb;                                   // res, then (GRU_ZR) the fp32 gates in place
                 uint8_t* s_A = sb + NB32 * 16384;                    // h (r gate) / z (candidate)
                 uint8_t* s_Y = sb + 2 * NB32 * 16384;                // candidate: h in, h out
-                uint8_t* s_hi = sb + 3 * NB32 * 16384;
+                uint8_t* s_hi = sb + (is_zr ? 2 : 3) * NB32 * 16384;      // the z|r launch has no Y region
                 uint8_t* s_lo = s_hi + NB16 * 16384;
                 uint8_t* s_O = is_zr ? s_R : s_Y;
                 const int mt0 = m_tile * T3_BM;
@@ -2086,7 +2097,8 @@ static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* om
         static int gru_tma = -1;
         if (gru_tma < 0) {
             const char* e = getenv("BFLOW_TC3_GRU_TMA");
-            gru_tma = (e != nullptr && e[0] == '0') ? 0 : 1;
+            gru_tma = (e != nullptr && e[0] == '1') ? 1 : 0;      // opt-in: measured equal to the per-row bulk / batched-load epilogues -- the 8-12 operand
+                                                                    // boxes arrive as 128-byte rows (~4 cycles each through the TMA unit), 6 us before the first use
         }
         const int regions = d.epi == BFLOW_EPI_GRU_Q ? 3 : 2;
         if (gru_tma && ostore_on && single1 && !slab && bn <= 128 && d.epi != BFLOW_EPI_STD && d.Cout % bn == 0 && d.y != nullptr && d.res != nullptr &&

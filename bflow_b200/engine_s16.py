@@ -131,13 +131,30 @@ class S16Recorder:
         if (epi == 'std' and res is None and res16 is None and stats is None and act1 in ('none', 'relu') and act2 in ('none', 'relu') and
                 (M + 127) // 128 * ((wt.cout + bn - 1) // bn) <= 148 and wt.cout % 4 == 0 and os.environ.get('BFLOW_TC3_OSTORE', '1') != '0'):
             # single-tile launch with a plain epilogue: outputs leave through tensor-map stores
-            omaps = (C.c_uint8 * 384)()
+            omaps = (C.c_uint8 * 640)()
             if y16 is not None and y16[0].ld % 8 == 0:
                 for j, base in enumerate((y16[0].hi(y16[1]), y16[0].lo(y16[1]))):
                     check(lib.bflow_tma_out_map(C.addressof(omaps) + 128 * j, base, M, wt.cout & ~7, y16[0].ld, 2), 'tma_out_map')      # a 4-channel tail is the kernel's
             if y is not None and ldy % 4 == 0:
                 check(lib.bflow_tma_out_map(C.addressof(omaps) + 256, y, M, wt.cout, ldy, 4), 'tma_out_map')
             if (y16 is None or y16[0].ld % 8 == 0) and (y is None or ldy % 4 == 0):
+                self.keep.append(omaps)
+                self._add(lib.bflow_conv2d_nhwc_tc3o, C.byref(d), C.addressof(maps), C.addressof(omaps), img.data_ptr(), bn, acc_scale, self.eng.err.data_ptr(),
+                          label=f'conv_tc3_{bn} {c0 + c1}->{wt.cout} {wt.kh}x{wt.kw}/{wt.stride} M={M}', flops=2.0 * M * wt.cout * wt.kh * wt.kw * (c0 + c1))
+                self.n_tc += 1
+                return Ho, Wo
+        if (epi in ('gru_zr', 'gru_q') and res is not None and y is not None and wt.cout % bn == 0 and (M + 127) // 128 * (wt.cout // bn) <= 148 and
+                ldy % 4 == 0 and ldr % 4 == 0 and ld_aux0 % 4 == 0 and os.environ.get('BFLOW_TC3_GRU_TMA', '0') == '1'):
+            # GRU gate epilogues on tensor maps: {fp16 hi, fp16 lo, y fp32, res, aux0}
+            t16 = aux1_16 if epi == 'gru_zr' else y16
+            hdim = wt.cout // 2 if epi == 'gru_zr' else wt.cout
+            if t16 is not None and t16[0].ld % 8 == 0 and hdim % 8 == 0:
+                omaps = (C.c_uint8 * 640)()
+                for j, base in enumerate((t16[0].hi(t16[1]), t16[0].lo(t16[1]))):
+                    check(lib.bflow_tma_out_map(C.addressof(omaps) + 128 * j, base, M, hdim, t16[0].ld, 2), 'tma_out_map')
+                check(lib.bflow_tma_out_map(C.addressof(omaps) + 256, y, M, wt.cout, ldy, 4), 'tma_out_map')
+                check(lib.bflow_tma_out_map(C.addressof(omaps) + 384, res, M, wt.cout, ldr, 4), 'tma_out_map')
+                check(lib.bflow_tma_out_map(C.addressof(omaps) + 512, aux0, M, hdim, ld_aux0, 4), 'tma_out_map')
                 self.keep.append(omaps)
                 self._add(lib.bflow_conv2d_nhwc_tc3o, C.byref(d), C.addressof(maps), C.addressof(omaps), img.data_ptr(), bn, acc_scale, self.eng.err.data_ptr(),
                           label=f'conv_tc3_{bn} {c0 + c1}->{wt.cout} {wt.kh}x{wt.kw}/{wt.stride} M={M}', flops=2.0 * M * wt.cout * wt.kh * wt.kw * (c0 + c1))

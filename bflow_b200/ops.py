@@ -182,7 +182,7 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
             L = _lib.lib()
             y16 = torch.zeros(2, N * Ho * Wo, (O + 7) // 8 * 8, device=x.device, dtype=torch.float16)
             d.y16_hi, d.y16_lo, d.ldy16 = y16[0].data_ptr(), y16[1].data_ptr(), y16.shape[-1]
-            omaps = (C.c_uint8 * 384)()
+            omaps = (C.c_uint8 * 640)()
             for j in range(2):
                 check(L.bflow_tma_out_map(C.addressof(omaps) + 128 * j, y16[j].data_ptr(), N * Ho * Wo, O & ~7, y16.shape[-1], 2), 'tma_out_map')
             check(L.bflow_tma_out_map(C.addressof(omaps) + 256, y.data_ptr(), N * Ho * Wo, O, O, 4), 'tma_out_map')
