@@ -173,7 +173,7 @@ struct T3Params {
     // along the other axis (see conv_slab64_kernel).  1: slab rows = (y, x) with x fastest (taps along y), 2: rows = (x, y) (taps along x).
     int slab, tiles_x, tiles_y, n_slabs, tps;
     int staged;   // every CTA owns exactly one tile: the epilogue goes through shared memory (coalesced, batched global accesses)
-    int dbg;      // development switches (bflow_tc3_debug): 1 no TMA loads, 2 no MMA, 4 no epilogue stores, 8 one MMA per k-step
+    int dbg;      // development switch (bflow_tc3_debug): 1 = no TMA loads (the producer only arrives: MMA + epilogue path alone)
 };
 
 template <int BN, int STAGES>
@@ -324,12 +324,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                     const int kh = tap / d.KW, kw = tap - kh * d.KW;
                     for (int cb = 0; cb < p.ncb0 + p.ncb1; ++cb, ++kb, ++it) {
                         const int s = (int)ps_;
-                        if (p.dbg & 256) {
-                            while (!t3_mbar_test_wait(empty_bar(s), pph ^ 1u)) {}
-                        } else {
-                            t3_mbar_wait(empty_bar(s), pph ^ 1u, err);
-                        }
-                        if (++ps_ == ((p.dbg & 512) ? 2u : (uint32_t)STAGES)) {
+                        t3_mbar_wait(empty_bar(s), pph ^ 1u, err);
+                        if (++ps_ == (uint32_t)STAGES) {
                             ps_ = 0;
                             pph ^= 1u;
                         }
