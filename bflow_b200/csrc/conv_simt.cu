@@ -320,24 +320,26 @@ __global__ void __launch_bounds__(256) conv_small_n_kernel(const bflow_conv_desc
 }
 // Same operator for the shape the Bezier head really has (3x3, stride 1, pad 1, Cin = 128 or 256, Cout <= 8).  Measured on B200: per-lane
 // loads from the 8 warps of a CTA move only ~9 B/clk per SM, and the warp-per-pixel kernel above reads every input row nine times.  Here a CTA
-// owns a 4x8 patch of output pixels: the 6x10 halo of input rows (1 KB each) and the whole weight matrix arrive by cp.async.bulk (the copy
+// owns a 5x8 patch of output pixels: the 7x10 halo of input rows (1 KB each) and the whole weight matrix arrive by cp.async.bulk (the copy
 // engine is not bound by per-thread load slots), a warp owns 4 consecutive pixels, lane l owns channels l + 32 i -- activations are read with
 // conflict-free LDS.32, the weights of a (tap, channel) with one conflict-free LDS.128 shared by the 4 pixels.
-template <int NV, int CB>   // NV = ceil(Cout/4), CB = Cin / 128
-__global__ void __launch_bounds__(256) conv_head3x3_kernel(const bflow_conv_desc d, const int M, unsigned long long* tl) {
-    extern __shared__ __align__(128) float hs[];          // [9*Cin][NV*4] weights (global order), then the [6][10][Cin] input patch
+// NV = ceil(Cout/4), CB = Cin / 128
+constexpr int HD_ROWS = 5;        // tile rows: 60x80 -> 12 x 10 = 120 CTAs, one wave on 148 SMs (4-row tiles: 150 CTAs, two SMs ran two CTAs in turn)
+template <int NV, int CB>
+__global__ void __launch_bounds__(64 * HD_ROWS) conv_head3x3_kernel(const bflow_conv_desc d, const int M, unsigned long long* tl) {
+    extern __shared__ __align__(128) float hs[];          // [9*Cin][NV*4] weights (global order), then the [HD_ROWS + 2][10][Cin] input patch
     __shared__ __align__(8) unsigned long long bar;
     constexpr int Cin = CB * 128;
-    constexpr int PR = 6, PC = 10;
+    constexpr int PR = HD_ROWS + 2, PC = 10;
     float* s_w = hs;
     float* s_x = hs + 9 * Cin * NV * 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_x = (d.Wo + 7) / 8, tiles_y = (d.Ho + 3) / 4;
+    const int tiles_x = (d.Wo + 7) / 8, tiles_y = (d.Ho + HD_ROWS - 1) / HD_ROWS;
     int bid = blockIdx.x;
     const int tx = bid % tiles_x; bid /= tiles_x;
     const int ty = bid % tiles_y;
     const int n = bid / tiles_y;
-    const int oy0 = ty * 4, ox0 = tx * 8;
+    const int oy0 = ty * HD_ROWS, ox0 = tx * 8;
     const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
     tl_begin(tl);
     if (threadIdx.x == 0) {
@@ -453,15 +455,15 @@ __global__ void __launch_bounds__(256) conv_head3x3_kernel(const bflow_conv_desc
 
 template <int NV, int CB>
 static cudaError_t launch_head3x3(const bflow_conv_desc& d, int M, cudaStream_t st, unsigned long long* tls) {
-    const size_t smem = (size_t)9 * CB * 128 * NV * 16 + (size_t)6 * 10 * CB * 128 * 4;
+    const size_t smem = (size_t)9 * CB * 128 * NV * 16 + (size_t)(HD_ROWS + 2) * 10 * CB * 128 * 4;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(conv_head3x3_kernel<NV, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const int g = d.N * ((d.Ho + 3) / 4) * ((d.Wo + 7) / 8);
-    conv_head3x3_kernel<NV, CB><<<(unsigned)g, 256, smem, st>>>(d, M, tls);
+    const int g = d.N * ((d.Ho + HD_ROWS - 1) / HD_ROWS) * ((d.Wo + 7) / 8);
+    conv_head3x3_kernel<NV, CB><<<(unsigned)g, 64 * HD_ROWS, smem, st>>>(d, M, tls);
     return cudaGetLastError();
 }
 }  // namespace bflow
@@ -514,14 +516,14 @@ extern "C" int bflow_conv2d_small_n(const bflow_conv_desc* dp, void* stream) {
 // ---------------------------------------------------------------------------------------------
 // 7x7 stride-1 convolution of a THIN input (Cin = 4, 8, ... 32) to 128 channels: convf1 of the motion encoder (update.py:91,
 // Bezier parameters 2*degree -> 128).  K = 49*Cin is too small and too ragged for the tensor-core tiles, and the generic CUDA-core
-// kernel gathers it element by element.  Here a CTA owns a 4x8 patch of output pixels; per chunk of 4 input channels the 49*4*128
-// weights (100 KB) sit in shared memory next to the (4+6)x(8+6) input patch; a thread owns 4 consecutive pixels x 4 output channels and,
+// kernel gathers it element by element.  Here a CTA owns a 5x8 patch of output pixels (60x80 -> 120 CTAs: one wave); per chunk of 4 input channels the 49*4*128
+// weights (100 KB) sit in shared memory next to the (5+6)x(8+6) input patch; a thread owns 4 consecutive pixels x 4 output channels and,
 // per (channel, filter row), loads the 10 inputs its pixels need once and reuses them across the 7 filter columns: 112 FMAs per 17
 // shared-memory loads.
 // ---------------------------------------------------------------------------------------------
 namespace bflow {
-constexpr int TH_ROWS = 4, TH_COLS = 8, TH_CO = 128, TH_K = 7, TH_PR = TH_ROWS + TH_K - 1, TH_PC = TH_COLS + TH_K - 1;
-__global__ void __launch_bounds__(256) conv_thin7_kernel(const bflow_conv_desc d, unsigned long long* tl) {
+constexpr int TH_ROWS = 5, TH_COLS = 8, TH_CO = 128, TH_K = 7, TH_PR = TH_ROWS + TH_K - 1, TH_PC = TH_COLS + TH_K - 1;
+__global__ void __launch_bounds__(64 * TH_ROWS) conv_thin7_kernel(const bflow_conv_desc d, unsigned long long* tl) {
     extern __shared__ __align__(16) float th_smem[];
     float* s_w = th_smem;                                    // [49][4][128]
     float* s_x = th_smem + TH_K * TH_K * 4 * TH_CO;          // [4][TH_PR][TH_PC]
@@ -561,7 +563,7 @@ __global__ void __launch_bounds__(256) conv_thin7_kernel(const bflow_conv_desc d
                          "l"(d.w + (size_t)(tid * d.c0 + c0) * d.ldw), "r"(4 * TH_CO * 4), "r"(wbar)
                          : "memory");
         }
-        for (int i = tid; i < TH_PR * TH_PC; i += 256) {
+        for (int i = tid; i < TH_PR * TH_PC; i += 64 * TH_ROWS) {
             const int yy = i / TH_PC, xx = i - yy * TH_PC;
             const int iy = oy0 + yy - 3, ix = ox0 + xx - 3;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -646,7 +648,7 @@ extern "C" int bflow_conv2d_thin7(const bflow_conv_desc* dp, void* stream) {
         }
         configured = true;
     }
-    bflow::conv_thin7_kernel<<<(unsigned)tiles, 256, smem, (cudaStream_t)stream>>>(d, bflow::timeline_next_slot("conv_thin7"));
+    bflow::conv_thin7_kernel<<<(unsigned)tiles, 64 * bflow::TH_ROWS, smem, (cudaStream_t)stream>>>(d, bflow::timeline_next_slot("conv_thin7"));
     return bflow::check_launch("bflow_conv2d_thin7");
 }
 
