@@ -11,14 +11,27 @@ import os
 from . import build as _build
 
 MAX_SLOTS, MAX_TARGETS, MAX_DEGREE = 16, 8, 16
+ABI_VERSION = 2
 ACT = {'none': 0, 'relu': 1, 'sigmoid': 2, 'tanh': 3}
 EPI = {'std': 0, 'gru_zr': 1, 'gru_q': 2}
 
 c_float_p = C.c_void_p   # device pointers travel as integers
 
 
-class ConvDesc(C.Structure):
-    _fields_ = [('x0', C.c_void_p), ('c0', C.c_int), ('ld0', C.c_int),
+PREC = {'f32x3': 0, 'f16': 1}      # BFLOW_PREC_SPLIT3 / BFLOW_PREC_F16
+
+
+class _Desc(C.Structure):
+    """Descriptors start with struct_size (ABI version 2): filled in here so that no caller can forget it."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.struct_size = C.sizeof(type(self))
+
+
+class ConvDesc(_Desc):
+    _fields_ = [('struct_size', C.c_int), ('precision', C.c_int),
+                ('x0', C.c_void_p), ('c0', C.c_int), ('ld0', C.c_int),
                 ('x1', C.c_void_p), ('c1', C.c_int), ('ld1', C.c_int),
                 ('w', C.c_void_p), ('ldw', C.c_int),
                 ('bias', C.c_void_p),
@@ -37,8 +50,9 @@ class ConvDesc(C.Structure):
                 ('stats', C.c_void_p), ('stats_hw', C.c_int)]
 
 
-class LookupDesc(C.Structure):
-    _fields_ = [('n_slots', C.c_int), ('n_targets', C.c_int), ('B', C.c_int), ('h', C.c_int), ('w', C.c_int), ('radius', C.c_int),
+class LookupDesc(_Desc):
+    _fields_ = [('struct_size', C.c_int),
+                ('n_slots', C.c_int), ('n_targets', C.c_int), ('B', C.c_int), ('h', C.c_int), ('w', C.c_int), ('radius', C.c_int),
                 ('vol', C.c_void_p * MAX_SLOTS),
                 ('hl', C.c_int * MAX_SLOTS), ('wl', C.c_int * MAX_SLOTS),
                 ('target', C.c_int * MAX_SLOTS),
@@ -57,12 +71,13 @@ _SIGNATURES = {
     'bflow_abi_version': (C.c_int, []),
     'bflow_last_error': (C.c_char_p, []),
     'bflow_built_for_sm': (C.c_int, []),
+    'bflow_sizeof_conv_desc': (C.c_int, []),
+    'bflow_sizeof_lookup_desc': (C.c_int, []),
+    'bflow_source_hash': (C.c_char_p, []),
     'bflow_zero': (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_void_p]),
     'bflow_nchw_to_nhwc': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_float, C.c_float, C.c_void_p]),
     'bflow_nhwc_to_nchw': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     'bflow_conv2d_nhwc': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
-    'bflow_conv2d_tc_supported': (C.c_int, [C.POINTER(ConvDesc)]),
-    'bflow_conv2d_nhwc_tc': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     'bflow_tma_im2col_map': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 10),
     'bflow_conv2d_nhwc_tc3': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     'bflow_tma_tile_map': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 8),
@@ -74,7 +89,6 @@ _SIGNATURES = {
     'bflow_im2col_split16': (C.c_int, [C.c_void_p] + [C.c_int] * 11 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'bflow_split_f16': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
     'bflow_pack_b_tc': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
-    'bflow_corr_volume_tc': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     'bflow_conv2d_small_n': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     'bflow_conv2d_thin7': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     'bflow_plane_sums': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -87,7 +101,9 @@ _SIGNATURES = {
     'bflow_corr_pool_tiled': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     'bflow_corr_lookup': (C.c_int, [C.POINTER(LookupDesc), C.c_void_p]),
     'bflow_voxelize': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_int,
-                                 C.c_void_p, C.c_void_p]),
+                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    'bflow_flow_metrics': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_float, C.POINTER(C.c_float), C.c_int,
+                                     C.c_void_p, C.c_void_p]),
     'bflow_voxel_norm': (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     'bflow_epe_masked': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
     'bflow_gru_rh': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
@@ -107,13 +123,21 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         path = _build.LIB
-        if not os.path.isfile(path):
-            path = _build.build()          # raises when nvcc is unavailable: there is no other path
+        if _build.built_hash() != _build.source_hash():
+            # missing, or compiled from other sources than the ones in the tree: rebuild (raises where nvcc is unavailable -- there is
+            # no other path, and a binary that does not match its sources is never loaded silently)
+            path = _build.build(force=True)
         handle = C.CDLL(path)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)     # AttributeError = ABI mismatch, also loud
             fn.restype = res
             fn.argtypes = args
+        if handle.bflow_abi_version() != ABI_VERSION:
+            raise RuntimeError(f'libbflow_b200.so has ABI version {handle.bflow_abi_version()}, this binding needs {ABI_VERSION}')
+        if (handle.bflow_sizeof_conv_desc(), handle.bflow_sizeof_lookup_desc()) != (C.sizeof(ConvDesc), C.sizeof(LookupDesc)):
+            raise RuntimeError('descriptor layouts of libbflow_b200.so and bflow_b200/_lib.py differ')
+        if handle.bflow_source_hash().decode() != _build.source_hash():
+            raise RuntimeError('libbflow_b200.so was not built from the sources in this tree (python -m bflow_b200.build --force)')
         _lib = handle
     return _lib
 

@@ -28,10 +28,12 @@ def bernstein_coeffs(timestamps: Sequence[float], degree: int) -> np.ndarray:
 class BezierCurves:
     CTRL_DIM: int = 2
 
-    def __init__(self, bezier_params: th.Tensor):
+    def __init__(self, bezier_params: th.Tensor, ready_event=None):
         assert bezier_params.ndim == 4
         assert bezier_params.shape[1] % 2 == 0
-        self._params = bezier_params
+        self._raw = bezier_params
+        # results of a pipelined forward (RAFTSpline.forward(non_blocking=True)) are in flight until this event completes
+        self._ready_event = ready_event
         self.batch, channels, self.ht, self.wd = bezier_params.shape
         self.n_ctrl_pts = channels // self.CTRL_DIM + 1
 
@@ -58,20 +60,32 @@ class BezierCurves:
 
     # ---- tensor plumbing -------------------------------------------------------------------
     @property
+    def _params(self) -> th.Tensor:
+        if self._ready_event is not None:
+            self._ready_event.synchronize()
+            self._ready_event = None
+        return self._raw
+
+    @_params.setter
+    def _params(self, value: th.Tensor) -> None:
+        self._raw = value
+        self._ready_event = None
+
+    @property
     def device(self):
-        return self._params.device
+        return self._raw.device
 
     @property
     def dtype(self):
-        return self._params.dtype
+        return self._raw.dtype
 
     @property
     def requires_grad(self):
-        return self._params.requires_grad
+        return self._raw.requires_grad
 
     @property
     def batch_size(self):
-        return self._params.shape[0]
+        return self._raw.shape[0]
 
     @property
     def degree(self):
@@ -79,15 +93,15 @@ class BezierCurves:
 
     @property
     def dim(self):
-        return self._params.shape[1]
+        return self._raw.shape[1]
 
     @property
     def height(self):
-        return self._params.shape[-2]
+        return self._raw.shape[-2]
 
     @property
     def width(self):
-        return self._params.shape[-1]
+        return self._raw.shape[-1]
 
     def get_params(self) -> th.Tensor:
         return self._params

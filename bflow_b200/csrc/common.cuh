@@ -17,6 +17,22 @@ int check_launch(const char* what);
             return BFLOW_ERR_INVALID;                  \
         }                                              \
     } while (0)
+// a descriptor built against another version of the header is refused before any field behind struct_size is read
+#define BFLOW_CHECK_DESC(dp, type, what)                                                                                          \
+    do {                                                                                                                           \
+        BFLOW_REQUIRE((dp) != nullptr, what ": null descriptor");                                                                  \
+        BFLOW_REQUIRE((dp)->struct_size == (int)sizeof(type), what ": descriptor size mismatch (caller built against another bflow_b200.h; set struct_size = sizeof(" #type "))"); \
+    } while (0)
+
+// Per-device host state.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are per DEVICE, the process may drive several:
+// every cache on the launch path is keyed by the current device ordinal.
+int current_device();      // runtime.cu
+int num_sms();             // SMs of the current device (148 on B200)
+struct PerDeviceFlag {
+    bool done[64] = {};
+    bool get() const { const int d = current_device(); return d >= 0 && d < 64 && done[d]; }
+    void set() { const int d = current_device(); if (d >= 0 && d < 64) done[d] = true; }
+};
 
 // Gate activations on the SFU: ex2.approx + a fast divide (absolute error ~2e-7, the size of fp32 rounding of the gate itself).  The libm
 // versions cost 30-50 dependent instructions per element, and the 8 epilogue warps of a tensor-core CTA are latency-bound on exactly that chain
@@ -67,8 +83,28 @@ __device__ __forceinline__ float4 load_split4(const void* hi_base, const void* l
     const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
     return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
 }
+// hi plane alone (BFLOW_PREC_F16 tensors)
+__device__ __forceinline__ void store_hi4(void* hi_base, size_t elem, float a, float b, float c, float d) {
+    uint2 h;
+    h.x = pack_f16x2_sat(a, b);
+    h.y = pack_f16x2_sat(c, d);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(hi_base) + elem) = h;
+}
+__device__ __forceinline__ float4 load_hi4(const void* hi_base, size_t elem) {
+    const uint2 h = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(hi_base) + elem);
+    const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+    return make_float4(h0.x, h0.y, h1.x, h1.y);
+}
 __device__ __forceinline__ float load_split1(const void* hi_base, const void* lo_base, size_t elem) {
     return __half2float(reinterpret_cast<const __half*>(hi_base)[elem]) + __half2float(reinterpret_cast<const __half*>(lo_base)[elem]);
+}
+
+// split residual of a convolution: hi + lo, or the hi plane alone when the producer ran in BFLOW_PREC_F16 (its lo plane is never written)
+__device__ __forceinline__ float4 load_res16_4(const bflow_conv_desc& d, size_t elem) {
+    return d.precision == BFLOW_PREC_F16 ? load_hi4(d.res16_hi, elem) : load_split4(d.res16_hi, d.res16_lo, elem);
+}
+__device__ __forceinline__ float load_res16_1(const bflow_conv_desc& d, size_t elem) {
+    return d.precision == BFLOW_PREC_F16 ? __half2float(reinterpret_cast<const __half*>(d.res16_hi)[elem]) : load_split1(d.res16_hi, d.res16_lo, elem);
 }
 
 // Epilogue shared by the CUDA-core and tensor-core convolutions for 4 consecutive output channels n..n+3 of row m.
@@ -82,7 +118,7 @@ __device__ __forceinline__ void conv_epilogue4(const bflow_conv_desc& d, int m, 
                 const float4 r = *reinterpret_cast<const float4*>(d.res + (size_t)m * d.ldr + n);
                 v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
             } else if (d.res16_hi != nullptr) {
-                const float4 r = load_split4(d.res16_hi, d.res16_lo, (size_t)m * d.ldr16 + n);
+                const float4 r = load_res16_4(d, (size_t)m * d.ldr16 + n);
                 v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
             }
 #pragma unroll
@@ -95,7 +131,7 @@ __device__ __forceinline__ void conv_epilogue4(const bflow_conv_desc& d, int m, 
                 if (n + j < d.Cout) {
                     float o = v[j];
                     if (d.res != nullptr) o += d.res[(size_t)m * d.ldr + n + j];
-                    else if (d.res16_hi != nullptr) o += load_split1(d.res16_hi, d.res16_lo, (size_t)m * d.ldr16 + n + j);
+                    else if (d.res16_hi != nullptr) o += load_res16_1(d, (size_t)m * d.ldr16 + n + j);
                     o = apply_act(o, d.act2);
                     if (d.y != nullptr) d.y[(size_t)m * d.ldy + n + j] = o;
                     if (d.y16_hi != nullptr) store_split1(d.y16_hi, d.y16_lo, (size_t)m * d.ldy16 + n + j, o);
@@ -153,7 +189,7 @@ __device__ __forceinline__ void conv_epilogue4_prefetch(const bflow_conv_desc& d
     if (!vec) return;
     if (d.epi == BFLOW_EPI_STD) {
         if (d.res != nullptr) e.r = *reinterpret_cast<const float4*>(d.res + (size_t)m * d.ldr + n);
-        else if (d.res16_hi != nullptr) e.r = load_split4(d.res16_hi, d.res16_lo, (size_t)m * d.ldr16 + n);
+        else if (d.res16_hi != nullptr) e.r = load_res16_4(d, (size_t)m * d.ldr16 + n);
     } else if (d.epi == BFLOW_EPI_GRU_ZR) {
         if (d.res != nullptr) e.r = *reinterpret_cast<const float4*>(d.res + (size_t)m * d.ldr + n);
         const int C = d.Cout >> 1;

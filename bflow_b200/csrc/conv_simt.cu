@@ -230,7 +230,7 @@ static int launch_conv(const bflow_conv_desc& d, cudaStream_t stream) {
 }  // namespace bflow
 
 extern "C" int bflow_conv2d_nhwc(const bflow_conv_desc* dp, void* stream) {
-    BFLOW_REQUIRE(dp != nullptr, "conv: null descriptor");
+    BFLOW_CHECK_DESC(dp, bflow_conv_desc, "conv");
     const bflow_conv_desc& d = *dp;
     BFLOW_REQUIRE(d.x0 != nullptr && d.w != nullptr, "conv: null tensor");
     BFLOW_REQUIRE(d.c0 > 0 && d.c1 >= 0 && d.ld0 >= d.c0, "conv: bad source 0");
@@ -456,11 +456,11 @@ __global__ void __launch_bounds__(64 * HD_ROWS) conv_head3x3_kernel(const bflow_
 template <int NV, int CB>
 static cudaError_t launch_head3x3(const bflow_conv_desc& d, int M, cudaStream_t st, unsigned long long* tls) {
     const size_t smem = (size_t)9 * CB * 128 * NV * 16 + (size_t)(HD_ROWS + 2) * 10 * CB * 128 * 4;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (!configured.get()) {
         cudaError_t e = cudaFuncSetAttribute(conv_head3x3_kernel<NV, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured.set();
     }
     const int g = d.N * ((d.Ho + HD_ROWS - 1) / HD_ROWS) * ((d.Wo + 7) / 8);
     conv_head3x3_kernel<NV, CB><<<(unsigned)g, 64 * HD_ROWS, smem, st>>>(d, M, tls);
@@ -469,7 +469,7 @@ static cudaError_t launch_head3x3(const bflow_conv_desc& d, int M, cudaStream_t 
 }  // namespace bflow
 
 extern "C" int bflow_conv2d_small_n(const bflow_conv_desc* dp, void* stream) {
-    BFLOW_REQUIRE(dp != nullptr, "conv_small_n: null descriptor");
+    BFLOW_CHECK_DESC(dp, bflow_conv_desc, "conv_small_n");
     const bflow_conv_desc& d = *dp;
     BFLOW_REQUIRE(d.x0 != nullptr && d.w != nullptr, "conv_small_n: null tensor");
     BFLOW_REQUIRE(d.c1 == 0 && d.c0 > 0 && d.c0 % 4 == 0 && d.ld0 % 4 == 0 && bflow::aligned16(d.x0), "conv_small_n: one aligned source, Cin % 4 == 0");
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(64 * TH_ROWS) conv_thin7_kernel(const bflow_co
 }  // namespace bflow
 
 extern "C" int bflow_conv2d_thin7(const bflow_conv_desc* dp, void* stream) {
-    BFLOW_REQUIRE(dp != nullptr, "conv_thin7: null descriptor");
+    BFLOW_CHECK_DESC(dp, bflow_conv_desc, "conv_thin7");
     const bflow_conv_desc& d = *dp;
     BFLOW_REQUIRE(d.x0 != nullptr && d.w != nullptr, "conv_thin7: null tensor");
     BFLOW_REQUIRE(d.c1 == 0 && d.c0 > 0 && d.c0 % 4 == 0 && d.ld0 % 4 == 0 && bflow::aligned16(d.x0), "conv_thin7: one aligned source, Cin % 4 == 0");
@@ -639,14 +639,14 @@ extern "C" int bflow_conv2d_thin7(const bflow_conv_desc* dp, void* stream) {
     const long long tiles = (long long)d.N * ((d.Ho + bflow::TH_ROWS - 1) / bflow::TH_ROWS) * ((d.Wo + bflow::TH_COLS - 1) / bflow::TH_COLS);
     BFLOW_REQUIRE(tiles > 0 && tiles < (1ll << 31), "conv_thin7: bad shape");
     const size_t smem = (size_t)(bflow::TH_K * bflow::TH_K * 4 * bflow::TH_CO + 4 * bflow::TH_PR * bflow::TH_PC) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static bflow::PerDeviceFlag configured;
+    if (!configured.get()) {
         cudaError_t e = cudaFuncSetAttribute(bflow::conv_thin7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             bflow::set_error(cudaGetErrorString(e));
             return BFLOW_ERR_CUDA;
         }
-        configured = true;
+        configured.set();
     }
     bflow::conv_thin7_kernel<<<(unsigned)tiles, 64 * bflow::TH_ROWS, smem, (cudaStream_t)stream>>>(d, bflow::timeline_next_slot("conv_thin7"));
     return bflow::check_launch("bflow_conv2d_thin7");

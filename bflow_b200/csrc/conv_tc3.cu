@@ -60,12 +60,16 @@ __device__ __forceinline__ bool t3_mbar_test_wait(uint32_t bar, uint32_t parity)
 // development: per-role clock64 stamps of CTA 0 (bflow_tc3_trace); the pointer travels as a kernel parameter
 #define T3_CTA(i) do { if (p.cta != nullptr) p.cta[blockIdx.x * 16 + (i)] = global_ns(); } while (0)
 #define T3_TRACE(slot, idx) do { if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 256) p.trace[(slot) * 256 + (idx)] = clock64(); } while (0)
-// bounded: a protocol bug sets the error word instead of hanging the GPU
+// bounded: a protocol bug cannot hang the GPU.  After 2^24 failed polls (>= 0.3 s; no legitimate wait is longer than a few hundred
+// microseconds) the error word is set and the kernel traps: the launch fails loudly (cudaErrorLaunchFailure at the next
+// synchronisation) instead of carrying on with unfinished TMA / TMEM data.
 __device__ __forceinline__ void t3_mbar_wait(uint32_t bar, uint32_t parity, int* err) {
 #pragma unroll 1
     for (uint32_t it = 0; it < (1u << 24); ++it)
         if (t3_mbar_try_wait(bar, parity)) return;
     if (err != nullptr) atomicExch(err, 1);
+    __threadfence_system();
+    __trap();
 }
 // one lane of a CONVERGED warp (elect.sync): the branch it guards is the idiom under which nvcc keeps warp-uniform operands in uniform
 // registers and issues UTCHMMA / UTCBAR directly.  Under `if (lane == 0)` it wraps every tcgen05.mma in an ELECT + 5 x R2UR + loop
@@ -172,6 +176,7 @@ struct T3Params {
     // slab mode (stride-1 3x3 / 1x5 / 5x1): an output tile is an 8 x 16 pixel patch and one halo slab per slow filter index serves all taps
     // along the other axis (see conv_slab64_kernel).  1: slab rows = (y, x) with x fastest (taps along y), 2: rows = (x, y) (taps along x).
     int slab, tiles_x, tiles_y, n_slabs, tps;
+    int f16;      // BFLOW_PREC_F16: one MMA per k-step on the hi planes (lo planes / the lo half of the weight tiles are not loaded)
     int staged;   // every CTA owns exactly one tile: the epilogue goes through shared memory (coalesced, batched global accesses)
     int dbg;      // development switch (bflow_tc3_debug): 1 = no TMA loads (the producer only arrives: MMA + epilogue path alone)
 };
@@ -338,10 +343,16 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                             if (p.dbg & 1) {                 // development: no loads (MMA + epilogue path alone)
                                 t3_mbar_arrive(bar);
                             } else {
-                                t3_mbar_arrive_expect_tx(bar, TX_BYTES);
-                                t3_tma_im2col(stage, src0 ? &map0h : &map1h, cc, cw, ch, n, (uint16_t)kw, (uint16_t)kh, bar);
-                                t3_tma_im2col(stage + T3_A_BYTES, src0 ? &map0l : &map1l, cc, cw, ch, n, (uint16_t)kw, (uint16_t)kh, bar);
-                                t3_bulk_g2s(stage + 2 * T3_A_BYTES, wt + (size_t)kb * (2 * B_BYTES), 2 * B_BYTES, bar);
+                                if (p.f16) {             // hi plane and the hi half of the weight tile only
+                                    t3_mbar_arrive_expect_tx(bar, T3_A_BYTES + B_BYTES);
+                                    t3_tma_im2col(stage, src0 ? &map0h : &map1h, cc, cw, ch, n, (uint16_t)kw, (uint16_t)kh, bar);
+                                    t3_bulk_g2s(stage + 2 * T3_A_BYTES, wt + (size_t)kb * (2 * B_BYTES), B_BYTES, bar);
+                                } else {
+                                    t3_mbar_arrive_expect_tx(bar, TX_BYTES);
+                                    t3_tma_im2col(stage, src0 ? &map0h : &map1h, cc, cw, ch, n, (uint16_t)kw, (uint16_t)kh, bar);
+                                    t3_tma_im2col(stage + T3_A_BYTES, src0 ? &map0l : &map1l, cc, cw, ch, n, (uint16_t)kw, (uint16_t)kh, bar);
+                                    t3_bulk_g2s(stage + 2 * T3_A_BYTES, wt + (size_t)kb * (2 * B_BYTES), 2 * B_BYTES, bar);
+                                }
                             }
                         }
                         __syncwarp();
@@ -413,7 +424,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t ko = (uint64_t)(k * 2);             // 32 bytes along K, in 16-byte descriptor units
-                        if (STACK) {
+                        if (p.f16) {
+                            t3_umma(tacc, dah0 + ko, dbh0 + ko, idesc, (kb > 0 || k > 0) ? 1u : 0u);       // hi*hi alone
+                        } else if (STACK) {
                             t3_umma(tacc, dah0 + ko, dbh0 + ko, idesc2, (kb > 0 || k > 0) ? 1u : 0u);      // hi*hi | hi*lo
                             t3_umma(tacc, dal0 + ko, dbh0 + ko, idesc, 1u);                               // lo*hi
                         } else {
@@ -441,6 +454,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
         // 8 warps: quadrant (warp & 3) of the TMEM lanes = 32 tile rows, column half ((warp - 2) >> 2).  The tile's bias slice is
         // staged in shared memory once per n_tile; all tcgen05.ld of a thread's columns are issued before the single wait.
         constexpr int HALF = BN / 2;                  // columns per thread
+        const bool two_halves = STACK && !p.f16;      // the accumulator is [hi*hi + lo*hi | hi*lo]: the epilogue adds the halves
+        const bool wlo = !p.f16;                      // BFLOW_PREC_F16: nobody reads the lo planes, the hot store paths skip them
         const int quad = warp & 3;
         const int chalf = (warp - 2) >> 2;
         const int etid = tid - 64;                   // 0 .. 255
@@ -588,7 +603,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                     float v[32];
                     t3_tmem_ld16_nowait(taddr + (uint32_t)c0, v);
                     t3_tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), v + 16);
-                    if (STACK) {
+                    if (two_halves) {
                         float u[32];
                         t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0), u);
                         t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0 + 16), u + 16);
@@ -685,7 +700,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                     float v[32];
                     t3_tmem_ld16_nowait(taddr + (uint32_t)c0, v);
                     t3_tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), v + 16);
-                    if (STACK) {
+                    if (two_halves) {
                         float u[32];
                         t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0), u);
                         t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0 + 16), u + 16);
@@ -716,7 +731,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                             split2(v[c + 6], v[c + 7], h4.w, l4.w);
                             const int chunk = (((col & 63) + c) >> 3) ^ (row & 7);
                             *reinterpret_cast<uint4*>(bh + (chunk << 4)) = h4;
-                            *reinterpret_cast<uint4*>(bl + (chunk << 4)) = l4;
+                            if (wlo) *reinterpret_cast<uint4*>(bl + (chunk << 4)) = l4;
                         }
                     }
                     if (o32) {
@@ -739,7 +754,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                         for (int b = 0; b < NB16; ++b) {
                             if (n0 + b * 64 < d.Cout) {
                                 t3_tma_store2d(&omap_hi, t3_smem_u32(s_hi + b * 16384), n0 + b * 64, mt0);
-                                t3_tma_store2d(&omap_lo, t3_smem_u32(s_lo + b * 16384), n0 + b * 64, mt0);
+                                if (wlo) t3_tma_store2d(&omap_lo, t3_smem_u32(s_lo + b * 16384), n0 + b * 64, mt0);
                             }
                         }
                     }
@@ -760,7 +775,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                         const int lc = c8 - n0;
                         const int off = (lc >> 6) * 16384 + etid * 128 + ((((lc & 63) >> 3) ^ (etid & 7)) << 4);
                         *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(d.y16_hi) + (size_t)mm * d.ldy16 + c8) = *reinterpret_cast<const uint2*>(s_hi + off);
-                        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(d.y16_lo) + (size_t)mm * d.ldy16 + c8) = *reinterpret_cast<const uint2*>(s_lo + off);
+                        if (wlo) *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(d.y16_lo) + (size_t)mm * d.ldy16 + c8) = *reinterpret_cast<const uint2*>(s_lo + off);
                     }
                 }
                 __syncwarp();
@@ -783,7 +798,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                         float v[32];
                         t3_tmem_ld16_nowait(taddr + (uint32_t)c0, v);
                         t3_tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), v + 16);
-                        if (STACK) {
+                        if (two_halves) {
                             float u[32];
                             t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0), u);
                             t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0 + 16), u + 16);
@@ -874,7 +889,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                         float v[32];
                         t3_tmem_ld16_nowait(taddr + (uint32_t)c0, v);
                         t3_tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), v + 16);
-                        if (STACK) {
+                        if (two_halves) {
                             float u[32];
                             t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0), u);
                             t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0 + 16), u + 16);
@@ -995,7 +1010,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                         float v[32];
                         t3_tmem_ld16_nowait(taddr + (uint32_t)c0, v);
                         t3_tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), v + 16);
-                        if (STACK) {
+                        if (two_halves) {
                             float u[32];
                             t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0), u);
                             t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0 + 16), u + 16);
@@ -1054,7 +1069,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 float v[HALF];
 #pragma unroll
                 for (int c = 0; c < HALF; c += 16) t3_tmem_ld16_nowait(taddr + (uint32_t)c, v + c);
-                if (STACK) {
+                if (two_halves) {
                     float u[HALF];
 #pragma unroll
                     for (int c = 0; c < HALF; c += 16) t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c), u + c);
@@ -1153,7 +1168,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                             } else if (d.res16_hi != nullptr) {
 #pragma unroll
                                 for (int j = 0; j < 16; j += 4) {
-                                    const float4 r4 = load_split4(d.res16_hi, d.res16_lo, (size_t)m * d.ldr16 + nb + j);
+                                    const float4 r4 = load_res16_4(d, (size_t)m * d.ldr16 + nb + j);
                                     w[j] += r4.x; w[j + 1] += r4.y; w[j + 2] += r4.z; w[j + 3] += r4.w;
                                 }
                             }
@@ -1179,7 +1194,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                                         split2(w[j + 4], w[j + 5], h4.z, l4.z);
                                         split2(w[j + 6], w[j + 7], h4.w, l4.w);
                                         *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y16_hi) + (size_t)m * d.ldy16 + nb + j) = h4;
-                                        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y16_lo) + (size_t)m * d.ldy16 + nb + j) = l4;
+                                        if (wlo) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y16_lo) + (size_t)m * d.ldy16 + nb + j) = l4;
                                     }
                                 } else {
 #pragma unroll
@@ -1236,7 +1251,7 @@ constexpr int SL_STAGE = 2 * SL_PLANE;                   // hi + lo
 constexpr int SL_STAGES = 2;
 
 struct SlabParams {
-    int tiles_x, tiles_y, n_tiles;
+    int tiles_x, tiles_y, n_tiles, f16;
     float acc_scale;
     unsigned long long* tl;
 };
@@ -1299,9 +1314,9 @@ conv_slab64_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
                 t3_mbar_wait(empty_bar(s), ph ^ 1u, err);
                 const uint32_t st = stage0 + (uint32_t)s * SL_STAGE;
                 if (t3_elect_one()) {
-                    t3_mbar_arrive_expect_tx(full_bar(s), SL_STAGE);
+                    t3_mbar_arrive_expect_tx(full_bar(s), p.f16 ? SL_PLANE : SL_STAGE);
                     sl_tma_tile(st, &map_hi, 0, x0 + kw - 1, y0 - 1, n, full_bar(s));
-                    sl_tma_tile(st + SL_PLANE, &map_lo, 0, x0 + kw - 1, y0 - 1, n, full_bar(s));
+                    if (!p.f16) sl_tma_tile(st + SL_PLANE, &map_lo, 0, x0 + kw - 1, y0 - 1, n, full_bar(s));
                 }
                 __syncwarp();
             }
@@ -1330,8 +1345,12 @@ conv_slab64_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
                         for (int k = 0; k < 4; ++k) {
                             const uint32_t ko = (uint32_t)k * 32u;
                             const uint64_t dbh = t3_umma_desc(b + ko);
-                            t3_umma(tacc, t3_umma_desc(a_hi + (uint32_t)kh * 1024u + ko), dbh, idesc2, (kw > 0 || kh > 0 || k > 0) ? 1u : 0u);
-                            t3_umma(tacc, t3_umma_desc(a_lo + (uint32_t)kh * 1024u + ko), dbh, idesc, 1u);
+                            if (p.f16) {
+                                t3_umma(tacc, t3_umma_desc(a_hi + (uint32_t)kh * 1024u + ko), dbh, idesc, (kw > 0 || kh > 0 || k > 0) ? 1u : 0u);
+                            } else {
+                                t3_umma(tacc, t3_umma_desc(a_hi + (uint32_t)kh * 1024u + ko), dbh, idesc2, (kw > 0 || kh > 0 || k > 0) ? 1u : 0u);
+                                t3_umma(tacc, t3_umma_desc(a_lo + (uint32_t)kh * 1024u + ko), dbh, idesc, 1u);
+                            }
                         }
                     }
                     t3_commit(empty_bar(s));
@@ -1385,8 +1404,13 @@ conv_slab64_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             float v[32], u[32];
             t3_tmem_ld16_nowait(taddr, v);
             t3_tmem_ld16_nowait(taddr + 16u, v + 16);
-            t3_tmem_ld16_nowait(taddr + (uint32_t)SL_BN, u);
-            t3_tmem_ld16_nowait(taddr + (uint32_t)SL_BN + 16u, u + 16);
+            if (!p.f16) {
+                t3_tmem_ld16_nowait(taddr + (uint32_t)SL_BN, u);
+                t3_tmem_ld16_nowait(taddr + (uint32_t)SL_BN + 16u, u + 16);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) u[c] = 0.f;
+            }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             t3_fence_before();
             __syncwarp();
@@ -1431,7 +1455,7 @@ conv_slab64_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
                 if (d.res16_hi != nullptr) {
 #pragma unroll
                     for (int c = 0; c < 32; c += 4) {
-                        const float4 r4 = load_split4(d.res16_hi, d.res16_lo, m * d.ldr16 + nb0 + c);
+                        const float4 r4 = load_res16_4(d, m * d.ldr16 + nb0 + c);
                         v[c] += r4.x; v[c + 1] += r4.y; v[c + 2] += r4.z; v[c + 3] += r4.w;
                     }
                 }
@@ -1451,7 +1475,7 @@ conv_slab64_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
                         split2(v[c + 4], v[c + 5], h4.z, l4.z);
                         split2(v[c + 6], v[c + 7], h4.w, l4.w);
                         *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y16_hi) + m * d.ldy16 + nb0 + c) = h4;
-                        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y16_lo) + m * d.ldy16 + nb0 + c) = l4;
+                        if (!p.f16) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y16_lo) + m * d.ldy16 + nb0 + c) = l4;
                     }
                 }
             }
@@ -1485,6 +1509,7 @@ constexpr int ST_PATCH_BYTES = ST_MAXC * ST_PH * ST_PW * 4;   // 28416
 struct StemParams {
     int tiles_x, tiles_y, n_tiles, cin, c_total, K;
     int n_win, ns, c_off[8];      // image n = window * ns + sample: channels [c_off[window], +cin) of input sample `sample`
+    int f16;
     float acc_scale, in_scale, in_shift;
     unsigned long long* tl;
 };
@@ -1579,8 +1604,12 @@ conv_stem7_kernel(const bflow_conv_desc d, const uint8_t* __restrict__ wtc, cons
                     for (int k = 0; k < 4; ++k) {
                         const uint32_t ko = (uint32_t)k * 32u;
                         const uint64_t dbh = t3_umma_desc(b + ko);
-                        t3_umma(tacc, t3_umma_desc(a_hi + ko), dbh, idesc2, (kb > 0 || k > 0) ? 1u : 0u);
-                        t3_umma(tacc, t3_umma_desc(a_lo + ko), dbh, idesc, 1u);
+                        if (p.f16) {
+                            t3_umma(tacc, t3_umma_desc(a_hi + ko), dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        } else {
+                            t3_umma(tacc, t3_umma_desc(a_hi + ko), dbh, idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+                            t3_umma(tacc, t3_umma_desc(a_lo + ko), dbh, idesc, 1u);
+                        }
                     }
                 }
                 t3_commit(a_empty);
@@ -1631,8 +1660,13 @@ conv_stem7_kernel(const bflow_conv_desc d, const uint8_t* __restrict__ wtc, cons
             float v[32], u[32];
             t3_tmem_ld16_nowait(taddr, v);
             t3_tmem_ld16_nowait(taddr + 16u, v + 16);
-            t3_tmem_ld16_nowait(taddr + (uint32_t)SL_BN, u);
-            t3_tmem_ld16_nowait(taddr + (uint32_t)SL_BN + 16u, u + 16);
+            if (!p.f16) {
+                t3_tmem_ld16_nowait(taddr + (uint32_t)SL_BN, u);
+                t3_tmem_ld16_nowait(taddr + (uint32_t)SL_BN + 16u, u + 16);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) u[c] = 0.f;
+            }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             t3_fence_before();
             const int nb0 = chalf * 32;
@@ -1685,7 +1719,7 @@ conv_stem7_kernel(const bflow_conv_desc d, const uint8_t* __restrict__ wtc, cons
                         split2(v[c + 4], v[c + 5], h4.z, l4.z);
                         split2(v[c + 6], v[c + 7], h4.w, l4.w);
                         *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y16_hi) + m * d.ldy16 + nb0 + c) = h4;
-                        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y16_lo) + m * d.ldy16 + nb0 + c) = l4;
+                        if (!p.f16) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y16_lo) + m * d.ldy16 + nb0 + c) = l4;
                     }
                 }
             }
@@ -1738,7 +1772,7 @@ conv_stem7_kernel(const bflow_conv_desc d, const uint8_t* __restrict__ wtc, cons
                 split2(xv[6], xv[7], h4.w, l4.w);
                 uint8_t* dst = gen + kb * (2 * T3_A_BYTES) + brow * 128 + ((j ^ (brow & 7)) << 4);
                 *reinterpret_cast<uint4*>(dst) = h4;
-                *reinterpret_cast<uint4*>(dst + T3_A_BYTES) = l4;
+                if (!p.f16) *reinterpret_cast<uint4*>(dst + T3_A_BYTES) = l4;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of A -> visible to the tensor core
             t3_mbar_arrive(a_full);
@@ -1780,16 +1814,6 @@ static EncodeIm2colFn get_encode_im2col() {
     return fn;
 }
 
-static int g_num_sms = 0;
-static int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
-    }
-    return g_num_sms;
-}
 static int g_tc3_debug = 0;
 static long long* g_tc3_trace = nullptr;
 static unsigned long long* g_tc3_cta = nullptr;
@@ -1798,14 +1822,14 @@ static int g_tc3_cta_nth = -1, g_tc3_cta_count = 0;
 template <int BN, int STAGES>
 static int launch_tc3(const CUtensorMap* maps, const bflow_conv_desc& d, const void* wtc, const T3Params& p, int* err, cudaStream_t stream) {      // maps: 4 input + 3 output
     constexpr int smem = t3_area_bytes(BN, STAGES) + 128 + 3 * BN * 4 + 64 + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (!configured.get()) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) {
             set_error(cudaGetErrorString(e));
             return BFLOW_ERR_CUDA;
         }
-        configured = true;
+        configured.set();
     }
     const int n_tiles = p.n_mtiles * p.n_ntiles;
     const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
@@ -1910,10 +1934,10 @@ extern "C" int bflow_im2col_split16(const float* src, int C_total, int c_off, in
     const long long g = (rows + bflow::I2C_ROWS - 1) / bflow::I2C_ROWS;
     BFLOW_REQUIRE((long long)cin * H * W < (1ll << 31), "im2col_split16: source too large");
     const size_t smem = (size_t)bflow::I2C_ROWS * (ld16 + 1) * sizeof(float) + (size_t)ld16 * 2 * sizeof(int);
-    static bool configured = false;
-    if (!configured) {
+    static bflow::PerDeviceFlag configured;
+    if (!configured.get()) {
         cudaFuncSetAttribute(bflow::im2col_split16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1025 * 4 + 1024 * 8);
-        configured = true;
+        configured.set();
     }
     bflow::im2col_split16_kernel<<<(unsigned)g, 256, smem, (cudaStream_t)stream>>>(src, C_total, c_off, cin, H, W, Ho, Wo, KH, KW, stride, pad_h, pad_w, scale, shift,
                                                                                 reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), ld16, rows,
@@ -1974,7 +1998,8 @@ extern "C" int bflow_tma_im2col_map(void* map_out, const void* base, int N, int 
 
 static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* omaps, const void* w_tc, int bn, float acc_scale, int slab, int* err,
                      void* stream) {
-    BFLOW_REQUIRE(dp != nullptr && maps != nullptr && w_tc != nullptr, "conv_tc3: null argument");
+    BFLOW_CHECK_DESC(dp, bflow_conv_desc, "conv_tc3");
+    BFLOW_REQUIRE(maps != nullptr && w_tc != nullptr, "conv_tc3: null argument");
     const bflow_conv_desc& d = *dp;
     if (slab) {
         BFLOW_REQUIRE(slab == 1 || slab == 2, "conv_tc3s: orientation must be 1 (taps along y) or 2 (taps along x)");
@@ -2013,6 +2038,9 @@ static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* om
     p.ncb1 = (d.c1 + 63) / 64;
     p.nkb = p.ntaps * (p.ncb0 + p.ncb1);
     p.acc_scale = acc_scale;
+    BFLOW_REQUIRE(d.precision == BFLOW_PREC_SPLIT3 || d.precision == BFLOW_PREC_F16, "conv_tc3: unknown precision");
+    BFLOW_REQUIRE(d.precision == BFLOW_PREC_SPLIT3 || !slab, "conv_tc3s: the halo-slab mode has no single-MMA form");
+    p.f16 = d.precision == BFLOW_PREC_F16 ? 1 : 0;
     p.dbg = bflow::g_tc3_debug;
     {
         const int sms = bflow::num_sms();
@@ -2198,7 +2226,8 @@ extern "C" int bflow_tma_tile_map(void* map_out, const void* base, int N, int H,
 // maps: two 128-byte tensor maps {hi, lo} from bflow_tma_tile_map(..., box_w 8, box_h 18).  w_tc: the bflow_conv2d_nhwc_tc3 weight image for
 // bn = 64 (tap-major k-blocks).  Epilogue: bias, act1, split residual, act2 (none / relu), fp32 and / or split output, fused InstanceNorm sums.
 extern "C" int bflow_conv2d_slab64(const bflow_conv_desc* dp, const void* maps, const void* w_tc, float acc_scale, int* err, void* stream) {
-    BFLOW_REQUIRE(dp != nullptr && maps != nullptr && w_tc != nullptr, "conv_slab64: null argument");
+    BFLOW_CHECK_DESC(dp, bflow_conv_desc, "conv_slab64");
+    BFLOW_REQUIRE(maps != nullptr && w_tc != nullptr, "conv_slab64: null argument");
     const bflow_conv_desc& d = *dp;
     BFLOW_REQUIRE(d.c0 == 64 && d.c1 == 0 && d.Cout == 64 && d.KH == 3 && d.KW == 3 && d.stride == 1 && d.pad_h == 1 && d.pad_w == 1, "conv_slab64: 3x3/1 64->64 only");
     BFLOW_REQUIRE(d.N > 0 && d.H > 0 && d.W > 0 && d.W % 8 == 0 && d.Ho == d.H && d.Wo == d.W, "conv_slab64: W must be a multiple of 8");
@@ -2215,16 +2244,18 @@ extern "C" int bflow_conv2d_slab64(const bflow_conv_desc* dp, const void* maps, 
     BFLOW_REQUIRE(nt < (1ll << 31), "conv_slab64: too large");
     p.n_tiles = (int)nt;
     p.acc_scale = acc_scale;
+    BFLOW_REQUIRE(d.precision == BFLOW_PREC_SPLIT3 || d.precision == BFLOW_PREC_F16, "conv_slab64: unknown precision");
+    p.f16 = d.precision == BFLOW_PREC_F16 ? 1 : 0;
     p.tl = bflow::timeline_next_slot("slab64");
     constexpr int smem = bflow::SL_B_BYTES + bflow::SL_STAGES * bflow::SL_STAGE + 128 + 3 * 64 * 4 + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static bflow::PerDeviceFlag configured;
+    if (!configured.get()) {
         cudaError_t e = cudaFuncSetAttribute(bflow::conv_slab64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) {
             bflow::set_error(cudaGetErrorString(e));
             return BFLOW_ERR_CUDA;
         }
-        configured = true;
+        configured.set();
     }
     alignas(64) CUtensorMap tm[2];
     memcpy(tm, maps, sizeof(tm));
@@ -2238,7 +2269,8 @@ extern "C" int bflow_conv2d_slab64(const bflow_conv_desc* dp, const void* maps, 
 // x0: the fp32 NCHW input; w_tc: tc3 weight image (bn 64) of the [64][256] matrix with K = (kh*7+kw)*cin + c.
 extern "C" int bflow_conv2d_stem7(const bflow_conv_desc* dp, const void* w_tc, int c_total, const int* c_offs, int n_windows, float in_scale,
                                   float in_shift, float acc_scale, int* err, void* stream) {
-    BFLOW_REQUIRE(dp != nullptr && w_tc != nullptr, "conv_stem7: null argument");
+    BFLOW_CHECK_DESC(dp, bflow_conv_desc, "conv_stem7");
+    BFLOW_REQUIRE(w_tc != nullptr, "conv_stem7: null argument");
     BFLOW_REQUIRE(dp->x0 != nullptr && bflow::aligned16(dp->x0) && dp->W % 4 == 0, "conv_stem7: x0 = 16-byte aligned fp32 NCHW input, W % 4 == 0");
     const bflow_conv_desc& d = *dp;
     BFLOW_REQUIRE(d.c0 > 0 && d.c0 <= bflow::ST_MAXC && 49 * d.c0 <= 256 && d.c1 == 0 && d.Cout == 64, "conv_stem7: cin <= 5, Cout == 64");
@@ -2266,16 +2298,18 @@ extern "C" int bflow_conv2d_stem7(const bflow_conv_desc* dp, const void* w_tc, i
     p.acc_scale = acc_scale;
     p.in_scale = in_scale;
     p.in_shift = in_shift;
+    BFLOW_REQUIRE(d.precision == BFLOW_PREC_SPLIT3 || d.precision == BFLOW_PREC_F16, "conv_stem7: unknown precision");
+    p.f16 = d.precision == BFLOW_PREC_F16 ? 1 : 0;
     p.tl = bflow::timeline_next_slot("stem7");
     constexpr int smem = bflow::ST_A_BYTES + bflow::ST_B_BYTES + bflow::ST_PATCH_BYTES + 64 + 256 * 4 + 3 * 64 * 4 + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static bflow::PerDeviceFlag configured;
+    if (!configured.get()) {
         cudaError_t e = cudaFuncSetAttribute(bflow::conv_stem7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) {
             bflow::set_error(cudaGetErrorString(e));
             return BFLOW_ERR_CUDA;
         }
-        configured = true;
+        configured.set();
     }
     const int grid = p.n_tiles < bflow::num_sms() ? p.n_tiles : bflow::num_sms();
     bflow::conv_stem7_kernel<<<grid, bflow::T3_THREADS, smem, (cudaStream_t)stream>>>(d, reinterpret_cast<const uint8_t*>(w_tc), p, err);

@@ -213,9 +213,11 @@ __device__ __forceinline__ void lookup_unit(const bflow_lookup_desc& d, const un
         if (lane + 32 * j < 81) {
             const float* f = f0 + soff[j];
             const float val = w00 * f[0] + w01 * f[1] + w10 * f[LK2_PITCH] + w11 * f[LK2_PITCH + 1];
-            if (d.out16_hi != nullptr)
-                store_split1(d.out16_hi, d.out16_lo, (size_t)bq * d.out16_ld + slot * 81 + lane + 32 * j, val);
-            else
+            if (d.out16_hi != nullptr) {
+                const size_t e = (size_t)bq * d.out16_ld + slot * 81 + lane + 32 * j;
+                if (d.out16_lo != nullptr) store_split1(d.out16_hi, d.out16_lo, e, val);
+                else reinterpret_cast<__half*>(d.out16_hi)[e] = __float2half_rn(fminf(fmaxf(val, -65504.f), 65504.f));      // BFLOW_PREC_F16 consumers
+            } else
                 d.out[(size_t)bq * d.out_ld + slot * 81 + lane + 32 * j] = val;
         }
     }
@@ -273,14 +275,14 @@ __global__ void __launch_bounds__(LK2_WARPS * 32) corr_lookup_tiled_kernel(const
 }  // namespace bflow
 
 extern "C" int bflow_corr_lookup(const bflow_lookup_desc* dp, void* stream) {
-    BFLOW_REQUIRE(dp != nullptr, "lookup: null descriptor");
+    BFLOW_CHECK_DESC(dp, bflow_lookup_desc, "lookup");
     const bflow_lookup_desc& d = *dp;
     BFLOW_REQUIRE(d.n_slots > 0 && d.n_slots <= BFLOW_MAX_SLOTS, "lookup: bad slot count");
     BFLOW_REQUIRE(d.n_targets > 0 && d.n_targets <= BFLOW_MAX_TARGETS, "lookup: bad target count");
     BFLOW_REQUIRE(d.B > 0 && d.h > 0 && d.w > 0, "lookup: bad shape");
     BFLOW_REQUIRE(d.radius == 4, "lookup: radius is fixed to 4 (raft.py:38-40, corr.py:279)");
     BFLOW_REQUIRE(d.out != nullptr || d.out16_hi != nullptr, "lookup: null output");
-    BFLOW_REQUIRE(d.out16_hi == nullptr || (d.out16_lo != nullptr && d.tiled && d.out_nhwc && d.out16_ld >= d.n_slots * 81),
+    BFLOW_REQUIRE(d.out16_hi == nullptr || (d.tiled && d.out_nhwc && d.out16_ld >= d.n_slots * 81),
                   "lookup: split-fp16 output needs the tiled NHWC path");
     BFLOW_REQUIRE(d.coords != nullptr || (d.params != nullptr && d.degree >= 1 && d.degree <= BFLOW_MAX_DEGREE &&
                                           d.params_ld >= 2 * d.degree),
@@ -294,17 +296,14 @@ extern "C" int bflow_corr_lookup(const bflow_lookup_desc* dp, void* stream) {
     if (d.tiled && d.out_nhwc) {
         BFLOW_REQUIRE(BQ * d.n_slots < (1ll << 31), "lookup: too many units");
         const long long n_units = BQ * d.n_slots;
-        static int mode = -1, occ = 0, sms = 0;
+        static int mode = -1, occ = 0;
         if (mode < 0) {
             const char* e = getenv("BFLOW_LK_FLAT");
             mode = (e != nullptr && e[0] == '0') ? 0 : 1;
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bflow::corr_lookup_tiled_kernel<true>, bflow::LK2_WARPS * 32, 0);
-            if (sms <= 0) sms = 148;
             if (occ <= 0) occ = 6;
         }
+        const int sms = bflow::num_sms();
         cudaError_t le;
         unsigned long long* tls = bflow::timeline_next_slot("corr_lookup");
         const long long resident_warps = (long long)sms * occ * bflow::LK2_WARPS;
@@ -315,10 +314,10 @@ extern "C" int bflow_corr_lookup(const bflow_lookup_desc* dp, void* stream) {
             le = bflow::launch_pdl(bflow::corr_lookup_tiled_kernel<true>, dim3((unsigned)g), dim3(bflow::LK2_WARPS * 32), 0, (cudaStream_t)stream, d, n_units, 0, tls);
         } else {
             long long g = bflow::ceil_div_ll(BQ, bflow::LK2_WARPS);
-            const long long cap = 148ll * 8 * 8;
+            const long long cap = (long long)sms * 8 * 8;
             if (g > cap) g = cap;
             // few query pixels: split the slots over blockIdx.y so that every SM still holds a full set of warps
-            long long groups = bflow::ceil_div_ll(148ll * 48, BQ);
+            long long groups = bflow::ceil_div_ll((long long)sms * 48, BQ);
             if (groups < 1) groups = 1;
             if (groups > d.n_slots) groups = d.n_slots;
             const int spg = (int)bflow::ceil_div_ll(d.n_slots, groups);

@@ -161,13 +161,119 @@ __global__ void __launch_bounds__(256) instnorm_relu16_kernel(const float* __res
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[j] = fmaxf((o[j] - mu_a[c + j]) * rs_a[c + j], 0.f);
         if (r != nullptr || r16h != nullptr) {
-            const float4 rv = r != nullptr ? *reinterpret_cast<const float4*>(r + pix * ldr + c) : load_split4(r16h, r16l, pix * ldr16 + c);
+            const float4 rv = r != nullptr ? *reinterpret_cast<const float4*>(r + pix * ldr + c) : (r16l != nullptr ? load_split4(r16h, r16l, pix * ldr16 + c) : load_hi4(r16h, pix * ldr16 + c));
             const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j] + (rr[j] - mu_r[c + j]) * rs_r[c + j], 0.f);
         }
         if (out != nullptr) *reinterpret_cast<float4*>(out + pix * ldo + c) = make_float4(o[0], o[1], o[2], o[3]);
-        if (o16h != nullptr) store_split4(o16h, o16l, pix * ldo16 + c, o[0], o[1], o[2], o[3]);
+        if (o16h != nullptr) {
+            if (o16l != nullptr) store_split4(o16h, o16l, pix * ldo16 + c, o[0], o[1], o[2], o[3]);
+            else store_hi4(o16h, pix * ldo16 + c, o[0], o[1], o[2], o[3]);
+        }
+    }
+    tl_end(tl);
+}
+
+// Eight consecutive channels of one pixel: InstanceNorm + ReLU (+ skip) and the hi / lo split.  o16l == nullptr: hi plane only.
+struct In8 {
+    float4 a0, a1;      // raw conv output
+    float4 r0, r1;      // fp32 residual
+    uint4 rh, rl;       // split residual
+};
+template <bool HAS_R32, bool HAS_R16>
+__device__ __forceinline__ void in8_load(In8& v, const float* __restrict__ a, size_t ia, const float* __restrict__ r, size_t ir,
+                                         const void* __restrict__ r16h, const void* __restrict__ r16l, size_t ir16) {
+    v.a0 = __ldcs(reinterpret_cast<const float4*>(a + ia));          // streamed once: do not keep the raw tensor in L1 / L2 ahead of others
+    v.a1 = __ldcs(reinterpret_cast<const float4*>(a + ia + 4));
+    if (HAS_R32) {
+        v.r0 = __ldg(reinterpret_cast<const float4*>(r + ir));
+        v.r1 = __ldg(reinterpret_cast<const float4*>(r + ir + 4));
+    }
+    if (HAS_R16) {
+        v.rh = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(r16h) + ir16));
+        v.rl = r16l != nullptr ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(r16l) + ir16)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+__device__ __forceinline__ float2 h2f(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+
+// Fast path of bflow_instnorm_relu16: C % 8 == 0 and every row 16-byte aligned.  A thread owns 8 channels of a pixel (two 16-byte loads,
+// one 16-byte store per output plane) and keeps two pixels in flight; a CTA covers IN_CHUNK pixels of one image.
+template <bool HAS_R32, bool HAS_R16>
+__global__ void __launch_bounds__(256) instnorm_relu16_v8_kernel(const float* __restrict__ a, int lda, const double* __restrict__ sums_a,
+                                                                 const float* __restrict__ r, int ldr, const double* __restrict__ sums_r,
+                                                                 const void* __restrict__ r16h, const void* __restrict__ r16l, int ldr16,
+                                                                 float* __restrict__ out, int ldo, void* __restrict__ o16h, void* __restrict__ o16l, int ldo16,
+                                                                 int HW, int C, float eps, unsigned long long* tl) {
+    __shared__ float mu_a[IN_MAXC], rs_a[IN_MAXC], mu_r[IN_MAXC], rs_r[IN_MAXC];
+    const int n = blockIdx.y;
+    tl_begin(tl);
+    const double inv_hw = 1.0 / (double)HW;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double s = sums_a[((size_t)n * C + c) * 2], ss = sums_a[((size_t)n * C + c) * 2 + 1];
+        double m = s * inv_hw;
+        double var = ss * inv_hw - m * m;
+        if (var < 0.0) var = 0.0;
+        mu_a[c] = (float)m;
+        rs_a[c] = rsqrtf((float)(var + (double)eps));
+        mu_r[c] = 0.f;
+        rs_r[c] = 1.f;
+        if (HAS_R32 && sums_r != nullptr) {
+            s = sums_r[((size_t)n * C + c) * 2]; ss = sums_r[((size_t)n * C + c) * 2 + 1];
+            m = s * inv_hw;
+            var = ss * inv_hw - m * m;
+            if (var < 0.0) var = 0.0;
+            mu_r[c] = (float)m;
+            rs_r[c] = rsqrtf((float)(var + (double)eps));
+        }
+    }
+    __syncthreads();
+    const int p0 = blockIdx.x * IN_CHUNK;
+    const int np = min(IN_CHUNK, HW - p0);
+    const int C8 = C >> 3;
+    const int total = np * C8;
+    auto finish = [&](const In8& v, size_t pix, int c) {
+        float o[8] = {v.a0.x, v.a0.y, v.a0.z, v.a0.w, v.a1.x, v.a1.y, v.a1.z, v.a1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaxf((o[j] - mu_a[c + j]) * rs_a[c + j], 0.f);
+        if (HAS_R32) {
+            const float rr[8] = {v.r0.x, v.r0.y, v.r0.z, v.r0.w, v.r1.x, v.r1.y, v.r1.z, v.r1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j] + (rr[j] - mu_r[c + j]) * rs_r[c + j], 0.f);
+        }
+        if (HAS_R16) {
+            const uint32_t hw_[4] = {v.rh.x, v.rh.y, v.rh.z, v.rh.w}, lw_[4] = {v.rl.x, v.rl.y, v.rl.z, v.rl.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 hf = h2f(hw_[j]), lf = h2f(lw_[j]);
+                o[2 * j] = fmaxf(o[2 * j] + (hf.x + lf.x), 0.f);
+                o[2 * j + 1] = fmaxf(o[2 * j + 1] + (hf.y + lf.y), 0.f);
+            }
+        }
+        if (out != nullptr) {
+            *reinterpret_cast<float4*>(out + pix * ldo + c) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(out + pix * ldo + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+        if (o16h != nullptr) {
+            uint4 h4, l4;
+            split2(o[0], o[1], h4.x, l4.x);
+            split2(o[2], o[3], h4.y, l4.y);
+            split2(o[4], o[5], h4.z, l4.z);
+            split2(o[6], o[7], h4.w, l4.w);
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(o16h) + pix * ldo16 + c) = h4;
+            if (o16l != nullptr) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(o16l) + pix * ldo16 + c) = l4;
+        }
+    };
+    for (int idx = threadIdx.x; idx < total; idx += 2 * 256) {
+        const int idx1 = idx + 256;
+        const int pp0 = idx / C8, c0 = (idx - pp0 * C8) * 8;
+        const int pp1 = idx1 / C8, c1 = (idx1 - pp1 * C8) * 8;
+        const size_t pix0 = (size_t)n * HW + p0 + pp0, pix1 = (size_t)n * HW + p0 + pp1;
+        In8 v0, v1;
+        in8_load<HAS_R32, HAS_R16>(v0, a, pix0 * lda + c0, r, pix0 * ldr + c0, r16h, r16l, pix0 * ldr16 + c0);
+        if (idx1 < total) in8_load<HAS_R32, HAS_R16>(v1, a, pix1 * lda + c1, r, pix1 * ldr + c1, r16h, r16l, pix1 * ldr16 + c1);
+        finish(v0, pix0, c0);
+        if (idx1 < total) finish(v1, pix1, c1);
     }
     tl_end(tl);
 }
@@ -322,7 +428,7 @@ __global__ void __launch_bounds__(256) cvx_upsample_kernel(const float* __restri
 
 static inline unsigned grid_1d(long long total, int block) {
     long long g = ceil_div_ll(total, block);
-    const long long cap = 148ll * 16;
+    const long long cap = (long long)num_sms() * 16;
     return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
@@ -375,13 +481,24 @@ extern "C" int bflow_instnorm_relu16(const float* a, int lda, const double* sums
     BFLOW_REQUIRE(N > 0 && N <= 65535 && HW > 0 && C > 0 && C <= IN_MAXC && C % 4 == 0, "instnorm16: bad shape (C%4==0, C<=512)");
     BFLOW_REQUIRE(lda >= C && lda % 4 == 0 && aligned16(a), "instnorm16: alignment");
     BFLOW_REQUIRE(out == nullptr || (ldo >= C && ldo % 4 == 0 && aligned16(out)), "instnorm16: fp32 output alignment");
-    BFLOW_REQUIRE(out16_hi == nullptr || (out16_lo != nullptr && ldo16 >= C && ldo16 % 4 == 0), "instnorm16: split output");
+    BFLOW_REQUIRE(out16_hi == nullptr || (ldo16 >= C && ldo16 % 4 == 0), "instnorm16: split output");
     BFLOW_REQUIRE(r == nullptr || (r16_hi == nullptr && ldr >= C && ldr % 4 == 0 && aligned16(r)), "instnorm16: residual alignment");
-    BFLOW_REQUIRE(r16_hi == nullptr || (r16_lo != nullptr && ldr16 >= C && ldr16 % 4 == 0 && sums_r == nullptr), "instnorm16: split residual");
+    BFLOW_REQUIRE(r16_hi == nullptr || (ldr16 >= C && ldr16 % 4 == 0 && sums_r == nullptr), "instnorm16: split residual");
     BFLOW_REQUIRE(r != nullptr || sums_r == nullptr, "instnorm16: residual sums without fp32 residual");
     dim3 grid(ceil_div(HW, IN_CHUNK), N);
-    instnorm_relu16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, lda, sums_a, r, ldr, sums_r, r16_hi, r16_lo, ldr16, out, ldo, out16_hi, out16_lo, ldo16,
-                                                                   HW, C, eps, timeline_next_slot("instnorm_relu16"));
+    unsigned long long* tls = timeline_next_slot("instnorm_relu16");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool v8 = C % 8 == 0 && lda % 4 == 0 && (out == nullptr || ldo % 4 == 0) &&
+                    (out16_hi == nullptr || (ldo16 % 8 == 0 && aligned16(out16_hi) && (out16_lo == nullptr || aligned16(out16_lo)))) &&
+                    (r16_hi == nullptr || (ldr16 % 8 == 0 && aligned16(r16_hi) && (r16_lo == nullptr || aligned16(r16_lo))));
+    if (v8 && r == nullptr && r16_hi == nullptr)
+        instnorm_relu16_v8_kernel<false, false><<<grid, 256, 0, st>>>(a, lda, sums_a, r, ldr, sums_r, r16_hi, r16_lo, ldr16, out, ldo, out16_hi, out16_lo, ldo16, HW, C, eps, tls);
+    else if (v8 && r != nullptr)
+        instnorm_relu16_v8_kernel<true, false><<<grid, 256, 0, st>>>(a, lda, sums_a, r, ldr, sums_r, r16_hi, r16_lo, ldr16, out, ldo, out16_hi, out16_lo, ldo16, HW, C, eps, tls);
+    else if (v8)
+        instnorm_relu16_v8_kernel<false, true><<<grid, 256, 0, st>>>(a, lda, sums_a, r, ldr, sums_r, r16_hi, r16_lo, ldr16, out, ldo, out16_hi, out16_lo, ldo16, HW, C, eps, tls);
+    else
+        instnorm_relu16_kernel<<<grid, 256, 0, st>>>(a, lda, sums_a, r, ldr, sums_r, r16_hi, r16_lo, ldr16, out, ldo, out16_hi, out16_lo, ldo16, HW, C, eps, tls);
     return check_launch("bflow_instnorm_relu16");
 }
 

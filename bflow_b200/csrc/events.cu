@@ -7,6 +7,8 @@
 //   bflow_voxel_norm      norm_voxel_grid (representations.py:9-18): mean / unbiased std over the non-zero voxels, applied to them.
 //   bflow_epe_masked      epe_masked (utils/metrics.py:196-213): sum over valid pixels of sqrt(sum_c (src-tgt)^2) and their count — the
 //                         per-rank state that bflow_b200.dist.gather_epe exchanges.
+//   bflow_flow_metrics    EPE, angular error (ae_masked, metrics.py:259-296) and N-pixel error (n_pixel_error_masked, :161-193) in one
+//                         pass, with an optional scale on the prediction (linear-assumption baseline, :298-305).
 #include "common.cuh"
 
 namespace bflow {
@@ -14,7 +16,7 @@ namespace bflow {
 template <bool FLOAT_XY>
 __global__ void voxelize_kernel(const void* __restrict__ xs, const void* __restrict__ ys, const unsigned char* __restrict__ pol,
                                 const long long* __restrict__ ts, long long n, long long t0c, long long t1c, int C, int H, int W,
-                                float* __restrict__ out) {
+                                float* __restrict__ out, int* __restrict__ oob) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         // t_norm = (time - t0)/(t1 - t0)*(C-1) in fp32, as torch computes it for an int64 tensor divided by a Python int
         const float tn = (float)(ts[i] - t0c) / (float)(t1c - t0c) * (float)(C - 1);
@@ -22,6 +24,11 @@ __global__ void voxelize_kernel(const void* __restrict__ xs, const void* __restr
         const float value = 2.f * (float)pol[i] - 1.f;
         if (!FLOAT_XY) {
             const long long x = reinterpret_cast<const long long*>(xs)[i], y = reinterpret_cast<const long long*>(ys)[i];
+            // the reference's put_ raises on an index outside the grid; here the event is dropped and reported, never written
+            if (x < 0 || x >= W || y < 0 || y >= H) {
+                if (oob != nullptr) atomicAdd(oob, 1);
+                continue;
+            }
 #pragma unroll
             for (int dt = 0; dt < 2; ++dt) {
                 const int tl = tf + dt;
@@ -106,25 +113,75 @@ __global__ void epe_masked_kernel(const float* __restrict__ src, const float* __
     }
 }
 
+// one pass: EPE sum, valid count, angular-error sum (radians), N-pixel-error counts for up to 4 thresholds
+struct MetricThresholds {
+    float t[4];
+    int n;
+};
+__global__ void flow_metrics_kernel(const float* __restrict__ src, const float* __restrict__ tgt, const unsigned char* __restrict__ valid, int N,
+                                    int Cc, long long HW, float src_scale, MetricThresholds th, double* __restrict__ out) {
+    double s = 0.0, c = 0.0, ae = 0.0;
+    double npe[4] = {0.0, 0.0, 0.0, 0.0};
+    const long long total = (long long)N * HW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        if (valid != nullptr && valid[i] == 0) continue;
+        const long long n = i / HW, p = i - n * HW;
+        float e2 = 0.f, dot = 1.f, ns = 1.f, nt = 1.f, gt2 = 0.f;       // the "+1": homogeneous extension of both vectors (metrics.py:266-272)
+        for (int ch = 0; ch < Cc; ++ch) {
+            const float a = src_scale * src[((size_t)n * Cc + ch) * HW + p], b = tgt[((size_t)n * Cc + ch) * HW + p];
+            const float dlt = a - b;
+            e2 = fmaf(dlt, dlt, e2);
+            dot = fmaf(a, b, dot);
+            ns = fmaf(a, a, ns);
+            nt = fmaf(b, b, nt);
+            gt2 = fmaf(b, b, gt2);
+        }
+        const float e = sqrtf(e2);
+        s += (double)e;
+        c += 1.0;
+        const float cs = fminf(fmaxf(dot / (sqrtf(ns) * sqrtf(nt)), -1.f), 1.f);
+        ae += (double)acosf(cs);
+        const float rel = e / fmaxf(sqrtf(gt2), 1e-6f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < th.n && e > th.t[k] && rel >= 0.05f) npe[k] += 1.0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        ae += __shfl_xor_sync(0xffffffffu, ae, o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) npe[k] += __shfl_xor_sync(0xffffffffu, npe[k], o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, s);
+        atomicAdd(out + 1, c);
+        atomicAdd(out + 2, ae);
+        for (int k = 0; k < th.n; ++k) atomicAdd(out + 3 + k, npe[k]);
+    }
+}
+
 static inline unsigned grid_for(long long total) {
     long long g = (total + 255) / 256;
     if (g < 1) g = 1;
-    if (g > 148 * 16) g = 148 * 16;
+    const long long cap = (long long)bflow::num_sms() * 16;
+    if (g > cap) g = cap;
     return (unsigned)g;
 }
 
 }  // namespace bflow
 
 extern "C" int bflow_voxelize(const void* x, const void* y, int xy_is_float, const unsigned char* pol, const long long* time, long long n_events,
-                              long long t0_center, long long t1_center, int channels, int H, int W, float* out, void* stream) {
+                              long long t0_center, long long t1_center, int channels, int H, int W, float* out, int* oob_count, void* stream) {
     BFLOW_REQUIRE(out != nullptr && channels > 1 && H > 1 && W > 1, "voxelize: bad grid (representations.py:28-34)");
     BFLOW_REQUIRE(n_events >= 0 && (n_events == 0 || (x != nullptr && y != nullptr && pol != nullptr && time != nullptr)), "voxelize: null events");
     BFLOW_REQUIRE(t1_center > t0_center, "voxelize: t1_center must be greater than t0_center");
     if (n_events == 0) return BFLOW_OK;
     if (xy_is_float)
-        bflow::voxelize_kernel<true><<<bflow::grid_for(n_events), 256, 0, (cudaStream_t)stream>>>(x, y, pol, time, n_events, t0_center, t1_center, channels, H, W, out);
+        bflow::voxelize_kernel<true><<<bflow::grid_for(n_events), 256, 0, (cudaStream_t)stream>>>(x, y, pol, time, n_events, t0_center, t1_center, channels, H, W, out, oob_count);
     else
-        bflow::voxelize_kernel<false><<<bflow::grid_for(n_events), 256, 0, (cudaStream_t)stream>>>(x, y, pol, time, n_events, t0_center, t1_center, channels, H, W, out);
+        bflow::voxelize_kernel<false><<<bflow::grid_for(n_events), 256, 0, (cudaStream_t)stream>>>(x, y, pol, time, n_events, t0_center, t1_center, channels, H, W, out, oob_count);
     return bflow::check_launch("bflow_voxelize");
 }
 
@@ -142,4 +199,18 @@ extern "C" int bflow_epe_masked(const float* src, const float* tgt, const unsign
     BFLOW_REQUIRE(src != nullptr && tgt != nullptr && sum_count != nullptr && N > 0 && C > 0 && HW > 0, "epe_masked: bad arguments");
     bflow::epe_masked_kernel<<<bflow::grid_for((long long)N * HW), 256, 0, (cudaStream_t)stream>>>(src, tgt, valid, N, C, HW, sum_count);
     return bflow::check_launch("bflow_epe_masked");
+}
+
+extern "C" int bflow_flow_metrics(const float* src, const float* tgt, const unsigned char* valid, int N, int C, long long HW, float src_scale,
+                                  const float* thresholds_host, int n_thresholds, double* out8, void* stream) {
+    BFLOW_REQUIRE(src != nullptr && tgt != nullptr && out8 != nullptr && N > 0 && C > 0 && HW > 0, "flow_metrics: bad arguments");
+    BFLOW_REQUIRE(n_thresholds >= 0 && n_thresholds <= 4 && (n_thresholds == 0 || thresholds_host != nullptr), "flow_metrics: at most 4 N-pixel thresholds");
+    bflow::MetricThresholds th{};
+    th.n = n_thresholds;
+    for (int k = 0; k < n_thresholds; ++k) {
+        BFLOW_REQUIRE(thresholds_host[k] > 0.f, "flow_metrics: n_pixels must be positive (metrics.py:140)");
+        th.t[k] = thresholds_host[k];
+    }
+    bflow::flow_metrics_kernel<<<bflow::grid_for((long long)N * HW), 256, 0, (cudaStream_t)stream>>>(src, tgt, valid, N, C, HW, src_scale, th, out8);
+    return bflow::check_launch("bflow_flow_metrics");
 }

@@ -27,6 +27,20 @@ unsigned long long* timeline_next_slot(const char* name) {
     g_tl_names[g_tl_next][23] = 0;
     return g_tl_buf + 2 * (g_tl_next++);
 }
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    return dev;
+}
+int num_sms() {
+    static int sms[64] = {};
+    const int dev = current_device();
+    if (dev < 0 || dev >= 64) return 148;
+    if (sms[dev] == 0) {
+        if (cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms[dev] <= 0) sms[dev] = 148;
+    }
+    return sms[dev];
+}
 bool pdl_enabled() {
     static int on = -1;
     if (on < 0) {
@@ -37,7 +51,13 @@ bool pdl_enabled() {
 }
 }  // namespace bflow
 
-extern "C" int bflow_abi_version(void) { return 1; }
+#ifndef BFLOW_SOURCE_HASH
+#define BFLOW_SOURCE_HASH "unknown"
+#endif
+extern "C" int bflow_abi_version(void) { return BFLOW_ABI_VERSION; }
+extern "C" int bflow_sizeof_conv_desc(void) { return (int)sizeof(bflow_conv_desc); }
+extern "C" int bflow_sizeof_lookup_desc(void) { return (int)sizeof(bflow_lookup_desc); }
+extern "C" const char* bflow_source_hash(void) { return BFLOW_SOURCE_HASH; }
 extern "C" const char* bflow_last_error(void) { return bflow::g_err; }
 extern "C" int bflow_built_for_sm(void) { return 100; }
 

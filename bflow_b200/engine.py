@@ -19,8 +19,10 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
+from collections import OrderedDict
+
 from . import _lib, config as _cfg
-from ._lib import ACT, EPI, ConvDesc, LookupDesc, check
+from ._lib import ACT, EPI, PREC, ConvDesc, LookupDesc, check
 from .bezier import bernstein_coeffs
 from .ops import pack_conv_weight, pack_conv_weight_tc, make_lookup_desc, tiled_plane_size
 from .engine_s16 import S16Recorder
@@ -31,62 +33,70 @@ def _ceil(a: int, b: int) -> int:
 
 
 class _Weight:
-    __slots__ = ('w', 'ldw', 'b', 'cout', 'cin', 'kh', 'kw', 'stride', 'pad', 'oihw', 'cin_pad', 'tc')
+    """One convolution's parameters.  Everything is packed on the HOST (numpy-speed torch CPU ops) and uploaded with plain copies, so
+    that building an engine launches no PyTorch kernels: the first kernels a profiler sees in a forward are this library's."""
+    __slots__ = ('w', 'ldw', 'b', 'cout', 'cin', 'kh', 'kw', 'stride', 'pad', 'oihw', 'cin_pad', 'tc', 'dev')
 
-    def __init__(self, w, ldw, b, cout, cin, kh, kw, stride, pad, oihw, cin_pad):
+    def __init__(self, w, ldw, b, cout, cin, kh, kw, stride, pad, oihw, cin_pad, dev):
         self.w, self.ldw, self.b, self.cout, self.cin = w, ldw, b, cout, cin
         self.kh, self.kw, self.stride, self.pad = kh, kw, stride, pad
-        self.oihw, self.cin_pad = oihw, cin_pad
-        self.tc = {}                       # bn -> tensor-core weight image (packed on first use)
-
-    def tc_image(self, bn: int):
-        if bn not in self.tc:
-            self.tc[bn] = pack_conv_weight_tc(self.oihw, bn, self.cin_pad)
-        return self.tc[bn]
+        self.oihw, self.cin_pad, self.dev = oihw, cin_pad, dev      # oihw stays on the host
+        self.tc = {}                       # (bn, c0) -> tensor-core weight image on the device (packed on first use)
 
     def tc3_image(self, bn: int, c0: int):
         """Weight image of the TMA-fed kernel: K ordered (tap, 64-channel block), sources padded separately."""
         key = ('tc3', bn, c0)
         if key not in self.tc:
-            self.tc[key] = pack_conv_weight_tc(self.oihw, bn, self.cin_pad, block_per_tap=True, c0=c0)
+            img, acc_scale = pack_conv_weight_tc(self.oihw, bn, self.cin_pad, block_per_tap=True, c0=c0)
+            self.tc[key] = (img.to(self.dev), acc_scale)
         return self.tc[key]
 
 
 class Engine:
-    def __init__(self, model, device: torch.device):
+    def __init__(self, model, device: torch.device, precision: str = 'f32x3'):
         self.cfg = model.model_params
         self.device = device
         self.lib = _lib.lib()
+        assert precision in PREC, f'precision must be one of {sorted(PREC)}'
+        self.precision = precision
+        self.prec = PREC[precision]
         self.use_graph = os.environ.get('BFLOW_GRAPH', '1') != '0'
-        self.use_tc = os.environ.get('BFLOW_TC', '1') != '0'      # tcgen05 convolutions (0: fp32 CUDA-core kernels only)
-        # TMA-fed persistent tensor-core kernel on split-fp16 activations (0: register-staged tcgen05 kernel on fp32 activations)
-        self.use_tc3 = self.use_tc and os.environ.get('BFLOW_TC3', '1') != '0'
-        self.err = torch.zeros(1, device=device, dtype=torch.int32)
+        self.use_tc = os.environ.get('BFLOW_TC', '1') != '0'      # tcgen05 convolutions (0: exact-fp32 CUDA-core kernels, the numerical anchor)
+        assert self.use_tc or self.prec == 0, 'BFLOW_TC=0 is the exact-fp32 anchor: it has no reduced-precision form'
         self.use_side_stream = os.environ.get('BFLOW_STREAMS', '1') != '0'
-        self._plans: Dict[tuple, '_Plan'] = {}
-        self._pack(model)
+        self.max_plans = max(1, int(os.environ.get('BFLOW_MAX_PLANS', '4')))
+        with torch.cuda.device(device):
+            self.err = torch.zeros(1, device=device, dtype=torch.int32)
+            self._err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._err_event = None
+            self.h2d_stream = torch.cuda.Stream(device=device)
+            self.d2h_stream = torch.cuda.Stream(device=device)
+            self._plans: 'OrderedDict[tuple, List[_Plan]]' = OrderedDict()
+            self._turn: Dict[tuple, int] = {}
+            self._pack(model)
 
     # ------------------------------------------------------------------------------------------------
-    # weight preparation (once per state_dict)
+    # weight preparation (once per state_dict; host-side packing, one upload per tensor)
     # ------------------------------------------------------------------------------------------------
     def _mk(self, conv, w=None, b=None, cin_pad=None) -> _Weight:
         w = conv.weight if w is None else w
         b = conv.bias if b is None else b
-        w = w.detach().to(self.device, torch.float32)
-        b = b.detach().to(self.device, torch.float32).contiguous()
+        w = w.detach().to('cpu', torch.float32).contiguous()
+        b = b.detach().to('cpu', torch.float32).contiguous()
         O, I, KH, KW = w.shape
         wp, ldw = pack_conv_weight(w, cin_pad)
-        return _Weight(wp, ldw, b, O, I if cin_pad is None else cin_pad, KH, KW, conv.stride, conv.pad, w, cin_pad)
+        return _Weight(wp.to(self.device), ldw, b.to(self.device), O, I if cin_pad is None else cin_pad, KH, KW, conv.stride, conv.pad, w, cin_pad,
+                       self.device)
 
     def _mk_folded(self, conv, bn, rows: Optional[slice] = None) -> _Weight:
         """Conv followed by eval-mode BatchNorm (extractor.py:21-25) folded into weight and bias."""
-        w = conv.weight.detach().to(self.device, torch.float32)
-        b = conv.bias.detach().to(self.device, torch.float32)
+        w = conv.weight.detach().to('cpu', torch.float32)
+        b = conv.bias.detach().to('cpu', torch.float32)
         if bn is not None:
-            g = bn.weight.detach().to(self.device, torch.float32)
-            beta = bn.bias.detach().to(self.device, torch.float32)
-            rm = bn.running_mean.detach().to(self.device, torch.float32)
-            rv = bn.running_var.detach().to(self.device, torch.float32)
+            g = bn.weight.detach().to('cpu', torch.float32)
+            beta = bn.bias.detach().to('cpu', torch.float32)
+            rm = bn.running_mean.detach().to('cpu', torch.float32)
+            rv = bn.running_var.detach().to('cpu', torch.float32)
             s = g * torch.rsqrt(rv + bn.eps)
             w = w * s[:, None, None, None]
             b = (b - rm) * s + beta
@@ -102,10 +112,10 @@ class Engine:
         O, I, KH, KW = w1.oihw.shape
         if KH * KW * I <= 512:      # stem as a GEMM over the materialised patch matrix (engine_s16: 'im2col' stem)
             kp = 256 if KH * KW * I <= 256 else _ceil(KH * KW * I, 64)      # bflow_conv2d_stem7 wants exactly 4 k-blocks
-            wm = torch.zeros(O, kp, 1, 1, device=self.device, dtype=torch.float32)
+            wm = torch.zeros(O, kp, 1, 1, dtype=torch.float32)
             wm[:, :KH * KW * I, 0, 0] = w1.oihw.permute(0, 2, 3, 1).reshape(O, -1)
             wp, ldw = pack_conv_weight(wm)
-            out['conv1_mat'] = _Weight(wp, ldw, w1.b, O, kp, 1, 1, 1, (0, 0), wm, None)
+            out['conv1_mat'] = _Weight(wp.to(self.device), ldw, w1.b, O, kp, 1, 1, 1, (0, 0), wm, None, self.device)
         for layer in (enc.layer1, enc.layer2, enc.layer3):
             for blk in layer:
                 e = {'conv1': f(blk.conv1, blk.norm1 if bn else None), 'conv2': f(blk.conv2, blk.norm2 if bn else None), 'down': None}
@@ -148,12 +158,14 @@ class Engine:
             # slice is the same in every iteration, so its contribution (+ bias) is computed once per forward ("*_inp") and the
             # per-iteration convs only see [h | motion] ("*_dyn").
             z, r, q = getattr(g, 'convz' + sfx), getattr(g, 'convr' + sfx), getattr(g, 'convq' + sfx)
-            wzr, bzr = torch.cat([z.weight, r.weight], 0), torch.cat([z.bias, r.bias], 0)
+            cpu = lambda t: t.detach().to('cpu', torch.float32)
+            wzr, bzr = torch.cat([cpu(z.weight), cpu(r.weight)], 0), torch.cat([cpu(z.bias), cpu(r.bias)], 0)
+            wq = cpu(q.weight)
             dyn = lambda w: torch.cat([w[:, :hd], w[:, hd + cd:]], 1).contiguous()
             U['zr' + sfx + '_inp'] = self._mk(z, wzr[:, hd:hd + cd].contiguous(), bzr)
             U['zr' + sfx + '_dyn'] = self._mk(z, dyn(wzr), bzr)
-            U['q' + sfx + '_inp'] = self._mk(q, q.weight[:, hd:hd + cd].contiguous(), q.bias)
-            U['q' + sfx + '_dyn'] = self._mk(q, dyn(q.weight), q.bias)
+            U['q' + sfx + '_inp'] = self._mk(q, wq[:, hd:hd + cd].contiguous(), q.bias)
+            U['q' + sfx + '_dyn'] = self._mk(q, dyn(wq), q.bias)
         U['head1'], U['head2'] = self._mk(ub.bezier_head.conv1), self._mk(ub.bezier_head.conv2)
         U['mask0'], U['mask2'] = self._mk(ub.mask[0]), self._mk(ub.mask[2])
         self.upd = U
@@ -161,23 +173,60 @@ class Engine:
         self.coef = bernstein_coeffs(ts, self.deg).astype('float32')      # (T, deg), float64 → fp32 like bezier.py:180
 
     # ------------------------------------------------------------------------------------------------
-    def run(self, voxel, images, iters: int, init, test_mode: bool):
+    # execution
+    # ------------------------------------------------------------------------------------------------
+    def _lanes(self, key) -> List['_Plan']:
+        """Plans of one (B, H, W, iters, test_mode): lane 0 always, lane 1 once a pipelined (non_blocking) call needs a second set of
+        input / workspace / output buffers.  Least-recently-used keys are dropped beyond BFLOW_MAX_PLANS (a D-shape plan holds ~1 GB)."""
+        lanes = self._plans.get(key)
+        if lanes is None:
+            while len(self._plans) >= self.max_plans:
+                self._plans.popitem(last=False)
+            lanes = [_Plan(self, *key)]
+            self._plans[key] = lanes
+        else:
+            self._plans.move_to_end(key)
+        return lanes
+
+    def plan(self, B, H, W, iters, test_mode) -> '_Plan':
+        with torch.cuda.device(self.device):
+            return self._lanes((B, H, W, iters, bool(test_mode)))[0]
+
+    def _poll_err(self):
+        """Raises if a tensor-core pipeline wait timed out in an EARLIER forward (the word travels with every forward's outputs; no sync)."""
+        if self._err_event is not None and self._err_event.query() and int(self._err_host[0]) != 0:
+            raise RuntimeError('bflow_b200: a tcgen05 pipeline wait timed out inside a kernel (the result of that forward is invalid)')
+
+    def run(self, voxel, images, iters: int, init, test_mode: bool, non_blocking: bool = False):
+        """One forward.  Blocking form (default, the reference's semantics): inputs are CUDA tensors, the launch list runs on the current
+        stream and the outputs are fresh device tensors.  Pipelined form (non_blocking=True): inputs may be pinned host tensors; the
+        H2D copy, the graph and the D2H copy of the results run on three streams over two alternating buffer sets, so that the copies of
+        frames i+1 and i-1 overlap the graph of frame i.  Returns (low, ups, event): pinned host tensors that are valid once `event`
+        has completed and until the second-next pipelined call reuses the lane."""
         ref = voxel if voxel is not None else images[0]
         B, _, H, W = ref.shape
         key = (B, H, W, iters, bool(test_mode))
-        plan = self._plans.get(key)
-        if plan is None:
-            plan = _Plan(self, B, H, W, iters, test_mode)
-            self._plans[key] = plan
-        plan.load_inputs(voxel, images, init)
-        plan.execute()
-        return plan.low.clone(), [u.clone() for u in plan.ups]
+        with torch.cuda.device(self.device):
+            self._poll_err()
+            lanes = self._lanes(key)
+            if not non_blocking:
+                plan = lanes[0]
+                plan.wait_idle()
+                plan.load_inputs(voxel, images, init)
+                plan.execute()
+                self._err_host_copy(torch.cuda.current_stream(self.device))
+                return plan.low.clone(), [u.clone() for u in plan.ups]
+            if len(lanes) < 2:
+                lanes.append(_Plan(self, *key))
+            turn = self._turn.get(key, 0)
+            self._turn[key] = turn + 1
+            return lanes[turn % 2].run_pipelined(voxel, images, init)
 
-    def plan(self, B, H, W, iters, test_mode) -> '_Plan':
-        key = (B, H, W, iters, bool(test_mode))
-        if key not in self._plans:
-            self._plans[key] = _Plan(self, B, H, W, iters, test_mode)
-        return self._plans[key]
+    def _err_host_copy(self, stream):
+        self._err_host.copy_(self.err, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        self._err_event = ev
 
 
 class _Plan(S16Recorder):
@@ -210,7 +259,10 @@ class _Plan(S16Recorder):
         self.low = torch.empty(B, 2 * eng.deg, self.h, self.w, **f32)
         n_up = 1 if test_mode else iters
         self.ups = [torch.empty(B, 2 * eng.deg, H, W, **f32) for _ in range(n_up)]
-        if eng.use_tc3:
+        # pipelined execution (Engine.run(non_blocking=True)): pinned result buffers and the events that order the three streams
+        self.low_host = self.ups_host = None
+        self.ev_done = self.ev_out = None
+        if eng.use_tc:
             self._record_s16()
         else:
             self._record()
@@ -254,13 +306,6 @@ class _Plan(S16Recorder):
         flops = 2.0 * N * Ho * Wo * wt.cout * wt.kh * wt.kw * (c0 + c1)
         if kernel == 'small_n':
             self._add(lib.bflow_conv2d_small_n, C.byref(d), label=f'conv_small_n {c0 + c1}->{wt.cout} {wt.kh}x{wt.kw}/{wt.stride} M={N * Ho * Wo}', flops=flops)
-        elif self.eng.use_tc and lib.bflow_conv2d_tc_supported(C.byref(d)) == 1:
-            mtiles = (N * Ho * Wo + 127) // 128
-            bn = 64 if (wt.cout <= 64 or mtiles * ((wt.cout + 127) // 128) < 148) else 128
-            img, acc_scale = wt.tc_image(bn)
-            self._add(lib.bflow_conv2d_nhwc_tc, C.byref(d), img.data_ptr(), bn, acc_scale, self.eng.err.data_ptr(),
-                      label=f'conv_tc{bn} {c0 + c1}->{wt.cout} {wt.kh}x{wt.kw}/{wt.stride} M={N * Ho * Wo}', flops=flops)
-            self.n_tc += 1
         else:
             self._add(lib.bflow_conv2d_nhwc, C.byref(d), label=f'conv_simt {c0 + c1}->{wt.cout} {wt.kh}x{wt.kw}/{wt.stride} M={N * Ho * Wo}', flops=flops)
         return Ho, Wo
@@ -331,6 +376,8 @@ class _Plan(S16Recorder):
 
     # ---- the whole forward ----------------------------------------------------------------------------------
     def _record(self):
+        """BFLOW_TC=0: every convolution on the exact-fp32 CUDA-core kernels over fp32 NHWC activations, the volume in the reference's
+        row-major layout -- the numerical anchor the tensor-core path (engine_s16._record_s16) is checked against."""
         eng, L = self.eng, self.eng.lib
         cfg, dev = eng.cfg, eng.device
         B, H, W, h, w, Q, R = self.B, self.H, self.W, self.h, self.w, self.Q, self.R
@@ -403,54 +450,35 @@ class _Plan(S16Recorder):
         # ---- initial Bezier parameters: zeros (+ flow_init) (raft.py:150-153) ----
         self._add(L.bflow_nchw_to_nhwc, self.init_in.data_ptr(), hx + poff * 4, B, 2 * deg, h, w, 0, 2 * deg, gw, 1.0, 0.0)
 
-        # ---- correlation volume + pyramid (corr.py:264-272, 293-305) ----
-        tiled = eng.use_tc and fd % 8 == 0
-        self.tiled = tiled
-        if tiled:
-            # tensor-core GEMM; the target feature map is packed once into the B-operand image (hi/lo fp16, swizzled) with its
-            # pixels in 4x4-tiled order, so the GEMM's row-major output IS the granule-tiled plane layout the lookup reads.
-            bn = 128
-            Np0 = tiled_plane_size(h, w)
-            self.vol0 = torch.empty(T, R, Np0, **f32)
-            img_bytes = ((Np0 + bn - 1) // bn) * ((fd + 63) // 64) * 2 * bn * 128
-            self.f2img = torch.zeros(T, B, img_bytes, device=dev, dtype=torch.uint8)
-            srcs = [(fm_ev, (t + 1) * B, fm_ev) for t in range(T_ev)] + ([(fm_img, B, fm_img)] if self.use_img else [])
-            for t, (fm2, n0, fm1) in enumerate(srcs):
-                for b in range(B):
-                    self._add(L.bflow_pack_b_tc, fm2.data_ptr() + (n0 + b) * Q * fd * 4, fd, self.f2img[t, b].data_ptr(), Q, fd, bn, h, w)
-                self._add(L.bflow_corr_volume_tc, fm1.data_ptr(), fd, self.f2img[t].data_ptr(), img_bytes, self.vol0[t].data_ptr(), B, fd, Q, Np0, bn,
-                          eng.err.data_ptr(), label=f'corr_volume_tc Q={Q} D={fd}', flops=2.0 * B * Q * Q * fd)
-        else:
-            self.vol0 = torch.empty(T, R, h, w, **f32)
-            if self.use_ev:
-                self.f2_ev = torch.empty(T_ev * B, fd, Q, **f32)
-                self._add(L.bflow_nhwc_to_nchw, fm_ev.data_ptr() + B * Q * fd * 4, self.f2_ev.data_ptr(), T_ev * B, fd, h, w, fd)
-                for t in range(T_ev):
-                    self._add(L.bflow_corr_volume, fm_ev.data_ptr(), fd, self.f2_ev.data_ptr() + t * B * fd * Q * 4, self.vol0[t].data_ptr(), B, fd, Q)
-            if self.use_img:
-                self.f2_img = torch.empty(B, fd, Q, **f32)
-                self._add(L.bflow_nhwc_to_nchw, fm_img.data_ptr() + B * Q * fd * 4, self.f2_img.data_ptr(), B, fd, h, w, fd)
-                self._add(L.bflow_corr_volume, fm_img.data_ptr(), fd, self.f2_img.data_ptr(), self.vol0[T_ev].data_ptr(), B, fd, Q)
+        # ---- correlation volume + pyramid (corr.py:264-272, 293-305): reference layout, one private row-major plane per query ----
+        self.tiled = False
+        self.vol0 = torch.empty(T, R, h, w, **f32)
+        if self.use_ev:
+            self.f2_ev = torch.empty(T_ev * B, fd, Q, **f32)
+            self._add(L.bflow_nhwc_to_nchw, fm_ev.data_ptr() + B * Q * fd * 4, self.f2_ev.data_ptr(), T_ev * B, fd, h, w, fd)
+            for t in range(T_ev):
+                self._add(L.bflow_corr_volume, fm_ev.data_ptr(), fd, self.f2_ev.data_ptr() + t * B * fd * Q * 4, self.vol0[t].data_ptr(), B, fd, Q)
+        if self.use_img:
+            self.f2_img = torch.empty(B, fd, Q, **f32)
+            self._add(L.bflow_nhwc_to_nchw, fm_img.data_ptr() + B * Q * fd * 4, self.f2_img.data_ptr(), B, fd, h, w, fd)
+            self._add(L.bflow_corr_volume, fm_img.data_ptr(), fd, self.f2_img.data_ptr(), self.vol0[T_ev].data_ptr(), B, fd, Q)
         # pyramid: level l holds the targets with more than l levels; (indices, tensor, hl, wl)
         pyr = [(list(range(T)), self.vol0, h, w)]
         for lvl in range(1, max(eng.levels)):
             prev_idx, prev, hp_, wp_ = pyr[-1]
             keep = [t for t in range(T) if eng.levels[t] > lvl]
             hl, wl = hp_ // 2, wp_ // 2
-            cur = torch.empty(len(keep), R, tiled_plane_size(hl, wl), **f32) if tiled else torch.empty(len(keep), R, hl, wl, **f32)
+            cur = torch.empty(len(keep), R, hl, wl, **f32)
             for j, t in enumerate(keep):
                 src = prev[prev_idx.index(t)]
-                self._add(L.bflow_corr_pool_tiled if tiled else L.bflow_corr_pool, src.data_ptr(), cur[j].data_ptr(), R, hp_, wp_)
+                self._add(L.bflow_corr_pool, src.data_ptr(), cur[j].data_ptr(), R, hp_, wp_)
             pyr.append((keep, cur, hl, wl))
         self.pyr = pyr
 
         # ---- lookup descriptor (corr.py:307-350); centres come from the Bezier params in hx ----
-        if tiled:
-            slots = [(lvl, t, pyr[lvl][1][pyr[lvl][0].index(t)], pyr[lvl][2], pyr[lvl][3]) for (lvl, t) in eng.slots]
-        else:
-            slots = [(lvl, t, pyr[lvl][1][pyr[lvl][0].index(t)]) for (lvl, t) in eng.slots]
+        slots = [(lvl, t, pyr[lvl][1][pyr[lvl][0].index(t)]) for (lvl, t) in eng.slots]
         self.corr = torch.zeros(R, eng.ldc, **f32)
-        ld = make_lookup_desc(slots, T, B, h, w, tiled)
+        ld = make_lookup_desc(slots, T, B, h, w, False)
         ld.coords = None
         ld.params, ld.params_ld, ld.degree = hx + poff * 4, gw, deg
         for t in range(T):
@@ -517,24 +545,27 @@ class _Plan(S16Recorder):
         self.n_launches = len(self.launches)
 
     # ---- execution -----------------------------------------------------------------------------------------
-    def load_inputs(self, voxel, images, init):
-        if self.use_ev:
-            assert voxel.shape == self.voxel_in.shape, (voxel.shape, self.voxel_in.shape)
-            self.voxel_in.copy_(voxel, non_blocking=True)
-        if self.use_img:
-            for dst, src in zip(self.img_in, images):
-                assert src.shape == dst.shape
-                dst.copy_(src, non_blocking=True)
-        if init is not None:
-            assert init.shape == self.init_in.shape
-            self.init_in.copy_(init, non_blocking=True)
-            self._init_dirty = True
-        elif getattr(self, '_init_dirty', False):
-            self.init_in.zero_()
-            self._init_dirty = False
+    def load_inputs(self, voxel, images, init, stream=None):
+        """Copies the call's inputs into the plan's static buffers (on `stream`, default: the current stream of the engine's device)."""
+        ctx = torch.cuda.stream(stream) if stream is not None else _NullCtx()
+        with ctx:
+            if self.use_ev:
+                assert voxel.shape == self.voxel_in.shape, (voxel.shape, self.voxel_in.shape)
+                self.voxel_in.copy_(voxel, non_blocking=True)
+            if self.use_img:
+                for dst, src in zip(self.img_in, images):
+                    assert src.shape == dst.shape
+                    dst.copy_(src, non_blocking=True)
+            if init is not None:
+                assert init.shape == self.init_in.shape
+                self.init_in.copy_(init, non_blocking=True)
+                self._init_dirty = True
+            elif getattr(self, '_init_dirty', False):
+                self.init_in.zero_()
+                self._init_dirty = False
 
     def launch_all(self):
-        main = torch.cuda.current_stream()
+        main = torch.cuda.current_stream(self.eng.device)
         if self.side_stream is None:
             self.side_stream = torch.cuda.Stream(device=self.eng.device)
         side = self.side_stream
@@ -553,20 +584,70 @@ class _Plan(S16Recorder):
                     main.wait_stream(side)
 
     def check(self):
-        """Synchronises and raises if a tensor-core pipeline wait timed out (never expected)."""
+        """Synchronises and raises if a tensor-core pipeline wait timed out (never expected; such a kernel also traps)."""
         if int(self.eng.err.item()) != 0:
             raise RuntimeError('bflow_b200: a tcgen05 pipeline wait timed out inside a kernel')
 
     def execute(self):
-        if not self.eng.use_graph:
-            self.launch_all()
-            return
-        if self.graph is None:
-            self.launch_all()                         # eager warm-up (also surfaces contract errors outside capture)
-            torch.cuda.current_stream().synchronize()
-            self.check()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+        with torch.cuda.device(self.eng.device):
+            if not self.eng.use_graph:
                 self.launch_all()
-            self.graph = g
-        self.graph.replay()
+                return
+            if self.graph is None:
+                self.launch_all()                         # eager warm-up (also surfaces contract errors outside capture)
+                torch.cuda.current_stream().synchronize()
+                self.check()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.launch_all()
+                self.graph = g
+            self.graph.replay()
+
+    def wait_idle(self):
+        """Blocking calls reuse lane 0: wait (on the current stream) for pipelined work that may still be using its buffers."""
+        cur = torch.cuda.current_stream(self.eng.device)
+        if self.ev_out is not None:
+            cur.wait_event(self.ev_out)
+
+    def run_pipelined(self, voxel, images, init):
+        """H2D on the engine's h2d stream, the graph on the current stream, D2H on the d2h stream; see Engine.run."""
+        eng = self.eng
+        cur = torch.cuda.current_stream(eng.device)
+        for t in ([voxel] if voxel is not None else []) + list(images or []):
+            assert t.is_cuda or t.is_pinned(), 'pipelined forward: host inputs must be pinned (tensor.pin_memory())'
+        if self.low_host is None:
+            self.low_host = torch.empty(self.low.shape, dtype=torch.float32).pin_memory()
+            self.ups_host = [torch.empty(u.shape, dtype=torch.float32).pin_memory() for u in self.ups]
+        # 1. inputs: the previous graph of this lane must have finished reading them
+        if self.ev_done is not None:
+            eng.h2d_stream.wait_event(self.ev_done)
+        else:
+            eng.h2d_stream.wait_stream(cur)
+        self.load_inputs(voxel, images, init, stream=eng.h2d_stream)
+        ev_in = torch.cuda.Event()
+        ev_in.record(eng.h2d_stream)
+        # 2. compute: inputs have landed, and the previous results of this lane have left the output buffers
+        cur.wait_event(ev_in)
+        if self.ev_out is not None:
+            cur.wait_event(self.ev_out)
+        self.execute()
+        self.ev_done = torch.cuda.Event()
+        self.ev_done.record(cur)
+        # 3. results (+ the error word) to pinned host memory
+        eng.d2h_stream.wait_event(self.ev_done)
+        with torch.cuda.stream(eng.d2h_stream):
+            self.low_host.copy_(self.low, non_blocking=True)
+            for dst, src in zip(self.ups_host, self.ups):
+                dst.copy_(src, non_blocking=True)
+            eng._err_host_copy(eng.d2h_stream)
+        self.ev_out = torch.cuda.Event()
+        self.ev_out.record(eng.d2h_stream)
+        return self.low_host, self.ups_host, self.ev_out
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

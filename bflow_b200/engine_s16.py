@@ -75,6 +75,7 @@ class S16Recorder:
         c1 = srcs[1][2] if len(srcs) > 1 else 0
         assert c0 + c1 == wt.cin, (c0, c1, wt.cin)
         d = ConvDesc()
+        d.precision = self.eng.prec
         d.x0, d.c0, d.ld0 = None, c0, srcs[0][0].ld
         d.x1, d.c1, d.ld1 = None, c1, (srcs[1][0].ld if c1 else 0)
         d.w, d.ldw, d.bias = None, 0, (wt.b.data_ptr() if bias else None)
@@ -95,7 +96,6 @@ class S16Recorder:
             d.aux1_16_hi, d.aux1_16_lo, d.ld_aux1_16 = aux1_16[0].hi(aux1_16[1]), aux1_16[0].lo(aux1_16[1]), aux1_16[0].ld
         self.keep.append(d)
         M = N * Ho * Wo
-        import os
         if (wt.kh == 3 and wt.kw == 3 and wt.stride == 1 and (ph, pw) == (1, 1) and c0 == 64 and c1 == 0 and wt.cout == 64 and W % 8 == 0 and
                 epi == 'std' and res is None and act1 in ('none', 'relu') and act2 in ('none', 'relu') and M >= 148 * 128 and
                 os.environ.get('BFLOW_SLAB', '1') != '0'):
@@ -113,7 +113,8 @@ class S16Recorder:
         bn = choose_bn(wt.cout, (M + 127) // 128)
         img, acc_scale = wt.tc3_image(bn, c0)
         orient = {(3, 3): 1, (5, 1): 1, (1, 5): 2}.get((wt.kh, wt.kw), 0)
-        if (orient and wt.stride == 1 and (ph, pw) == (wt.kh // 2, wt.kw // 2) and bn <= 128 and os.environ.get('BFLOW_TC3_SLAB', '0') == '1'):
+        if (orient and wt.stride == 1 and (ph, pw) == (wt.kh // 2, wt.kw // 2) and bn <= 128 and self.eng.prec == 0 and
+                os.environ.get('BFLOW_TC3_SLAB', '0') == '1'):
             # halo slabs instead of im2col rows: A traffic / 2.7 (3x3) ... / 4 (1x5, 5x1).  Opt-in: measured on B200 it buys nothing here -- the
             # main loops of these layers are bound by the tensor pipe (bn 128) or by MMA issue (bn 64), not by L2 -> SM traffic
             taps = wt.kh if orient == 1 else wt.kw
@@ -194,7 +195,6 @@ class S16Recorder:
         from .engine import _ceil
         L, dev = self.eng.lib, self.eng.device
         shared = {} if shared is None else shared
-        import os
         if 49 * cin <= 256 and W % 4 == 0 and os.environ.get('BFLOW_STEM7', '1') != '0':
             # fused stem: input footprint -> patch matrix in shared memory -> tcgen05 (bflow_conv2d_stem7)
             return dict(kind='stem7', src=src_nchw.data_ptr(), C_total=C_total, c_off=c_off, cin=cin, ns=ns, scale=scale, shift=shift)
@@ -234,6 +234,9 @@ class S16Recorder:
         def s16(ptr, rows, c):
             return _S16(rows, c, dev, base=ptr)
 
+        f16 = self.eng.prec == 1
+        lo = (lambda t: None) if f16 else (lambda t: t.lo())       # BFLOW_PREC_F16: lo planes are neither written nor read
+
         H2, W2 = H // 2, W // 2
         rows = Np * H2 * W2
         w1 = E['conv1']
@@ -262,6 +265,7 @@ class S16Recorder:
                 wm = E['conv1_mat']
                 img, acc_scale = wm.tc3_image(64, wm.cin)
                 d = ConvDesc()
+                d.precision = self.eng.prec
                 d.x0, d.c0, d.c1, d.bias = win['src'], win['cin'], 0, wm.b.data_ptr()
                 d.y, d.ldy = y, 64
                 d.N, d.H, d.W, d.Ho, d.Wo, d.Cout = ns, H, W, H2, W2, 64
@@ -298,7 +302,7 @@ class S16Recorder:
             X = s16(xptr, rows, 64)
             if not fused:
                 self._add(L.bflow_plane_sums, raw, 64, sm, Np, H2 * W2, 64)
-            self._add(L.bflow_instnorm_relu16, raw, 64, sm, None, 0, None, None, None, 0, None, 0, X.hi(), X.lo(), 64, Np, H2 * W2, 64, 1e-5)
+            self._add(L.bflow_instnorm_relu16, raw, 64, sm, None, 0, None, None, None, 0, None, 0, X.hi(), lo(X), 64, Np, H2 * W2, 64, 1e-5)
             free.append(raw)
         else:
             xptr = free.pop()
@@ -320,7 +324,7 @@ class S16Recorder:
                 self._conv3(c1, [(X, 0, Cc)], Np, Hc, Wc, y=raw1, ldy=Co, stats=sm)
                 y1p = free.pop()
                 Y1 = s16(y1p, rout, Co)
-                self._add(L.bflow_instnorm_relu16, raw1, Co, sm, None, 0, None, None, None, 0, None, 0, Y1.hi(), Y1.lo(), Co, Np, Ho * Wo, Co, 1e-5)
+                self._add(L.bflow_instnorm_relu16, raw1, Co, sm, None, 0, None, None, None, 0, None, 0, Y1.hi(), lo(Y1), Co, Np, Ho * Wo, Co, 1e-5)
                 raw2 = raw1                                     # raw1 is dead: reuse it for conv2's output
                 sm2 = self._sums(Np, Co)
                 self._conv3(c2, [(Y1, 0, Co)], Np, Ho, Wo, y=raw2, ldy=Co, stats=sm2)
@@ -330,10 +334,10 @@ class S16Recorder:
                     rawd = free.pop()
                     smd = self._sums(Np, Co)
                     self._conv3(dn, [(X, 0, Cc)], Np, Hc, Wc, y=rawd, ldy=Co, stats=smd)
-                    self._add(L.bflow_instnorm_relu16, raw2, Co, sm2, rawd, Co, smd, None, None, 0, None, 0, OUT.hi(), OUT.lo(), Co, Np, Ho * Wo, Co, 1e-5)
+                    self._add(L.bflow_instnorm_relu16, raw2, Co, sm2, rawd, Co, smd, None, None, 0, None, 0, OUT.hi(), lo(OUT), Co, Np, Ho * Wo, Co, 1e-5)
                     free.append(rawd)
                 else:
-                    self._add(L.bflow_instnorm_relu16, raw2, Co, sm2, None, 0, None, X.hi(), X.lo(), Cc, None, 0, OUT.hi(), OUT.lo(), Co, Np, Ho * Wo, Co, 1e-5)
+                    self._add(L.bflow_instnorm_relu16, raw2, Co, sm2, None, 0, None, X.hi(), lo(X), Cc, None, 0, OUT.hi(), lo(OUT), Co, Np, Ho * Wo, Co, 1e-5)
                 free.append(raw2)
                 free.append(xptr)
                 X, xptr = OUT, outp
@@ -451,6 +455,7 @@ class S16Recorder:
                 # corr[bq, n] = <f1[bq, :], f2[n, :]> / sqrt(D): a 1x1 "convolution" over the Q query pixels of sample b whose weight
                 # image is the packed target feature map
                 d = ConvDesc()
+                d.precision = self.eng.prec
                 d.c0, d.ld0 = fd, fd
                 d.y, d.ldy = self.vol0[t].data_ptr() + b * Q * Np0 * 4, Np0
                 d.N, d.H, d.W, d.Ho, d.Wo, d.Cout = 1, 1, Q, 1, Q, Np0
@@ -485,7 +490,7 @@ class S16Recorder:
             for k in range(deg):
                 ld.coef[t][k] = float(eng.coef[t, k])
         ld.out, ld.out_nhwc, ld.out_ld = None, 1, eng.ldc
-        ld.out16_hi, ld.out16_lo, ld.out16_ld = self.corr16.hi(), self.corr16.lo(), eng.ldc
+        ld.out16_hi, ld.out16_lo, ld.out16_ld = self.corr16.hi(), (None if eng.prec == 1 else self.corr16.lo()), eng.ldc
         self.keep.append(ld)
         self.lookup_desc = ld
 

@@ -1,6 +1,7 @@
 """Tensor-level wrappers over the C ABI: argument checks (dtype/device/contiguity → AssertionError, the
-reference's error convention), output allocation, current-stream plumbing.  Used by the public mirrors
-(:mod:`bflow_b200.corr`, :class:`BezierCurves`) and by the parity tests; the engine calls the ABI directly.
+reference's error convention), output allocation, current-stream plumbing.  These are the reference-level
+operator mirrors (NCHW layouts of models/raft_utils/corr.py, utils.py and bezier.py) used by :class:`BezierCurves`
+and by the parity tests; the engine calls the ABI directly.
 """
 from __future__ import annotations
 
@@ -19,6 +20,31 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_tensor_device(fn):
+    """Runs the wrapped operator with the device of its first CUDA tensor argument current: allocations, the stream handle and the
+    `<<<>>>` launches inside the library all follow the CURRENT device, which need not be the tensors' device."""
+    import functools
+
+    def first_cuda(objs):
+        for o in objs:
+            if isinstance(o, torch.Tensor) and o.is_cuda:
+                return o
+            if isinstance(o, (list, tuple)):
+                t = first_cuda(o)
+                if t is not None:
+                    return t
+        return None
+
+    @functools.wraps(fn)
+    def wrapper(*a, **k):
+        t = first_cuda(list(a) + list(k.values()))
+        if t is None:
+            return fn(*a, **k)
+        with torch.cuda.device(t.device):
+            return fn(*a, **k)
+    return wrapper
+
+
 def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     assert isinstance(t, torch.Tensor), f'{name}: tensor expected'
     assert t.is_cuda, f'{name}: CUDA tensor expected (bflow_b200 has no CPU path)'
@@ -27,6 +53,7 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 # ---- layout ------------------------------------------------------------------------------------------
+@_on_tensor_device
 def nchw_to_nhwc(x: torch.Tensor, c_off: int = 0, c_cnt: Optional[int] = None, out: Optional[torch.Tensor] = None,
                  out_ld: Optional[int] = None, scale: float = 1.0, shift: float = 0.0) -> torch.Tensor:
     x = _f32c(x, 'x')
@@ -40,6 +67,7 @@ def nchw_to_nhwc(x: torch.Tensor, c_off: int = 0, c_cnt: Optional[int] = None, o
     return out
 
 
+@_on_tensor_device
 def nhwc_to_nchw(x: torch.Tensor, C_: Optional[int] = None) -> torch.Tensor:
     x = _f32c(x, 'x')
     N, H, W, ld = x.shape
@@ -62,7 +90,7 @@ def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None) -> Tuple[to
 
 def pack_conv_weight_tc(w: torch.Tensor, bn: int, cin_pad: Optional[int] = None, prescale: bool = True,
                         block_per_tap: bool = False, c0: Optional[int] = None) -> Tuple[torch.Tensor, float]:
-    """OIHW fp32 → (tensor-core weight image of bflow_conv2d_nhwc_tc, acc_scale).
+    """OIHW fp32 → (tensor-core weight image of bflow_conv2d_nhwc_tc3, acc_scale).
     Image: [ceil(O/bn)][ceil(K/64)][hi | lo (fp16)][bn][64] with K = (kh*KW+kw)*Cin + c flattened and the 16-byte
     chunks of every 128-byte row XOR-swizzled by (row % 8) — byte for byte the SWIZZLE_128B shared-memory tile.
     The weights are multiplied by 2^k (largest magnitude in [0.5, 1)) so that the fp16 residuals stay normal;
@@ -108,6 +136,7 @@ def pack_conv_weight_tc(w: torch.Tensor, bn: int, cin_pad: Optional[int] = None,
     return img.view(-1), 2.0 ** (-k)
 
 
+@_on_tensor_device
 def split_f16(x_nhwc: torch.Tensor, ld16: Optional[int] = None) -> torch.Tensor:
     """(..., C) fp32 rows → (2, rows, ld16) fp16 planes [hi, lo] with x = hi + lo."""
     x = _f32c(x_nhwc, 'x')
@@ -130,6 +159,7 @@ def tma_im2col_maps(planes: torch.Tensor, N: int, H: int, W: int, Cc: int, KH: i
     return buf
 
 
+@_on_tensor_device
 def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, stride: int = 1,
            padding=(0, 0), act: str = 'none', scale: float = 1.0, backend: str = 'simt', bn: int = 128) -> torch.Tensor:
     """NCHW in / NCHW out convenience form of bflow_conv2d_nhwc (used by tests and the operator mirror)."""
@@ -153,6 +183,7 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     d.N, d.H, d.W, d.Ho, d.Wo, d.Cout = N, H, W, Ho, Wo, O
     d.KH, d.KW, d.stride, d.pad_h, d.pad_w = KH, KW, stride, ph, pw
     d.act1, d.act2, d.scale = ACT[act], 0, scale
+    d.precision = _lib.PREC[getattr(conv2d, 'precision', 'f32x3')]
     if backend == 'tc3s':
         orient = {(3, 3): 1, (5, 1): 1, (1, 5): 2}[(KH, KW)]
         ld16 = (Cin + 7) // 8 * 8
@@ -217,17 +248,12 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         check(L.bflow_conv2d_slab64(C.byref(d), C.addressof(maps), wtc.data_ptr(), acc_scale, err.data_ptr(), _stream()), 'conv2d_slab64')
         if int(err.item()) != 0:
             raise RuntimeError('bflow_conv2d_slab64: pipeline wait timed out inside the kernel')
-    elif backend == 'tc':
-        wtc, acc_scale = pack_conv_weight_tc(weight, bn)
-        err = torch.zeros(1, device=x.device, dtype=torch.int32)
-        check(_lib.lib().bflow_conv2d_nhwc_tc(C.byref(d), wtc.data_ptr(), bn, acc_scale, err.data_ptr(), _stream()), 'conv2d_tc')
-        if int(err.item()) != 0:
-            raise RuntimeError('bflow_conv2d_nhwc_tc: pipeline wait timed out inside the kernel')
     else:
         check(_lib.lib().bflow_conv2d_nhwc(C.byref(d), _stream()), 'conv2d')
     return nhwc_to_nchw(y)
 
 
+@_on_tensor_device
 def instance_norm_relu(x: torch.Tensor, residual: Optional[torch.Tensor] = None, residual_norm: bool = False,
                        eps: float = 1e-5) -> torch.Tensor:
     """NCHW convenience form: relu(IN(x)) or relu(relu(IN(x)) + R)."""
@@ -250,6 +276,7 @@ def instance_norm_relu(x: torch.Tensor, residual: Optional[torch.Tensor] = None,
 
 
 # ---- correlation -------------------------------------------------------------------------------------------
+@_on_tensor_device
 def corr_volume(fmap1: torch.Tensor, fmap2: torch.Tensor) -> torch.Tensor:
     """fmap1 (B,D,h,w) or (T,B,D,h,w); fmap2 (T,B,D,h,w), reference layout → (T, B*h*w, 1, h, w)
     (models/raft_utils/corr.py:264-272)."""
@@ -266,6 +293,7 @@ def corr_volume(fmap1: torch.Tensor, fmap2: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def corr_pool(vol: torch.Tensor) -> torch.Tensor:
     """(..., H, W) → (..., H//2, W//2), avg_pool2d(2, 2) (corr.py:119)."""
     vol = _f32c(vol, 'vol')
@@ -297,6 +325,7 @@ def from_tiled(flat: torch.Tensor, h: int, w: int) -> torch.Tensor:
     return p[..., :h, :w].contiguous()
 
 
+@_on_tensor_device
 def corr_pool_tiled(flat: torch.Tensor, h: int, w: int) -> torch.Tensor:
     """avg_pool2d(2,2) on tiled planes (..., tiled(h, w)) → (..., tiled(h//2, w//2))."""
     flat = _f32c(flat, 'vol')
@@ -328,6 +357,7 @@ def make_lookup_desc(slots: Sequence[tuple], n_targets: int, B: int, h: int, w: 
     return d
 
 
+@_on_tensor_device
 def corr_lookup(slots: Sequence[tuple], coords: torch.Tensor, nhwc: bool = False, tiled: bool = False) -> torch.Tensor:
     """coords (T,B,2,h,w) → (B, S*81, h, w) [reference layout] or (B,h,w,S*81) when nhwc (corr.py:307-350)."""
     coords = _f32c(coords, 'coords')
@@ -347,6 +377,7 @@ def corr_lookup(slots: Sequence[tuple], coords: torch.Tensor, nhwc: bool = False
 
 
 # ---- Bezier ------------------------------------------------------------------------------------------------
+@_on_tensor_device
 def bezier_eval(params: torch.Tensor, coef: np.ndarray) -> torch.Tensor:
     params = _f32c(params, 'params')
     B, c2, H, W = params.shape
@@ -363,6 +394,7 @@ def bezier_eval(params: torch.Tensor, coef: np.ndarray) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def cvx_upsample(data: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     """data (N,C,h,w), mask (N,576,h,w) in the reference layout → (N,C,8h,8w) (utils.py:33-48)."""
     data, mask = _f32c(data, 'data'), _f32c(mask, 'mask')

@@ -126,8 +126,15 @@ def _update_block(cfg: Dict[str, Any], hdim: int) -> nn.Module:
 
 
 class RAFTSpline(nn.Module):
-    def __init__(self, model_params: Dict[str, Any], seed: Optional[int] = 0, verbose: bool = False):
+    """``precision``: arithmetic of the tensor-core convolutions.  ``'f32x3'`` (default): split-fp16 operands, three MMAs per product,
+    fp32-equivalent (the 1e-3 px configuration of BASELINE.json).  ``'f16'``: one fp16 MMA per product on the hi planes (the reduced-
+    precision configuration, 1e-2 px bar).  Default from the environment variable BFLOW_PRECISION."""
+
+    def __init__(self, model_params: Dict[str, Any], seed: Optional[int] = 0, verbose: bool = False, precision: Optional[str] = None):
         super().__init__()
+        import os
+        self.precision = precision if precision is not None else os.environ.get('BFLOW_PRECISION', 'f32x3')
+        assert self.precision in ('f32x3', 'f16'), self.precision
         p = model_params
         nctx, ncorr = p['num_bins']['context'], p['num_bins']['correlation']
         self.bezier_degree = p['bezier_degree']
@@ -167,6 +174,11 @@ class RAFTSpline(nn.Module):
 
         self.model_params = p
         self._engine = None
+        self._engine_versions = None
+        # the reference's RAFTSplineModule loads checkpoints through the PARENT module: PyTorch then copies into the parameters in place and
+        # never calls this module's load_state_dict.  The post-hook fires for nested loads too; in-place updates (optimizer steps, EMA swaps,
+        # param.data.copy_) are caught by the tensor version counters checked in engine().
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
         if verbose:
             print(f'bflow_b200 RAFT-Spline: context bins {nctx}, correlation bins {ncorr}, '
                   f'degree {self.bezier_degree}, events {p["use_events"]}, images {p["use_boundary_images"]}')
@@ -211,6 +223,10 @@ class RAFTSpline(nn.Module):
     def _invalidate(self, *_):
         self._engine = None
 
+    def _versions(self):
+        """Fingerprint of the parameter / buffer storage the packed weight images were made from."""
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
     def load_state_dict(self, *a, **k):
         out = super().load_state_dict(*a, **k)
         self._engine = None
@@ -233,9 +249,12 @@ class RAFTSpline(nn.Module):
         device = torch.device(device) if device is not None else next(self.parameters()).device
         if device.type != 'cuda':
             raise RuntimeError('bflow_b200.RAFTSpline runs only on CUDA (sm_100a); there is no CPU path')
-        if self._engine is None or self._engine.device != device:
+        ver = self._versions()
+        if (self._engine is None or self._engine.device != device or self._engine.precision != self.precision or
+                self._engine_versions != ver):
             from .engine import Engine
-            self._engine = Engine(self, device)
+            self._engine = Engine(self, device, self.precision)
+            self._engine_versions = ver
         return self._engine
 
     @torch.no_grad()
@@ -244,7 +263,12 @@ class RAFTSpline(nn.Module):
                 images: Optional[List[torch.Tensor]] = None,
                 iters: int = 12,
                 flow_init: Optional[BezierCurves] = None,
-                test_mode: bool = False):
+                test_mode: bool = False,
+                non_blocking: bool = False):
+        """Same contract as the reference (raft.py:101-200).  ``non_blocking=True`` (an extension) pipelines consecutive calls: inputs may be
+        PINNED host tensors, the host-to-device copy of this call and the device-to-host copy of the previous results overlap the
+        compute of the neighbouring calls, and the returned ``BezierCurves`` hold pinned HOST tensors that become valid when first
+        accessed (``get_params`` / ``cpu`` / ``get_flow_from_reference`` wait on an event) and stay valid until the second-next such call."""
         assert voxel_grid is not None or images is not None
         assert iters > 0
         if self.fnet_ev is not None:
@@ -255,9 +279,17 @@ class RAFTSpline(nn.Module):
             assert images is not None and len(images) == 2
         ref = voxel_grid if voxel_grid is not None else images[0]
         assert ref.shape[-2] % 8 == 0 and ref.shape[-1] % 8 == 0
+        init = flow_init.get_params() if flow_init is not None else None
+        if non_blocking:
+            dev = next(self.parameters()).device
+            if dev.type != 'cuda':
+                raise RuntimeError('bflow_b200.RAFTSpline runs only on CUDA (sm_100a); move the module to a CUDA device first')
+            low, ups, ev = self.engine(dev).run(voxel_grid, images, iters, init, test_mode, non_blocking=True)
+            if test_mode:
+                return BezierCurves(low, ready_event=ev), BezierCurves(ups[-1], ready_event=ev)
+            return [BezierCurves(u, ready_event=ev) for u in ups]
         if not ref.is_cuda:
             raise RuntimeError('bflow_b200.RAFTSpline runs only on CUDA tensors (sm_100a); there is no CPU path')
-        init = flow_init.get_params() if flow_init is not None else None
         low, ups = self.engine(ref.device).run(voxel_grid, images, iters, init, test_mode)
         if test_mode:
             return BezierCurves(low), BezierCurves(ups[-1])

@@ -46,10 +46,24 @@ extern "C" {
 #define BFLOW_MAX_TARGETS 8
 #define BFLOW_MAX_DEGREE 16
 
+/* ABI version 2: both descriptors start with `struct_size` (= sizeof of the struct the CALLER was compiled against; the library
+ * refuses a descriptor of another size with BFLOW_ERR_INVALID instead of reading past it), bflow_conv_desc carries `precision`,
+ * bflow_sizeof_*() / bflow_source_hash() exist.  Bumped whenever a descriptor layout or an entry-point signature changes. */
+#define BFLOW_ABI_VERSION 2
 int bflow_abi_version(void);
 const char* bflow_last_error(void);
 /* compute capability the library was built for (100 for sm_100a) */
 int bflow_built_for_sm(void);
+/* sizeof(bflow_conv_desc) / sizeof(bflow_lookup_desc) as the LIBRARY was compiled: a binding checks its own struct against these */
+int bflow_sizeof_conv_desc(void);
+int bflow_sizeof_lookup_desc(void);
+/* hex sha256 over the library sources (every .cu and .cuh under csrc, then include/bflow_b200.h; sorted) baked in at build time:
+ * bflow_b200/build.py recomputes it from the working tree, so a stale binary is detected by content, not by mtime */
+const char* bflow_source_hash(void);
+
+/* arithmetic of the tensor-core convolutions (bflow_conv_desc.precision) */
+#define BFLOW_PREC_SPLIT3 0   /* x = hi + lo (two fp16 planes), hi*hi + hi*lo + lo*hi, fp32 accumulate: fp32-equivalent (default) */
+#define BFLOW_PREC_F16 1      /* single fp16 MMA on the hi planes only (lo planes neither read nor written), fp32 accumulate */
 
 /* ---------------------------------------------------------------------------------------------
  * Layout plumbing.  Replaces torch slicing/cat of the voxel grid windows (models/raft_spline/raft.py:88-99),
@@ -69,6 +83,8 @@ int bflow_nhwc_to_nchw(const float* src, float* dst, int N, int C, int H, int W,
  * Weights are pre-packed K-major: w[((kh*KW + kw)*Cin + c) * ldw + o], zero padded to ldw (ldw % 4 == 0).
  * ------------------------------------------------------------------------------------------- */
 typedef struct bflow_conv_desc {
+    int struct_size;                       /* sizeof(bflow_conv_desc) of the caller */
+    int precision;                         /* BFLOW_PREC_*: tensor-core entry points only */
     const float* x0; int c0; int ld0;
     const float* x1; int c1; int ld1;      /* x1 == NULL / c1 == 0: single source */
     const float* w;  int ldw;
@@ -96,20 +112,19 @@ typedef struct bflow_conv_desc {
 } bflow_conv_desc;
 int bflow_conv2d_nhwc(const bflow_conv_desc* d, void* stream);
 
-/* Tensor-core form of the same operator (tcgen05.mma, TMEM accumulators, split 16-bit operands: every fp32
+/* Tensor-core forms of the same operator (tcgen05.mma, TMEM accumulators, split 16-bit operands: every fp32
  * operand x = hi + lo with hi = fp16(x), lo = fp16(x - hi), saturating at |x| = 1.3e5; products hi*hi + hi*lo + lo*hi
  * accumulated in fp32).
  * `d->w/ldw` are ignored; `w_tc` is the packed image of W / acc_scale
  *   [ceil(Cout/bn)][ceil(K/64)][hi | lo (fp16)][bn rows][64 elements]
  * whose 16-byte chunks are XOR-swizzled by (row % 8), i.e. byte for byte the SWIZZLE_128B shared-memory tile
  * (bflow_b200/ops.py pack_conv_weight_tc); acc_scale (a power of two) is multiplied back onto the accumulator.
- * Needs c0 % 8 == 0, c1 % 8 == 0, ld % 4 == 0, 16-byte aligned sources and KH*KW <= 32
- * (bflow_conv2d_tc_supported returns 1).  bn in {64,128,256}.  `err`: optional device int, set to 1 if an
- * in-kernel pipeline wait timed out (never expected; the waits are bounded so that a bug cannot hang the GPU). */
-int bflow_conv2d_tc_supported(const bflow_conv_desc* d);
-/* TMA-fed, persistent form of the tensor-core convolution.  Activations are read as split-fp16 planes (hi, lo) through
+ * bn in {64,128,256}.  `err`: optional device int, set to 1 if an in-kernel pipeline wait timed out (never expected; the
+ * waits are bounded so that a bug cannot hang the GPU; a CTA that times out stops issuing work and exits).
+ * precision = BFLOW_PREC_F16 runs ONE tcgen05.mma per k-step on the hi planes / the hi half of the weight image. */
+/* TMA-fed, persistent tensor-core convolution.  Activations are read as split-fp16 planes (hi, lo) through
  * im2col tensor maps (cp.async.bulk.tensor.4d...im2col: the TMA unit does the implicit-GEMM gather and the zero padding),
- * weights as in bflow_conv2d_nhwc_tc but with K ordered (tap, 64-channel block) — pack_conv_weight_tc(block_per_tap=True).
+ * weights as the image above with K ordered (tap, 64-channel block) — pack_conv_weight_tc(block_per_tap=True).
  * One CTA per SM loops over 128 x bn tiles; TMEM holds two accumulators so the epilogue of a tile overlaps the MMAs of the
  * next.  Warp roles: TMA producer / MMA issuer / 4 epilogue warps.  d->x0/x1 are ignored (c0/c1 and the geometry are used).
  * maps: host array of four 128-byte tensor maps {source0 hi, source0 lo, source1 hi, source1 lo} from bflow_tma_im2col_map
@@ -157,10 +172,6 @@ int bflow_split_f16(const float* src, int ld, void* hi, void* lo, int ld16, long
  * perm(r): identity when tile_w == 0; otherwise the source rows are pixels (y, x) of a tile_h x tile_w plane and
  * land in 4x4-pixel-tiled order (the layout bflow_corr_lookup reads with tiled = 1). */
 int bflow_pack_b_tc(const float* src, int ld, void* dst, int rows, int K, int bn, int plane_h, int plane_w, void* stream);
-/* Correlation volume on tensor cores (corr.py:264-272): corr[bq, n] = sum_d f1[bq, d] * f2[n, d] / sqrt(D), n in [0, Np).
- * f2_img: per-sample images from bflow_pack_b_tc (img_stride bytes apart). */
-int bflow_corr_volume_tc(const float* f1, int ld1, const void* f2_img, long long img_stride, float* corr,
-                         int B, int D, int Q, int Np, int bn, int* err, void* stream);
 /* Direct convolution for tiny Cout (<= 32): one warp per output pixel, K split over lanes, shuffle reduction.
  * Same descriptor and packed weights as bflow_conv2d_nhwc (Bezier head conv2: 256 -> 2*degree, update.py:18). */
 int bflow_conv2d_small_n(const bflow_conv_desc* d, void* stream);
@@ -168,7 +179,6 @@ int bflow_conv2d_small_n(const bflow_conv_desc* d, void* stream);
  * shared memory: convf1 of the motion encoder, Bezier parameters -> 128 (update.py:91).  Same descriptor and packed fp32
  * weights as bflow_conv2d_nhwc; standard epilogue only. */
 int bflow_conv2d_thin7(const bflow_conv_desc* d, void* stream);
-int bflow_conv2d_nhwc_tc(const bflow_conv_desc* d, const void* w_tc, int bn, float acc_scale, int* err, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * InstanceNorm2d (biased variance, eps, no affine; extractor.py:27-31) in two passes:
@@ -183,7 +193,8 @@ int bflow_instnorm_relu(const float* a, int lda, const double* sums_a,
                         const float* r, int ldr, const double* sums_r,
                         float* out, int ldo, int N, int HW, int C, float eps, void* stream);
 /* split-fp16 form: the residual may come from a split tensor (r16_hi/lo, identity skip of an encoder block whose input is
- * stored split) and the result may be written as fp32 (out, may be NULL) and/or split planes (out16_hi/lo, may be NULL). */
+ * stored split; r16_lo == NULL: the hi plane alone) and the result may be written as fp32 (out, may be NULL) and/or split
+ * planes (out16_hi/lo, may be NULL; out16_lo == NULL with out16_hi set: hi plane only, BFLOW_PREC_F16 consumers). */
 int bflow_instnorm_relu16(const float* a, int lda, const double* sums_a,
                           const float* r, int ldr, const double* sums_r,
                           const void* r16_hi, const void* r16_lo, int ldr16,
@@ -213,6 +224,7 @@ int bflow_corr_pool_tiled(const float* in, float* out, long long planes, int H, 
  * from `params` (NHWC rows (B*Q) x 2*degree at pixel stride params_ld; channel = dim*degree + i-1).
  * ------------------------------------------------------------------------------------------- */
 typedef struct bflow_lookup_desc {
+    int struct_size;                       /* sizeof(bflow_lookup_desc) of the caller */
     int n_slots, n_targets, B, h, w, radius;
     const float* vol[BFLOW_MAX_SLOTS];     /* (B*Q, hl, wl) planes of this slot's (level, target) */
     int hl[BFLOW_MAX_SLOTS], wl[BFLOW_MAX_SLOTS];
@@ -225,7 +237,8 @@ typedef struct bflow_lookup_desc {
     int out_nhwc;                          /* 0: (B, S*81, h, w) like the reference; 1: rows (B*Q) x out_ld */
     int out_ld;
     void* out16_hi; void* out16_lo;        /* when non-NULL (NHWC only): write split-fp16 planes (x = hi + lo) instead of `out`, */
-    int out16_ld;                          /* row stride in halves — the form the TMA-fed convolution reads */
+    int out16_ld;                          /* row stride in halves — the form the TMA-fed convolution reads; out16_lo == NULL: hi plane
+                                              only (BFLOW_PREC_F16 consumers) */
     int tiled;                             /* 0: planes row-major (hl x wl) like the reference; 1: planes stored as 4x4-pixel
                                               tiles (64-byte DRAM granules), ceil(hl/4) x ceil(wl/4) tiles of 16 floats, zero padded */
 } bflow_lookup_desc;
@@ -260,14 +273,25 @@ int bflow_cvx_upsample(const float* data, int ldd, int data_nchw, const float* m
  * Scope rows (f1)/(f2): the steps on either side of forward().
  * bflow_voxelize: VoxelGrid.convert (data/utils/representations.py:64-111).  x, y: int64 pixel coordinates (xy_is_float = 0) or
  * fp32 sub-pixel coordinates (1); pol: uint8/bool 0|1; time: int64; out: (channels, H, W) fp32, ACCUMULATED into (zero it first).
+ * Integer coordinates outside [0, W) x [0, H) make the reference's put_ raise; here such events are dropped and counted in
+ * *oob_count (device int, may be NULL) so that the binding can raise the same IndexError without corrupting memory.
  * bflow_voxel_norm: norm_voxel_grid (representations.py:9-18), in place; stats3: 3 doubles of scratch.
  * bflow_epe_masked: epe_masked (utils/metrics.py:196-213) as (sum, count): sum_count[0] += sum of sqrt(sum_c (src-tgt)^2) over the
  * valid pixels, sum_count[1] += their number (valid: uint8/bool (N, HW) or NULL); src/tgt NCHW (N, C, HW).
  * ------------------------------------------------------------------------------------------- */
 int bflow_voxelize(const void* x, const void* y, int xy_is_float, const unsigned char* pol, const long long* time, long long n_events,
-                   long long t0_center, long long t1_center, int channels, int H, int W, float* out, void* stream);
+                   long long t0_center, long long t1_center, int channels, int H, int W, float* out, int* oob_count, void* stream);
 int bflow_voxel_norm(float* voxel, long long numel, double* stats3, void* stream);
 int bflow_epe_masked(const float* src, const float* tgt, const unsigned char* valid, int N, int C, long long HW, double* sum_count, void* stream);
+/* Row (f2), the remaining flow metrics in ONE pass over NCHW (N, C, HW) tensors — n_pixel_error_masked (utils/metrics.py:161-193),
+ * epe_masked (:196-213), ae_masked (:259-296), and, through src_scale, the linear-assumption baseline (:298-305: prediction at
+ * time t = t * final flow).  With s = src_scale * src, e = |s - tgt|_2 and the sums running over the valid pixels:
+ *   out[0] += sum e            out[1] += number of valid pixels
+ *   out[2] += sum acos(clamp((<s, tgt> + 1) / (sqrt(|s|^2 + 1) * sqrt(|tgt|^2 + 1)), -1, 1))        (radians)
+ *   out[3 + k] += #{ e > thresholds[k]  and  e / max(|tgt|_2, 1e-6) >= 0.05 },  k < n_thresholds <= 4   (host array)
+ * out: 8 doubles, zeroed by the caller.  valid: uint8/bool (N, HW) or NULL. */
+int bflow_flow_metrics(const float* src, const float* tgt, const unsigned char* valid, int N, int C, long long HW, float src_scale,
+                       const float* thresholds_host, int n_thresholds, double* out8, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,32 +1,57 @@
-"""TEST INFRASTRUCTURE ONLY.  Imports the UNMODIFIED reference model code from /root/reference.
+"""TEST / BENCH INFRASTRUCTURE ONLY.  Imports the UNMODIFIED reference model code.
 
-Only usable in the build container (the GPU box has no /root/reference).  The single missing
-import on the model path is ``omegaconf.ListConfig`` (models/raft_utils/corr.py:8, used in one
-``isinstance``); a two-class shim is injected before import.  Nothing is written to the
-reference tree (bytecode writing is disabled)."""
+Search order: the live tree (/root/reference, build container only), then the byte-for-byte copy that
+``oracle/build_ref.py`` stages under ``oracle/_ref/`` (git-ignored, shipped to the GPU box with the working tree).
+The single missing import on the model path is ``omegaconf.ListConfig`` (models/raft_utils/corr.py:8, used in one
+``isinstance``); a two-class shim is injected before import.  Nothing is written to the reference tree (bytecode
+writing is disabled)."""
 import os
 import sys
 import types
 
-REF_ROOT = os.environ.get('BFLOW_REFERENCE_ROOT', '/root/reference')
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIVE_ROOT = os.environ.get('BFLOW_REFERENCE_ROOT', '/root/reference')
+STAGED_ROOT = os.path.join(HERE, '_ref')
+
+
+def _has(root: str) -> bool:
+    return os.path.isfile(os.path.join(root, 'models', 'raft_spline', 'raft.py'))
+
+
+def root() -> str:
+    """Directory the reference is imported from ('' when neither the live tree nor the staged copy exists)."""
+    if _has(LIVE_ROOT):
+        return LIVE_ROOT
+    if _has(STAGED_ROOT):
+        return STAGED_ROOT
+    return ''
+
+
+REF_ROOT = root()
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REF_ROOT, 'models', 'raft_spline', 'raft.py'))
+    return root() != ''
+
+
+def live() -> bool:
+    """The reference checkout itself (not the staged copy) is present: build container only."""
+    return _has(LIVE_ROOT)
 
 
 def load():
     """Returns the reference ``models.raft_spline.raft`` module."""
-    if not available():
-        raise RuntimeError(f'reference not found at {REF_ROOT}')
+    r = root()
+    if not r:
+        raise RuntimeError(f'reference not found at {LIVE_ROOT} nor staged under {STAGED_ROOT} (python -m oracle.build_ref)')
     sys.dont_write_bytecode = True
     if 'omegaconf' not in sys.modules:
         shim = types.ModuleType('omegaconf')
         shim.ListConfig = type('ListConfig', (list,), {})
         shim.DictConfig = type('DictConfig', (dict,), {})
         sys.modules['omegaconf'] = shim
-    if REF_ROOT not in sys.path:
-        sys.path.insert(0, REF_ROOT)
+    if r not in sys.path:
+        sys.path.insert(0, r)
     import importlib
     import contextlib
     import io

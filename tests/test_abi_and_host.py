@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f'{name} declared in include/bflow_b200.h but not exported'
     assert sorted(_lib.exported_symbols()) == declared, 'ctypes binding and header disagree'
-    assert lib.bflow_abi_version() == 1
+    assert lib.bflow_abi_version() == 2
     assert lib.bflow_built_for_sm() == 100
 
 
@@ -36,6 +36,16 @@ def test_contract_violations_return_invalid_without_touching_the_gpu():
     d = _lib.LookupDesc()
     d.n_slots = 99
     assert lib.bflow_corr_lookup(C.byref(d), None) == 1
+    assert b'bad slot count' in lib.bflow_last_error()
+    # a descriptor built against another header (wrong struct_size) is refused before anything behind that field is read
+    d2 = _lib.LookupDesc()
+    d2.struct_size -= 24
+    assert lib.bflow_corr_lookup(C.byref(d2), None) == 1
+    assert b'descriptor size mismatch' in lib.bflow_last_error()
+    c = _lib.ConvDesc()
+    c.struct_size = 0
+    for fn in (lib.bflow_conv2d_nhwc, lib.bflow_conv2d_small_n, lib.bflow_conv2d_thin7):
+        assert fn(C.byref(c), None) == 1 and b'descriptor size mismatch' in lib.bflow_last_error()
     with pytest.raises(AssertionError):
         _lib.check(lib.bflow_corr_pool(None, None, 1, 4, 4, None), 'corr_pool')
 
@@ -55,6 +65,61 @@ def test_struct_layouts_match_the_header():
         a, b = map(int, subprocess.check_output([exe]).split())
     assert a == C.sizeof(_lib.ConvDesc)
     assert b == C.sizeof(_lib.LookupDesc)
+    # ... and as the LIBRARY was compiled
+    lib = _lib.lib()
+    assert lib.bflow_sizeof_conv_desc() == a and lib.bflow_sizeof_lookup_desc() == b
+    assert _lib.ConvDesc().struct_size == a and _lib.LookupDesc().struct_size == b
+
+
+def test_library_is_built_from_the_sources_in_the_tree():
+    from bflow_b200 import build
+    h = _lib.lib().bflow_source_hash().decode()
+    assert len(h) == 64 and h == build.source_hash()
+
+
+def test_integration_md_ctypes_stub_matches_the_header():
+    """The binding INTEGRATION.md tells a maintainer to paste must describe the struct the library reads."""
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    blocks = re.findall(r'```python\n(.*?)```', doc, flags=re.S)
+    stub = next(b for b in blocks if 'class LookupDesc' in b)
+    ns = {}
+    exec(compile(stub.replace("C.CDLL('bflow_b200/libbflow_b200.so')", f"C.CDLL({_lib._build.LIB!r})"), 'INTEGRATION.md', 'exec'), ns)
+    lib = _lib.lib()
+    assert C.sizeof(ns['LookupDesc']) == lib.bflow_sizeof_lookup_desc() == C.sizeof(_lib.LookupDesc)
+    assert [f[0] for f in ns['LookupDesc']._fields_] == [f[0] for f in _lib.LookupDesc._fields_]
+    for (n1, t1), (n2, t2) in zip(ns['LookupDesc']._fields_, _lib.LookupDesc._fields_):
+        assert C.sizeof(t1) == C.sizeof(t2), n1
+    assert callable(ns['corr_block_call'])
+
+
+def test_packed_weights_follow_in_place_parameter_updates():
+    """a checkpoint loaded through a PARENT module, an optimizer step or param.data.copy_ never calls
+    RAFTSpline.load_state_dict; the engine must notice through the load-state-dict post hook / the tensor version counters."""
+    net = RAFTSpline(config.preset('E_LU4_BD2'), seed=0)
+    v0 = net._versions()
+    net._engine, net._engine_versions = 'packed', v0                       # stands for a built engine (no GPU here)
+    with torch.no_grad():
+        net.update_block.gru.convz1.weight.mul_(1.5)                        # in-place update
+    assert net._versions() != v0
+    parent = torch.nn.Module()
+    parent.net = net
+    net._engine = 'packed'
+    parent.load_state_dict({'net.' + k: v for k, v in RAFTSpline(config.preset('E_LU4_BD2'), seed=3).state_dict().items()}, strict=True)
+    assert net._engine is None                                              # the post hook fired for the nested load
+    net.precision = 'f16'
+    assert net.precision == 'f16'
+    with pytest.raises(AssertionError):
+        RAFTSpline(config.preset('E_LU4_BD2'), precision='int8')
+
+
+def test_reference_copy_under_oracle_ref_is_unmodified():
+    from oracle import build_ref, ref_loader
+    if not os.path.isdir(build_ref.DST):
+        pytest.skip('oracle/_ref not staged (python -m oracle.build_ref)')
+    assert build_ref.verify()
+    if ref_loader.live():
+        for rel in build_ref.FILES:
+            assert build_ref.sha256(os.path.join(build_ref.SRC, rel)) == build_ref.sha256(os.path.join(build_ref.DST, rel))
 
 
 def test_config_tables():
@@ -123,6 +188,22 @@ def test_bezier_curves_cpu_api():
     z = BezierCurves.create_from_voxel_grid(torch.zeros(1, 9, 64, 96), bezier_degree=10)
     assert z.get_params().shape == (1, 20, 8, 12)
     assert b.cpu().get_params().device.type == 'cpu' and not b.detach().requires_grad
+
+
+def test_weight_images_are_packed_on_the_host():
+    """Engine packing must not launch PyTorch kernels (the driver's launch capture should start with this library's kernels)."""
+    from bflow_b200.ops import pack_conv_weight_tc
+    w = torch.randn(96, 70, 3, 3)
+    img, acc = pack_conv_weight_tc(w, 64, block_per_tap=True)
+    assert img.device.type == 'cpu' and img.dtype == torch.int16
+    assert img.numel() == 2 * 9 * 2 * 2 * 64 * 64                          # n-tiles x (tap, 64-ch block) x hi|lo x rows x 64
+    k = -int(np.log2(acc))
+    # tile 0, k-block 0 (tap 0, channels 0..63), hi plane, row r: chunk j holds source chunk j ^ (r % 8)
+    hi = img.view(2, 18, 2, 64, 8, 8)[0, 0, 0].view(torch.float16)
+    want = (w[:64, :64, 0, 0] * 2.0 ** k).half()
+    for r in (0, 3, 63):
+        for j in (0, 5):
+            assert torch.equal(hi[r, j], want[r, (j ^ (r % 8)) * 8:(j ^ (r % 8)) * 8 + 8])
 
 
 def test_weight_packing_layout():

@@ -47,18 +47,48 @@ def test_conv2d_matches_torch(N, Cin, H, W, Cout, k, s, p, act):
     (1, 96, 16, 24, 128, (3, 3), 1, (1, 1), 'relu', 64),       # k-blocks straddle taps
     (1, 384, 8, 12, 256, (1, 5), 1, (0, 2), 'sigmoid', 64),
     (1, 384, 8, 12, 128, (5, 1), 1, (2, 0), 'tanh', 128),
-    (1, 256, 8, 12, 4, (3, 3), 1, (1, 1), 'none', 64),
     (4, 128, 40, 60, 64, (3, 3), 1, (1, 1), 'relu', 64),
 ])
-def test_conv2d_tensor_core_matches_torch(N, Cin, H, W, Cout, k, s, p, act, bn):
-    """tcgen05 path with split-bf16 operands: ~16 mantissa bits per operand, fp32 accumulate."""
+def test_conv2d_tc3_small_shapes_match_torch(N, Cin, H, W, Cout, k, s, p, act, bn):
+    """tcgen05 path with split-fp16 operands (hi*hi + hi*lo + lo*hi): ~22 mantissa bits per operand, fp32 accumulate."""
     x = torch.randn(N, Cin, H, W, generator=g(1))
     w = torch.randn(Cout, Cin, *k, generator=g(2)) / (Cin * k[0] * k[1]) ** 0.5
     b = torch.randn(Cout, generator=g(3))
     ref = F.conv2d(x.double(), w.double(), b.double(), stride=s, padding=p).float()
     ref = {'none': lambda t: t, 'relu': torch.relu, 'sigmoid': torch.sigmoid, 'tanh': torch.tanh}[act](ref)
-    out = ops.conv2d(x.to(DEV), w.to(DEV), b.to(DEV), stride=s, padding=p, act=act, backend='tc', bn=bn).cpu()
+    out = ops.conv2d(x.to(DEV), w.to(DEV), b.to(DEV), stride=s, padding=p, act=act, backend='tc3', bn=bn).cpu()
     assert (out - ref).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize('backend,N,Cin,H,W,Cout,k,s,p,act,bn', [
+    ('tc3', 1, 576, 60, 80, 256, (1, 1), 1, (0, 0), 'relu', 128),        # convc1 shape, tensor-map store epilogue
+    ('tc3', 1, 256, 60, 80, 124, (3, 3), 1, (1, 1), 'relu', 64),         # ragged Cout
+    ('tc3', 2, 64, 96, 100, 96, (3, 3), 2, (1, 1), 'none', 128),         # multi-tile, stride 2
+    ('tc3', 1, 256, 60, 80, 256, (1, 5), 1, (0, 2), 'sigmoid', 128),     # GRU-shaped, bulk-copy epilogue
+    ('tc3', 1, 64, 8, 16, 256, (1, 1), 1, (0, 0), 'none', 256),          # bn 256 (three-MMA form in split mode)
+    ('slab64', 2, 64, 40, 48, 64, (3, 3), 1, (1, 1), 'relu', 64),
+    ('stem7', 2, 5, 64, 96, 64, (7, 7), 2, (3, 3), 'relu', 64),
+])
+def test_conv2d_single_mma_f16_precision(backend, N, Cin, H, W, Cout, k, s, p, act, bn):
+    """BFLOW_PREC_F16 (row g): ONE fp16 MMA per k-step on the hi planes, fp32 accumulate.  Checked two ways: against fp64 on the
+    fp16-ROUNDED operands it is as exact as the split mode (proves that the lo planes / the lo half of the weight image are really
+    ignored and nothing else changed), and against the unrounded fp32 operands it is within the fp16 rounding of the inputs."""
+    x = torch.randn(N, Cin, H, W, generator=g(1))
+    w = torch.randn(Cout, Cin, *k, generator=g(2)) / (Cin * k[0] * k[1]) ** 0.5
+    b = torch.randn(Cout, generator=g(3))
+    fn = {'none': lambda t: t, 'relu': torch.relu, 'sigmoid': torch.sigmoid, 'tanh': torch.tanh}[act]
+    kexp = int(torch.floor(-torch.log2(w.abs().max())))                 # the packer's power-of-two prescale (exact)
+    w16 = (w * 2.0 ** kexp).half().double() * 2.0 ** (-kexp)
+    ref16 = fn(F.conv2d(x.half().double(), w16, b.double(), stride=s, padding=p).float())
+    ref32 = fn(F.conv2d(x.double(), w.double(), b.double(), stride=s, padding=p).float())
+    ops.conv2d.precision = 'f16'
+    try:
+        out = ops.conv2d(x.to(DEV), w.to(DEV), b.to(DEV), stride=s, padding=p, act=act, backend=backend, bn=bn).cpu()
+    finally:
+        ops.conv2d.precision = 'f32x3'
+    assert (out - ref16).abs().max() < 1e-4
+    assert (out - ref32).abs().max() < 2e-2
+    assert (out - ref32).abs().max() > 1e-5          # ... and it is NOT the split path
 
 
 @pytest.mark.parametrize('N,Cin,H,W,Cout,k,s,p,act,bn', [

@@ -1,5 +1,5 @@
 """Single-convolution microbench / ncu target.
-    python tools/conv_bench.py --n 1 --cin 384 --h 60 --w 80 --cout 128 --kh 1 --kw 5 --backend tc --bn 64"""
+    python tools/conv_bench.py --n 1 --cin 384 --h 60 --w 80 --cout 128 --kh 1 --kw 5 --backend tc3 --bn 64"""
 import argparse
 import ctypes as C
 import os
@@ -17,7 +17,7 @@ def main():
     ap = argparse.ArgumentParser()
     for k, v in dict(n=1, cin=384, h=60, w=80, cout=128, kh=1, kw=5, stride=1, bn=64, reps=10).items():
         ap.add_argument('--' + k, type=int, default=v)
-    ap.add_argument('--backend', default='tc')
+    ap.add_argument('--backend', default='tc3', choices=['tc3', 'simt'])
     ap.add_argument('--dbg', type=int, default=0)
     ap.add_argument('--trace', action='store_true')
     a = ap.parse_args()
@@ -30,7 +30,6 @@ def main():
     b = torch.randn(a.cout, device=dev)
     y = torch.empty(a.n, Ho, Wo, a.cout, device=dev)
     wp, ldw = ops.pack_conv_weight(w)
-    wtc, acc_scale = ops.pack_conv_weight_tc(w, a.bn)
     err = torch.zeros(1, device=dev, dtype=torch.int32)
     x16 = ops.split_f16(x, (a.cin + 7) // 8 * 8)
     m = ops.tma_im2col_maps(x16, a.n, a.h, a.w, a.cin, a.kh, a.kw, a.stride, ph, pw)
@@ -52,8 +51,6 @@ def main():
     def run():
         if a.backend == 'tc3':
             _lib.check(lib.bflow_conv2d_nhwc_tc3(C.byref(d), C.addressof(maps), wtc3.data_ptr(), a.bn, acc3, err.data_ptr(), st), 'tc3')
-        elif a.backend == 'tc':
-            _lib.check(lib.bflow_conv2d_nhwc_tc(C.byref(d), wtc.data_ptr(), a.bn, acc_scale, err.data_ptr(), st), 'tc')
         else:
             _lib.check(lib.bflow_conv2d_nhwc(C.byref(d), st), 'simt')
     for _ in range(3):

@@ -33,11 +33,12 @@ def main():
                 i = hdr.index(k)
                 print(f'{k:88s} {r[i]:>16s} {units[i]}')
     src = page(rep, 'source')
-    if len(src) > 2:
-        h = src[1]
+    hrow = next((i for i, r in enumerate(src[:6]) if 'Source' in r and '# Samples' in r), None)      # the header row moves between ncu versions
+    if hrow is not None and len(src) > hrow + 1:
+        h = src[hrow]
         isrc, ismp, iex = h.index('Source'), h.index('# Samples'), h.index('Instructions Executed')
         stalls = [i for i, x in enumerate(h) if x.startswith('stall_') and 'Not Issued' not in x]
-        data = src[2:]
+        data = [r for r in src[hrow + 1:] if len(r) == len(h)]
         tot = sum(int(r[ismp] or 0) for r in data) or 1
         print(f'\n## hottest SASS instructions of the last launch ({tot} warp samples, {len(data)} instructions)')
         for r in sorted(data, key=lambda r: -int(r[ismp] or 0))[:14]:
