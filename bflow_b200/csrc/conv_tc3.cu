@@ -414,6 +414,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
             for (int kb = 0; kb < p.nkb; ++kb) {
                 t3_mbar_wait(full_bar(ms), mph, err);
                 t3_fence_after();
+                if (kb == 0 && lt == 0 && lane == 0) T3_CTA(3);
                 const uint32_t a_hi = smem_base + ms * (uint32_t)STAGE_BYTES;
                 const uint64_t dah0 = t3_umma_desc(a_hi);
                 const uint64_t dal0 = dah0 + (uint64_t)(T3_A_BYTES >> 4);
@@ -1817,7 +1818,7 @@ static EncodeIm2colFn get_encode_im2col() {
 static int g_tc3_debug = 0;
 static long long* g_tc3_trace = nullptr;
 static unsigned long long* g_tc3_cta = nullptr;
-static int g_tc3_cta_nth = -1, g_tc3_cta_count = 0;
+static int g_tc3_cta_nth = -1, g_tc3_cta_span = 1, g_tc3_cta_count = 0;
 
 template <int BN, int STAGES>
 static int launch_tc3(const CUtensorMap* maps, const bflow_conv_desc& d, const void* wtc, const T3Params& p, int* err, cudaStream_t stream) {      // maps: 4 input + 3 output
@@ -1952,6 +1953,14 @@ extern "C" void bflow_tc3_trace(long long* device_buf_6x256) { bflow::g_tc3_trac
 extern "C" void bflow_tc3_cta_trace(void* buf, int nth) {
     bflow::g_tc3_cta = reinterpret_cast<unsigned long long*>(buf);
     bflow::g_tc3_cta_nth = nth;
+    bflow::g_tc3_cta_span = 1;
+    bflow::g_tc3_cta_count = 0;
+}
+// the same for `count` consecutive tc3 launches starting at the nth: buf[count][148][16]
+extern "C" void bflow_tc3_cta_trace_range(void* buf, int nth, int count) {
+    bflow::g_tc3_cta = reinterpret_cast<unsigned long long*>(buf);
+    bflow::g_tc3_cta_nth = nth;
+    bflow::g_tc3_cta_span = count > 0 ? count : 1;
     bflow::g_tc3_cta_count = 0;
 }
 
@@ -2096,7 +2105,11 @@ static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* om
             p.staged = 3;
     }
     p.trace = bflow::g_tc3_trace;
-    p.cta = (bflow::g_tc3_cta != nullptr && bflow::g_tc3_cta_count++ == bflow::g_tc3_cta_nth) ? bflow::g_tc3_cta : nullptr;
+    p.cta = nullptr;
+    if (bflow::g_tc3_cta != nullptr) {
+        const int idx = bflow::g_tc3_cta_count++ - bflow::g_tc3_cta_nth;
+        if (idx >= 0 && idx < bflow::g_tc3_cta_span) p.cta = bflow::g_tc3_cta + (size_t)idx * 148 * 16;
+    }
     p.tl = bflow::timeline_next_slot(bn == 64 ? "tc3_64" : bn == 128 ? "tc3_128" : "tc3_256");
     alignas(64) CUtensorMap tm[9];
     memset(tm, 0, sizeof(tm));

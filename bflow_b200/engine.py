@@ -24,7 +24,7 @@ from collections import OrderedDict
 from . import _lib, config as _cfg
 from ._lib import ACT, EPI, PREC, ConvDesc, LookupDesc, check
 from .bezier import bernstein_coeffs
-from .ops import pack_conv_weight, pack_conv_weight_tc, make_lookup_desc, tiled_plane_size
+from .ops import pack_conv_weight, pack_conv_weight_tc, make_lookup_desc, tiled_plane_size, dev_zeros
 from .engine_s16 import S16Recorder
 
 
@@ -66,7 +66,7 @@ class Engine:
         self.use_side_stream = os.environ.get('BFLOW_STREAMS', '1') != '0'
         self.max_plans = max(1, int(os.environ.get('BFLOW_MAX_PLANS', '4')))
         with torch.cuda.device(device):
-            self.err = torch.zeros(1, device=device, dtype=torch.int32)
+            self.err = dev_zeros(1, device=device, dtype=torch.int32)
             self._err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
             self._err_event = None
             self.h2d_stream = torch.cuda.Stream(device=device)
@@ -252,9 +252,9 @@ class _Plan(S16Recorder):
         nctx, ncorr = cfg['num_bins']['context'], cfg['num_bins']['correlation']
         self.cin_vox = nctx + ncorr - 1
         # static inputs
-        self.voxel_in = torch.zeros(B, self.cin_vox, H, W, **f32) if self.use_ev else None
-        self.img_in = [torch.zeros(B, 3, H, W, **f32) for _ in range(2)] if self.use_img else None
-        self.init_in = torch.zeros(B, 2 * eng.deg, self.h, self.w, **f32)
+        self.voxel_in = dev_zeros(B, self.cin_vox, H, W, **f32) if self.use_ev else None
+        self.img_in = [dev_zeros(B, 3, H, W, **f32) for _ in range(2)] if self.use_img else None
+        self.init_in = dev_zeros(B, 2 * eng.deg, self.h, self.w, **f32)
         # outputs
         self.low = torch.empty(B, 2 * eng.deg, self.h, self.w, **f32)
         n_up = 1 if test_mode else iters
@@ -388,27 +388,27 @@ class _Plan(S16Recorder):
         T = len(eng.levels)
         np_max = max((T_ev + 1) * B if self.use_ev else 0, 2 * B if self.use_img else 0, B)
         bufs = [torch.empty(np_max * (H // 2) * (W // 2) * 64, **f32) for _ in range(4)]
-        self.sums = torch.zeros(64 * np_max * 128 * 2, device=dev, dtype=torch.float64)
+        self.sums = dev_zeros(64 * np_max * 128 * 2, device=dev, dtype=torch.float64)
         self._sums_off = 0
         self.keep += bufs
         self._add(L.bflow_zero, self.sums.data_ptr(), self.sums.numel() * 8)
 
         gw = hd + cd + md                              # GRU input width = [h | inp | motion]
         poff = hd + cd + md - 2 * deg                  # Bezier params live at the tail of hx
-        self.hx = torch.zeros(R, gw, **f32)
+        self.hx = dev_zeros(R, gw, **f32)
         self.poff, self.gw = poff, gw
         hx = self.hx.data_ptr()
 
         # ---- inputs to NHWC ----
         ctx_c = (nctx if self.use_ev else 0) + (3 if self.use_img else 0)
-        self.ctx = torch.zeros(B, H, W, ctx_c, **f32)
+        self.ctx = dev_zeros(B, H, W, ctx_c, **f32)
         if self.use_ev:
-            self.vox = torch.zeros(B, H, W, self.cin_vox, **f32)
+            self.vox = dev_zeros(B, H, W, self.cin_vox, **f32)
             self._add(L.bflow_nchw_to_nhwc, self.voxel_in.data_ptr(), self.vox.data_ptr(), B, self.cin_vox, H, W, 0, self.cin_vox,
                       self.cin_vox, 1.0, 0.0)
         if self.use_img:
             # images -> 2*(x/255)-1 (raft.py:134); image 0 is also the tail of the context input (raft.py:137-140)
-            self.imgs = torch.zeros(2 * B, H, W, 3, **f32)
+            self.imgs = dev_zeros(2 * B, H, W, 3, **f32)
             for i in range(2):
                 self._add(L.bflow_nchw_to_nhwc, self.img_in[i].data_ptr(), self.imgs.data_ptr() + i * B * H * W * 3 * 4, B, 3, H, W, 0, 3, 3,
                           2.0 / 255.0, -1.0)
@@ -477,7 +477,7 @@ class _Plan(S16Recorder):
 
         # ---- lookup descriptor (corr.py:307-350); centres come from the Bezier params in hx ----
         slots = [(lvl, t, pyr[lvl][1][pyr[lvl][0].index(t)]) for (lvl, t) in eng.slots]
-        self.corr = torch.zeros(R, eng.ldc, **f32)
+        self.corr = dev_zeros(R, eng.ldc, **f32)
         ld = make_lookup_desc(slots, T, B, h, w, False)
         ld.coords = None
         ld.params, ld.params_ld, ld.degree = hx + poff * 4, gw, deg

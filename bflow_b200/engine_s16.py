@@ -16,7 +16,7 @@ import torch
 
 from . import _lib
 from ._lib import ACT, EPI, ConvDesc, check
-from .ops import make_lookup_desc, tiled_plane_size
+from .ops import make_lookup_desc, tiled_plane_size, dev_zeros
 
 
 class _S16:
@@ -26,7 +26,7 @@ class _S16:
     def __init__(self, rows: int, ld: int, dev, base: Optional[int] = None, lo_base: Optional[int] = None):
         self.rows, self.ld = rows, ld
         if base is None:
-            self.t = torch.zeros(2, rows, ld, device=dev, dtype=torch.float16)
+            self.t = dev_zeros(2, rows, ld, device=dev, dtype=torch.float16)
             base = self.t.data_ptr()
         self.base = base
         self.lo_base = base + 2 * rows * ld if lo_base is None else lo_base
@@ -207,7 +207,7 @@ class S16Recorder:
             key = ('x16', src_nchw.data_ptr())
             if key not in shared:        # NCHW fp32 -> NHWC fp32 -> split planes, once per source tensor
                 ld = _ceil(C_total, 8)
-                x32 = torch.zeros(ns, H, W, ld, device=dev, dtype=torch.float32)
+                x32 = dev_zeros(ns, H, W, ld, device=dev, dtype=torch.float32)
                 x16 = _S16(ns * H * W, ld, dev)
                 self._add(L.bflow_nchw_to_nhwc, src_nchw.data_ptr(), x32.data_ptr(), ns, C_total, H, W, 0, C_total, ld, scale, shift)
                 self._add(L.bflow_split_f16, x32.data_ptr(), ld, x16.hi(), x16.lo(), ld, ns * H * W, ld)
@@ -216,7 +216,7 @@ class S16Recorder:
             return dict(kind='tma', x16=shared[key], c_off=c_off, cin=cin, ns=ns)
         key = ('x32', src_nchw.data_ptr())
         if key not in shared:
-            x32 = torch.zeros(ns, H, W, C_total, device=dev, dtype=torch.float32)
+            x32 = dev_zeros(ns, H, W, C_total, device=dev, dtype=torch.float32)
             self._add(L.bflow_nchw_to_nhwc, src_nchw.data_ptr(), x32.data_ptr(), ns, C_total, H, W, 0, C_total, C_total, scale, shift)
             shared[key] = x32
             self.keep.append(x32)
@@ -379,13 +379,13 @@ class S16Recorder:
         # the context encoder runs beside the feature encoder on the second stream and needs its own scratch
         self.pool_c = [torch.empty(B * (H // 2) * (W // 2) * 64 * 4, device=dev, dtype=torch.uint8) for _ in range(5)]
         pool_c = [t.data_ptr() for t in self.pool_c]
-        self.sums = torch.zeros(64 * np_max * 128 * 2, device=dev, dtype=torch.float64)
+        self.sums = dev_zeros(64 * np_max * 128 * 2, device=dev, dtype=torch.float64)
         self._sums_off = 0
         self._add(L.bflow_zero, self.sums.data_ptr(), self.sums.numel() * 8)
 
         gw = hd + cd + md
         poff = hd + cd + md - 2 * deg
-        self.hx = torch.zeros(R, gw, **f32)                 # fp32 masters: h (cols 0:hd) and the Bezier params (cols poff:)
+        self.hx = dev_zeros(R, gw, **f32)                 # fp32 masters: h (cols 0:hd) and the Bezier params (cols poff:)
         self.hx16 = _S16(R, gw, dev)                        # what the convolutions read
         self.poff, self.gw = poff, gw
         hx, hx16 = self.hx.data_ptr(), self.hx16
@@ -398,7 +398,7 @@ class S16Recorder:
         if self.use_ev and self.use_img:
             # context = cat(voxel[:, -nctx:], image0) (raft.py:137-138): NHWC fp32 -> split planes -> 7x7 im2col-TMA stem
             ctx_ld = _ceil(ctx_c, 8)
-            self.ctx = torch.zeros(B, H, W, ctx_ld, **f32)
+            self.ctx = dev_zeros(B, H, W, ctx_ld, **f32)
             self.ctx16 = _S16(B * H * W, ctx_ld, dev)
             self._add(L.bflow_nchw_to_nhwc, self.voxel_in.data_ptr(), self.ctx.data_ptr(), B, self.cin_vox, H, W, self.cin_vox - nctx, nctx, ctx_ld, 1.0, 0.0)
             self._add(L.bflow_nchw_to_nhwc, self.img_in[0].data_ptr(), self.ctx.data_ptr() + nctx * 4, B, 3, H, W, 0, 3, ctx_ld, 2.0 / 255.0, -1.0)
@@ -447,7 +447,7 @@ class S16Recorder:
         Np0 = tiled_plane_size(h, w)
         self.vol0 = torch.empty(T, R, Np0, **f32)
         img_bytes = ((Np0 + bnv - 1) // bnv) * ((fd + 63) // 64) * 2 * bnv * 128
-        self.f2img = torch.zeros(T, B, img_bytes, device=dev, dtype=torch.uint8)
+        self.f2img = dev_zeros(T, B, img_bytes, device=dev, dtype=torch.uint8)
         srcs = [(fm_ev, (t + 1) * B, fm_ev16) for t in range(T_ev)] + ([(fm_img, B, fm_img16)] if self.use_img else [])
         for t, (fm2, n0, fm1_16) in enumerate(srcs):
             for b in range(B):

@@ -20,6 +20,16 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def dev_zeros(*shape, device, dtype=torch.float32) -> torch.Tensor:
+    """Zero-filled device tensor through cudaMemsetAsync (bflow_zero) instead of an ATen fill kernel: building a plan then launches
+    nothing but this library's kernels, which is what a launch capture of a forward should show first."""
+    t = torch.empty(*shape, device=device, dtype=dtype)
+    if t.numel():
+        with torch.cuda.device(t.device):
+            check(_lib.lib().bflow_zero(t.data_ptr(), t.numel() * t.element_size(), torch.cuda.current_stream(t.device).cuda_stream), 'zero')
+    return t
+
+
 def _on_tensor_device(fn):
     """Runs the wrapped operator with the device of its first CUDA tensor argument current: allocations, the stream handle and the
     `<<<>>>` launches inside the library all follow the CURRENT device, which need not be the tensors' device."""

@@ -3,7 +3,9 @@
 voxel_grid  : VoxelGrid.convert  (data/utils/representations.py:64-111)
 norm_voxel  : norm_voxel_grid    (data/utils/representations.py:9-18)
 epe_masked  : epe_masked         (utils/metrics.py:196-213)
-Pinned against the reference's own functions through tests/golden/events.npz (oracle/make_golden.py: make_events).
+flow_metrics: epe_masked, ae_masked (:259-296), n_pixel_error_masked (:161-193) and the linear-assumption prediction (:298-305)
+Pinned against the reference's own functions through tests/golden/events.npz and tests/golden/metrics.npz
+(oracle/make_golden.py: make_events, make_metrics).
 """
 import numpy as np
 
@@ -51,3 +53,24 @@ def epe_masked(src, tgt, valid=None):
     if valid is not None:
         e = e[np.asarray(valid).astype(bool)]
     return float(e.astype(np.float64).sum()), int(e.size)
+
+
+def flow_metrics(src, tgt, valid=None, n_pixels=(), scale=1.0):
+    """dict(epe, ae_deg, npe{n}: percent, count) of scale * src against tgt over the valid pixels; (N, C, *) arrays."""
+    src = np.asarray(src, np.float32) * np.float32(scale)
+    tgt = np.asarray(tgt, np.float32)
+    m = np.ones(src.shape[:1] + src.shape[2:], bool) if valid is None else np.asarray(valid).astype(bool)
+    e = np.sqrt(((src - tgt) ** 2).sum(1))
+    ext_s = np.concatenate([src, np.ones_like(src[:, :1])], 1)
+    ext_t = np.concatenate([tgt, np.ones_like(tgt[:, :1])], 1)
+    cs = (ext_s * ext_t).sum(1) / (np.linalg.norm(ext_s, axis=1) * np.linalg.norm(ext_t, axis=1))
+    ae = np.arccos(np.clip(cs, -1.0, 1.0))
+    n = int(m.sum())
+    out = {'count': n,
+           'epe': float(e[m].astype(np.float64).sum() / n) if n else None,
+           'ae_deg': float(ae[m].astype(np.float64).sum() / n / np.pi * 180) if n else float('nan')}
+    rel = e / np.clip(np.sqrt((tgt ** 2).sum(1)), 1e-6, None)
+    for k in n_pixels:
+        bad = (e > k) & (rel >= 0.05)
+        out[f'npe{k}'] = float(bad[m].sum() / n * 100) if n else float('nan')
+    return out

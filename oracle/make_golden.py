@@ -28,6 +28,10 @@ CASES = [
     ('m_128_i3_bn',     'E_I_LU5_BD10', 2, 128, 160, 3, 0, True,  'sparse_norm', False),
     ('d_480x640_i12',   'E_LU4_BD2',    1, 480, 640, 12, 0, True, 'sparse_norm', False),
     ('m_384x512_i12',   'E_I_LU5_BD10', 1, 384, 512, 12, 0, True, 'sparse_norm', False),
+    # BASELINE configs #3 (M at batch 4) and #4 (D at batch 4 per GPU): the batch-4 code paths (24-sample fnet, 12 288-row update
+    # block, per-pixel-walk lookup) at full size
+    ('m_384x512_i12_b4', 'E_I_LU5_BD10', 4, 384, 512, 12, 0, True, 'sparse_norm', False),
+    ('d_480x640_i12_b4', 'E_LU4_BD2',    4, 480, 640, 12, 0, True, 'sparse_norm', False),
 ]
 N_SAMPLES = 40000
 
@@ -136,12 +140,53 @@ def make_events():
     print('events ok', float(out_int.abs().sum()), float(out_flt.abs().sum()))
 
 
+def make_metrics():
+    """Reference utils/metrics.py functions (its only missing import, torchmetrics.Metric, is a base class of the Metric wrappers
+    around them and is shimmed by an empty class) on seeded flow pairs."""
+    import importlib
+    import types
+    ref_loader.load()
+    if 'torchmetrics' not in sys.modules:
+        tm = types.ModuleType('torchmetrics')
+        tm.Metric = type('Metric', (), {})
+        sys.modules['torchmetrics'] = tm
+    sys.path.insert(0, ref_loader.LIVE_ROOT)
+    M = importlib.import_module('utils.metrics')
+    g = torch.Generator().manual_seed(17)
+    N, H, W = 3, 40, 56
+    tgt = torch.randn(N, 2, H, W, generator=g) * 6
+    src = tgt + torch.randn(N, 2, H, W, generator=g) * torch.tensor([0.2, 2.0, 6.0]).view(3, 1, 1, 1)
+    tgt[0, :, :4] = 0                                   # zero ground truth: the relative-error clip path
+    valid = torch.rand(N, H, W, generator=g) > 0.3
+    ts = [0.2, 0.4, 0.6, 0.8, 1.0]
+    tgts = [tgt * t + 0.3 * torch.randn(N, 2, H, W, generator=g) for t in ts]
+    lin = M.predictions_from_lin_assumption(src, ts)
+    out = dict(src=src.numpy(), tgt=tgt.numpy(), valid=valid.numpy(), ts=np.array(ts), tgts=np.stack([t.numpy() for t in tgts]),
+               epe=float(M.epe_masked(src, tgt)), epe_v=float(M.epe_masked(src, tgt, valid)),
+               ae=float(M.ae_masked(src, tgt)), ae_v=float(M.ae_masked(src, tgt, valid)), ae_rad_v=float(M.ae_masked(src, tgt, valid, degrees=False)),
+               npe1=float(M.n_pixel_error_masked(src, tgt, None, 1)), npe2_v=float(M.n_pixel_error_masked(src, tgt, valid, 2)),
+               npe3_v=float(M.n_pixel_error_masked(src, tgt, valid, 3)),
+               epe_multi_lin=float(M.epe_masked_multi(lin, tgts)), ae_multi_lin=float(M.ae_masked_multi(lin, tgts)),
+               epe_multi_lin_v=float(M.epe_masked_multi(lin, tgts, [valid] * len(ts))),
+               ae_multi_lin_v=float(M.ae_masked_multi(lin, tgts, [valid] * len(ts))))
+    np.savez_compressed(os.path.join(GOLD, 'metrics.npz'), **out)
+    print('metrics ok', out['epe_v'], out['ae_v'], out['npe2_v'], out['epe_multi_lin'])
+
+
 if __name__ == '__main__':
-    assert ref_loader.available(), 'needs /root/reference (build container only)'
+    assert ref_loader.live(), 'needs /root/reference (build container only)'
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    make_bezier()
-    make_lookup()
-    make_events()
+    only = set(sys.argv[1:])
+    want = lambda name: not only or name in only
+    if want('bezier'):
+        make_bezier()
+    if want('lookup'):
+        make_lookup()
+    if want('events'):
+        make_events()
+    if want('metrics'):
+        make_metrics()
     for c in CASES:
-        make_case(*c)
+        if want(c[0]):
+            make_case(*c)
