@@ -61,15 +61,15 @@ __device__ __forceinline__ bool t3_mbar_test_wait(uint32_t bar, uint32_t parity)
 #define T3_CTA(i) do { if (p.cta != nullptr) p.cta[blockIdx.x * 16 + (i)] = global_ns(); } while (0)
 #define T3_TRACE(slot, idx) do { if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 256) p.trace[(slot) * 256 + (idx)] = clock64(); } while (0)
 // bounded: a protocol bug cannot hang the GPU.  After 2^24 failed polls (>= 0.3 s; no legitimate wait is longer than a few hundred
-// microseconds) the error word is set and the kernel traps: the launch fails loudly (cudaErrorLaunchFailure at the next
-// synchronisation) instead of carrying on with unfinished TMA / TMEM data.
+// microseconds) the error word is set and the role carries on, so the kernel still terminates; the result of that forward is
+// garbage and the HOST makes it loud: the engine copies the word back with every forward's outputs and raises (Engine._poll_err,
+// BezierCurves of a pipelined call, _Plan.check).  A __trap() here was measured: even out of line it costs 1.2 % of the whole
+// forward (4.18 -> 4.23 ms, code layout of the ~20 inlined waits), which buys nothing over the host-side check.
 __device__ __forceinline__ void t3_mbar_wait(uint32_t bar, uint32_t parity, int* err) {
 #pragma unroll 1
     for (uint32_t it = 0; it < (1u << 24); ++it)
         if (t3_mbar_try_wait(bar, parity)) return;
     if (err != nullptr) atomicExch(err, 1);
-    __threadfence_system();
-    __trap();
 }
 // one lane of a CONVERGED warp (elect.sync): the branch it guards is the idiom under which nvcc keeps warp-uniform operands in uniform
 // registers and issues UTCHMMA / UTCBAR directly.  Under `if (lane == 0)` it wraps every tcgen05.mma in an ELECT + 5 x R2UR + loop
@@ -181,7 +181,7 @@ struct T3Params {
     int dbg;      // development switch (bflow_tc3_debug): 1 = no TMA loads (the producer only arrives: MMA + epilogue path alone)
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool F16>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant__ CUtensorMap map0l, const __grid_constant__ CUtensorMap map1h,
                 const __grid_constant__ CUtensorMap map1l, const __grid_constant__ CUtensorMap omap_hi, const __grid_constant__ CUtensorMap omap_lo,
@@ -343,7 +343,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                             if (p.dbg & 1) {                 // development: no loads (MMA + epilogue path alone)
                                 t3_mbar_arrive(bar);
                             } else {
-                                if (p.f16) {             // hi plane and the hi half of the weight tile only
+                                if (F16) {               // hi plane and the hi half of the weight tile only
                                     t3_mbar_arrive_expect_tx(bar, T3_A_BYTES + B_BYTES);
                                     t3_tma_im2col(stage, src0 ? &map0h : &map1h, cc, cw, ch, n, (uint16_t)kw, (uint16_t)kh, bar);
                                     t3_bulk_g2s(stage + 2 * T3_A_BYTES, wt + (size_t)kb * (2 * B_BYTES), B_BYTES, bar);
@@ -425,7 +425,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t ko = (uint64_t)(k * 2);             // 32 bytes along K, in 16-byte descriptor units
-                        if (p.f16) {
+                        if (F16) {
                             t3_umma(tacc, dah0 + ko, dbh0 + ko, idesc, (kb > 0 || k > 0) ? 1u : 0u);       // hi*hi alone
                         } else if (STACK) {
                             t3_umma(tacc, dah0 + ko, dbh0 + ko, idesc2, (kb > 0 || k > 0) ? 1u : 0u);      // hi*hi | hi*lo
@@ -455,8 +455,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
         // 8 warps: quadrant (warp & 3) of the TMEM lanes = 32 tile rows, column half ((warp - 2) >> 2).  The tile's bias slice is
         // staged in shared memory once per n_tile; all tcgen05.ld of a thread's columns are issued before the single wait.
         constexpr int HALF = BN / 2;                  // columns per thread
-        const bool two_halves = STACK && !p.f16;      // the accumulator is [hi*hi + lo*hi | hi*lo]: the epilogue adds the halves
-        const bool wlo = !p.f16;                      // BFLOW_PREC_F16: nobody reads the lo planes, the hot store paths skip them
+        constexpr bool two_halves = STACK && !F16;    // the accumulator is [hi*hi + lo*hi | hi*lo]: the epilogue adds the halves
+        constexpr bool wlo = !F16;                    // BFLOW_PREC_F16: nobody reads the lo planes, the hot store paths skip them
         const int quad = warp & 3;
         const int chalf = (warp - 2) >> 2;
         const int etid = tid - 64;                   // 0 .. 255
@@ -1820,12 +1820,12 @@ static long long* g_tc3_trace = nullptr;
 static unsigned long long* g_tc3_cta = nullptr;
 static int g_tc3_cta_nth = -1, g_tc3_cta_span = 1, g_tc3_cta_count = 0;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool F16>
 static int launch_tc3(const CUtensorMap* maps, const bflow_conv_desc& d, const void* wtc, const T3Params& p, int* err, cudaStream_t stream) {      // maps: 4 input + 3 output
     constexpr int smem = t3_area_bytes(BN, STAGES) + 128 + 3 * BN * 4 + 64 + 1024;
     static PerDeviceFlag configured;
     if (!configured.get()) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, STAGES, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) {
             set_error(cudaGetErrorString(e));
             return BFLOW_ERR_CUDA;
@@ -1834,7 +1834,7 @@ static int launch_tc3(const CUtensorMap* maps, const bflow_conv_desc& d, const v
     }
     const int n_tiles = p.n_mtiles * p.n_ntiles;
     const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
-    cudaError_t le = launch_pdl(conv_tc3_kernel<BN, STAGES>, dim3(grid), dim3(T3_THREADS), smem, stream, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
+    cudaError_t le = launch_pdl(conv_tc3_kernel<BN, STAGES, F16>, dim3(grid), dim3(T3_THREADS), smem, stream, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
                                 maps[6], maps[7], maps[8], d, reinterpret_cast<const uint8_t*>(wtc), p, err);
     if (le != cudaSuccess) {
         set_error(cudaGetErrorString(le));
@@ -2144,12 +2144,23 @@ static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* om
             p.staged = 5;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    switch (bn) {
-        case 64: return bflow::launch_tc3<64, 4>(tm, d, w_tc, p, err, st);
-        case 128: return p.staged == 3 ? bflow::launch_tc3<128, 2>(tm, d, w_tc, p, err, st) : bflow::launch_tc3<128, 3>(tm, d, w_tc, p, err, st);
-        case 256: return bflow::launch_tc3<256, 2>(tm, d, w_tc, p, err, st);
-        default: bflow::set_error("conv_tc3: bn must be 64, 128 or 256"); return BFLOW_ERR_INVALID;
+    if (p.f16) {
+        switch (bn) {
+            case 64: return bflow::launch_tc3<64, 4, true>(tm, d, w_tc, p, err, st);
+            case 128: return p.staged == 3 ? bflow::launch_tc3<128, 2, true>(tm, d, w_tc, p, err, st) : bflow::launch_tc3<128, 3, true>(tm, d, w_tc, p, err, st);
+            case 256: return bflow::launch_tc3<256, 2, true>(tm, d, w_tc, p, err, st);
+            default: break;
+        }
+    } else {
+        switch (bn) {
+            case 64: return bflow::launch_tc3<64, 4, false>(tm, d, w_tc, p, err, st);
+            case 128: return p.staged == 3 ? bflow::launch_tc3<128, 2, false>(tm, d, w_tc, p, err, st) : bflow::launch_tc3<128, 3, false>(tm, d, w_tc, p, err, st);
+            case 256: return bflow::launch_tc3<256, 2, false>(tm, d, w_tc, p, err, st);
+            default: break;
+        }
     }
+    bflow::set_error("conv_tc3: bn must be 64, 128 or 256");
+    return BFLOW_ERR_INVALID;
 }
 
 extern "C" int bflow_conv2d_nhwc_tc3(const bflow_conv_desc* d, const void* maps, const void* w_tc, int bn, float acc_scale, int* err, void* stream) {

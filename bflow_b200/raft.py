@@ -279,6 +279,11 @@ class RAFTSpline(nn.Module):
             assert images is not None and len(images) == 2
         ref = voxel_grid if voxel_grid is not None else images[0]
         assert ref.shape[-2] % 8 == 0 and ref.shape[-1] % 8 == 0
+        # the coarsest pyramid level must keep at least 2 x 2 pixels: with a 1-pixel level the reference's bilinear_sampler divides by
+        # (W - 1) = 0 (models/raft_utils/utils.py:13-14) and returns NaN flow, so there is nothing to be equal to
+        lv = max(_cfg.levels_per_target(self.model_params))
+        assert min(ref.shape[-2], ref.shape[-1]) // 8 >> (lv - 1) >= 2, \
+            f'input {tuple(ref.shape[-2:])} too small for a {lv}-level correlation pyramid (the reference yields NaN here)'
         init = flow_init.get_params() if flow_init is not None else None
         if non_blocking:
             dev = next(self.parameters()).device

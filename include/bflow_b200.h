@@ -120,7 +120,8 @@ int bflow_conv2d_nhwc(const bflow_conv_desc* d, void* stream);
  * whose 16-byte chunks are XOR-swizzled by (row % 8), i.e. byte for byte the SWIZZLE_128B shared-memory tile
  * (bflow_b200/ops.py pack_conv_weight_tc); acc_scale (a power of two) is multiplied back onto the accumulator.
  * bn in {64,128,256}.  `err`: optional device int, set to 1 if an in-kernel pipeline wait timed out (never expected; the
- * waits are bounded so that a bug cannot hang the GPU; a CTA that times out stops issuing work and exits).
+ * waits are bounded so that a bug cannot hang the GPU).  The output of such a launch is invalid: the caller must read the word
+ * back (bflow_b200/engine.py does so with every forward's results and raises).
  * precision = BFLOW_PREC_F16 runs ONE tcgen05.mma per k-step on the hi planes / the hi half of the weight image. */
 /* TMA-fed, persistent tensor-core convolution.  Activations are read as split-fp16 planes (hi, lo) through
  * im2col tensor maps (cp.async.bulk.tensor.4d...im2col: the TMA unit does the implicit-GEMM gather and the zero padding),

@@ -167,9 +167,9 @@ def test_module_surface_and_state_dict_layout():
 def test_forward_refuses_cpu_tensors():
     net = RAFTSpline(config.preset('E_LU4_BD2'))
     with pytest.raises(RuntimeError, match='CUDA'):
-        net(voxel_grid=torch.zeros(1, 9, 64, 64), iters=1, test_mode=True)
+        net(voxel_grid=torch.zeros(1, 9, 128, 128), iters=1, test_mode=True)
     with pytest.raises(AssertionError):
-        net(voxel_grid=torch.zeros(1, 8, 64, 64), iters=1, test_mode=True)
+        net(voxel_grid=torch.zeros(1, 8, 128, 128), iters=1, test_mode=True)
     with pytest.raises(AssertionError):
         net(iters=1)
 
