@@ -142,6 +142,17 @@ __device__ __forceinline__ void t3_tmem_ld16_nowait(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 16 consecutive accumulator columns of this thread's TMEM lane (= tile row) <- registers
+__device__ __forceinline__ void t3_tmem_st16(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+        "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])),
+        "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
+        "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+
 __host__ __device__ constexpr int t3_area_bytes(int bn, int stages) {
     return bn <= 128 ? 224 * 1024 : stages * (2 * T3_A_BYTES + 2 * bn * 128);
 }
@@ -195,7 +206,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
     // instead of 3 (the single issuing thread, not the tensor pipe, is the limiter for small N).  The epilogue adds the two halves.
     constexpr bool STACK = BN <= 128;
     constexpr int ACC_COLS = STACK ? 2 * BN : BN;
-    constexpr int TMEM_COLS = 2 * ACC_COLS;                   // two accumulators
+    // two accumulators; 512 columns in every instantiation: single-tile GRU launches (staged 6) park their per-element operands behind
+    // accumulator 0 (BN = 64: 128 + 3 x 64 columns)
+    constexpr int TMEM_COLS = 512;
     // data area: the pipeline stages; for BN <= 128 it is stretched to 224 KB so that the bulk-copy epilogue of a single-tile CTA (below) can
     // park the fp32 tile and up to three operand tiles in it once the pipeline has drained
     constexpr int AREA_BYTES = t3_area_bytes(BN, STAGES);
@@ -467,6 +480,161 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                              (d.res == nullptr || (((d.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.res) & 15) == 0)));
         const float post = d.scale;
         const bool wide16 = d.y16_hi != nullptr && (d.ldy16 & 7) == 0 && ((reinterpret_cast<uintptr_t>(d.y16_hi) | reinterpret_cast<uintptr_t>(d.y16_lo)) & 15) == 0;
+        if (p.staged == 6) {
+            // GRU gate epilogues of a single-tile CTA (update.py:36-45), everything per-element fetched BEFORE the accumulator is ready.
+            // Measured (tools/timeline.py --cta-iter): the z|r and candidate launches spent 7-13 us after their last MMA, longer than
+            // their main loops, waiting for the hoisted term, h and z to arrive and walking staging tiles.  The 8 epilogue warps are idle
+            // while the pipeline fills and the MMAs run, and a single-tile CTA uses only one of the two TMEM accumulators.  So, right
+            // after the prologue, each thread loads its row's slices of the hoisted term `res`, of h (r gate) or of z and h (candidate)
+            // and parks them with tcgen05.st in the TMEM columns BEHIND accumulator 0 (thread = TMEM lane = tile row, the layout
+            // tcgen05.ld hands back): no registers held across the main loop, no shared memory (the pipeline owns it), and the slow
+            // row-wise loads (~3.6 us per 64 KB through the LSU) hide under the MMAs.  (Writing `res` into the accumulator itself and letting
+            // the MMAs add to it was measured first: it delays the first MMA by 1-3 us.)  After the last MMA only TMEM -> registers ->
+            // gate arithmetic -> SWIZZLE_128B boxes in the idle pipeline stages -> one thread issues the tensor-map stores remains.
+            // r itself is never stored (only r * h is consumed, update.py:39).
+            const int tile = blockIdx.x;
+            const int m_tile = tile / p.n_ntiles, n_tile = tile - m_tile * p.n_ntiles;
+            const int n0 = n_tile * BN, mt0 = m_tile * T3_BM;
+            const int row = quad * 32 + lane;
+            const int colbase = chalf * HALF;
+            const int mm = mt0 + row;
+            const bool row_ok = mm < p.M;
+            const bool is_zr = d.epi == BFLOW_EPI_GRU_ZR;
+            const int Cg = d.Cout >> 1;
+            const bool r_tile = is_zr && n0 >= Cg;
+            const int acol0 = is_zr ? n0 - Cg : n0;              // column of the aux0 / fp16 tile
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)colbase;
+            const uint32_t t_res = taddr + (uint32_t)ACC_COLS, t_a = t_res + (uint32_t)BN, t_y = t_a + (uint32_t)BN;      // parked operands
+            const bool hasA = r_tile || !is_zr, hasY = !is_zr;
+            // Parking one operand: the warp owns rows [quad*32, +32) x columns [colbase, +HALF) of the tile.  Loading thread = row would
+            // touch 32 different lines per instruction (measured: the LSU then moves ~9 B/clk and the TMA loads of the main loop
+            // queue behind it), so the warp loads PK_ROWS whole row slices per pass with lanes along the columns (a few full lines per
+            // instruction), bounces them through a private slab of the 32 KB of shared memory behind the pipeline stages, and every
+            // lane picks its own row up from there.
+            constexpr int PK_ROWS = 512 / HALF;               // rows per pass: 8 (BN 128), 16 (BN 64)
+            constexpr int PK_PITCH = HALF + 4;                // floats; +4 keeps the row-wise 16-byte reads conflict-free
+            constexpr int PK_C4 = HALF / 4;                   // float4 per row slice
+            float* pk = reinterpret_cast<float*>(smem_raw + (smem_base - t3_smem_u32(smem_raw)) + STAGES * STAGE_BYTES) + (warp - 2) * (PK_ROWS * PK_PITCH);
+            static_assert(STAGES * STAGE_BYTES + T3_EPI_WARPS * PK_ROWS * PK_PITCH * 4 <= AREA_BYTES || BN > 128, "operand bounce buffer does not fit behind the stages");
+            auto park = [&](const float* gtile, int ldg, uint32_t tdst) {      // gtile: (row mt0, column of this warp's slice)
+                float v[HALF];
+#pragma unroll
+                for (int pass = 0; pass < 32 / PK_ROWS; ++pass) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int idx = i * 32 + lane;
+                        const int rr = idx / PK_C4, c4 = idx - rr * PK_C4;
+                        const int gr = quad * 32 + pass * PK_ROWS + rr;
+                        const float4 x4 = (mt0 + gr < p.M) ? *reinterpret_cast<const float4*>(gtile + (size_t)gr * ldg + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        *reinterpret_cast<float4*>(pk + rr * PK_PITCH + c4 * 4) = x4;
+                    }
+                    __syncwarp();
+                    if (lane / PK_ROWS == pass) {
+                        const float* prow = pk + (lane - pass * PK_ROWS) * PK_PITCH;
+#pragma unroll
+                        for (int c = 0; c < HALF; c += 4) {
+                            const float4 x4 = *reinterpret_cast<const float4*>(prow + c);
+                            v[c] = x4.x; v[c + 1] = x4.y; v[c + 2] = x4.z; v[c + 3] = x4.w;
+                        }
+                    }
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int c = 0; c < HALF; c += 16) t3_tmem_st16(tdst + (uint32_t)c, v + c);
+            };
+            if (BN <= 128) {
+                park(d.res + (size_t)mt0 * d.ldr + n0 + colbase, d.ldr, t_res);
+                if (hasA) park(d.aux0 + (size_t)mt0 * d.ld_aux0 + acol0 + colbase, d.ld_aux0, t_a);
+                if (hasY) park(d.y + (size_t)mt0 * d.ldy + n0 + colbase, d.ldy, t_y);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            uint8_t* sb = smem_raw + (smem_base - t3_smem_u32(smem_raw));
+            constexpr int NB16 = (BN + 63) / 64, NB32 = (BN + 31) / 32;
+            uint8_t* s_32 = sb;                                  // fp32 boxes (z, or the new h)
+            uint8_t* s_hi = sb + NB32 * 16384;
+            uint8_t* s_lo = s_hi + NB16 * 16384;
+            const bool out32 = !r_tile;
+            const bool out16 = is_zr ? r_tile : d.y16_hi != nullptr;
+            t3_mbar_wait(tfull_bar(0), 0u, err);
+            t3_fence_after();
+            if (warp == 2 && lane == 0) T3_CTA(5);
+#pragma unroll 1
+            for (int c0 = 0; c0 < HALF; c0 += 16) {
+                float v[16], rs[16], av[16], yv[16];
+                t3_tmem_ld16_nowait(taddr + (uint32_t)c0, v);
+                t3_tmem_ld16_nowait(t_res + (uint32_t)c0, rs);
+                if (hasA) t3_tmem_ld16_nowait(t_a + (uint32_t)c0, av);
+                if (hasY) t3_tmem_ld16_nowait(t_y + (uint32_t)c0, yv);
+                if (two_halves) {
+                    float u[16];
+                    t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0), u);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) v[c] += u[c];
+                } else {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                }
+                float h[16];
+                if (is_zr) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        v[c] = fast_sigmoid(fmaf(v[c], p.acc_scale, rs[c]));
+                        h[c] = hasA ? v[c] * av[c] : 0.f;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        v[c] = (1.f - av[c]) * yv[c] + av[c] * fast_tanh(fmaf(v[c], p.acc_scale, rs[c]));
+                        h[c] = v[c];
+                    }
+                }
+                const int col = colbase + c0;
+                if (out32) {
+                    uint8_t* b3 = s_32 + (col >> 5) * 16384 + row * 128;
+#pragma unroll
+                    for (int c = 0; c < 16; c += 4) {
+                        const int chunk = (((col & 31) + c) >> 2) ^ (row & 7);
+                        *reinterpret_cast<float4*>(b3 + (chunk << 4)) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                    }
+                }
+                if (out16) {
+                    uint8_t* bh = s_hi + (col >> 6) * 16384 + row * 128;
+                    uint8_t* bl = s_lo + (col >> 6) * 16384 + row * 128;
+#pragma unroll
+                    for (int c = 0; c < 16; c += 8) {
+                        uint4 h4, l4;
+                        split2(h[c], h[c + 1], h4.x, l4.x);
+                        split2(h[c + 2], h[c + 3], h4.y, l4.y);
+                        split2(h[c + 4], h[c + 5], h4.z, l4.z);
+                        split2(h[c + 6], h[c + 7], h4.w, l4.w);
+                        const int chunk = (((col & 63) + c) >> 3) ^ (row & 7);
+                        *reinterpret_cast<uint4*>(bh + (chunk << 4)) = h4;
+                        if (wlo) *reinterpret_cast<uint4*>(bl + (chunk << 4)) = l4;
+                    }
+                }
+            }
+            if (warp == 2 && lane == 0) T3_CTA(8);
+            t3_fence_before();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (warp == 2 && t3_elect_one()) {
+                if (out32) {
+#pragma unroll
+                    for (int b = 0; b < NB32; ++b) t3_tma_store2d(&omap32, t3_smem_u32(s_32 + b * 16384), n0 + b * 32, mt0);
+                }
+                if (out16) {
+#pragma unroll
+                    for (int b = 0; b < NB16; ++b) {
+                        t3_tma_store2d(&omap_hi, t3_smem_u32(s_hi + b * 16384), acol0 + b * 64, mt0);
+                        if (wlo) t3_tma_store2d(&omap_lo, t3_smem_u32(s_lo + b * 16384), acol0 + b * 64, mt0);
+                    }
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the boxes have left shared memory; the writes complete with the grid
+            }
+            __syncwarp();
+            if (warp == 2 && lane == 0) T3_CTA(6);
+        } else {
         uint32_t lt = 0;
         int bias_tile = -1;
         // fused InstanceNorm statistics: per-CTA partial (sum, sum of squares) of the current image in shared memory, flushed with
@@ -1222,6 +1390,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
         }
         if (d.stats != nullptr) flush_stats(cur_img, stat_n0);
         if (p.staged == 3) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
     }
     __syncthreads();
     if (tid == 0) T3_TRACE(4, 255);              // CTA end
@@ -2137,8 +2306,19 @@ static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* om
             gru_tma = (e != nullptr && e[0] == '1') ? 1 : 0;      // opt-in: measured equal to the per-row bulk / batched-load epilogues -- the 8-12 operand
                                                                     // boxes arrive as 128-byte rows (~4 cycles each through the TMA unit), 6 us before the first use
         }
+        // staged 6: GRU gate epilogues with the hoisted term pre-loaded into the accumulator and h / z prefetched into registers (default)
+        static int gru6 = -1;
+        if (gru6 < 0) {
+            const char* e = getenv("BFLOW_TC3_GRU6");
+            gru6 = (e != nullptr && e[0] == '0') ? 0 : 1;
+        }
+        auto a16_ = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+        if (gru6 && ostore_on && single1 && !slab && bn <= 128 && d.epi != BFLOW_EPI_STD && d.Cout % bn == 0 && d.bias == nullptr && d.scale == 1.f &&
+            d.res != nullptr && a16_(d.res) && d.ldr % 4 == 0 && d.y != nullptr && a16_(d.y) && d.ldy % 4 == 0 && a16_(d.aux0) && d.ld_aux0 % 4 == 0 &&
+            (d.epi == BFLOW_EPI_GRU_Q ? (bn == 64 && d.y16_hi != nullptr) : ((d.Cout / 2) % bn == 0 && d.aux1 == nullptr && d.aux1_16_hi != nullptr)))
+            p.staged = 6;
         const int regions = d.epi == BFLOW_EPI_GRU_Q ? 3 : 2;
-        if (gru_tma && ostore_on && single1 && !slab && bn <= 128 && d.epi != BFLOW_EPI_STD && d.Cout % bn == 0 && d.y != nullptr && d.res != nullptr &&
+        if (p.staged != 6 && gru_tma && ostore_on && single1 && !slab && bn <= 128 && d.epi != BFLOW_EPI_STD && d.Cout % bn == 0 && d.y != nullptr && d.res != nullptr &&
             (d.epi == BFLOW_EPI_GRU_Q ? d.y16_hi != nullptr : ((d.Cout / 2) % bn == 0 && d.aux1 == nullptr && d.aux1_16_hi != nullptr)) &&
             (regions * ((bn + 31) / 32) + 2 * ((bn + 63) / 64)) * 16384 <= bflow::t3_area_bytes(bn, 0))
             p.staged = 5;

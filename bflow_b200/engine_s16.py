@@ -145,8 +145,8 @@ class S16Recorder:
                 self.n_tc += 1
                 return Ho, Wo
         if (epi in ('gru_zr', 'gru_q') and res is not None and y is not None and wt.cout % bn == 0 and (M + 127) // 128 * (wt.cout // bn) <= 148 and
-                ldy % 4 == 0 and ldr % 4 == 0 and ld_aux0 % 4 == 0 and os.environ.get('BFLOW_TC3_GRU_TMA', '0') == '1'):
-            # GRU gate epilogues on tensor maps: {fp16 hi, fp16 lo, y fp32, res, aux0}
+                ldy % 4 == 0 and ldr % 4 == 0 and ld_aux0 % 4 == 0):
+            # GRU gate epilogues leave through tensor-map stores: {fp16 hi, fp16 lo, y fp32, res, aux0} (the last two only for BFLOW_TC3_GRU_TMA=1)
             t16 = aux1_16 if epi == 'gru_zr' else y16
             hdim = wt.cout // 2 if epi == 'gru_zr' else wt.cout
             if t16 is not None and t16[0].ld % 8 == 0 and hdim % 8 == 0:
