@@ -275,6 +275,25 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// Division of a 32-bit unsigned by a launch-time constant without the ~150-cycle IDIV sequence (Granlund-Montgomery): the host
+// precomputes (mul, shift), the device spends a multiply-high, a subtract and two shifts.  Exact for every 32-bit dividend.
+struct FastDiv {
+    unsigned mul, shift, d;
+};
+__host__ inline FastDiv make_fastdiv(unsigned d) {
+    FastDiv f;
+    f.d = d < 1u ? 1u : d;
+    unsigned l = 0;
+    while ((1ull << l) < f.d) ++l;                       // ceil(log2 d)
+    f.shift = l;
+    f.mul = (unsigned)(((1ull << 32) * ((1ull << l) - f.d)) / f.d + 1ull);
+    return f;
+}
+__device__ __forceinline__ unsigned fastdiv(unsigned n, const FastDiv& f) {
+    const unsigned t = __umulhi(n, f.mul);
+    return f.shift == 0 ? n : (t + ((n - t) >> 1)) >> (f.shift - 1);
+}
+
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ __forceinline__ long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

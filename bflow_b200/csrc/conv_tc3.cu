@@ -188,6 +188,7 @@ struct T3Params {
     // along the other axis (see conv_slab64_kernel).  1: slab rows = (y, x) with x fastest (taps along y), 2: rows = (x, y) (taps along x).
     int slab, tiles_x, tiles_y, n_slabs, tps;
     int f16;      // BFLOW_PREC_F16: one MMA per k-step on the hi planes (lo planes / the lo half of the weight tiles are not loaded)
+    FastDiv fd_ntiles, fd_wo, fd_ho;      // tile -> (m_tile, n_tile), first output pixel -> (n, oh, ow) on the producer's critical path
     int staged;   // every CTA owns exactly one tile: the epilogue goes through shared memory (coalesced, batched global accesses)
     int dbg;      // development switch (bflow_tc3_debug): 1 = no TMA loads (the producer only arrives: MMA + epilogue path alone)
 };
@@ -237,14 +238,43 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
 
     if (tid == 0) T3_TRACE(5, 255);              // CTA start
     if (tid == 0) T3_CTA(0);
-    if (tid == 32) {                             // descriptor fetch overlaps barrier init / TMEM allocation
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map0h)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map0l)) : "memory");
-        if (p.ncb1 > 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map1h)) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map1l)) : "memory");
+    tl_begin(p.tl);
+    // Prologue.  The producer warp only needs the mbarriers: it initialises them, signals named barrier 2 WITHOUT waiting and goes
+    // straight to its first TMA issue, while warp 1 allocates TMEM (~0.3 us) and everybody else waits on barrier 2 for both.  Measured
+    // before: first TMA issue 1.25 us after the CTA start (0.5 us of common prologue + 0.7 us of integer divisions in the producer).
+    uint32_t tmem_base = 0;
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map0h)) : "memory");
+            if (!F16) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map0l)) : "memory");
+            if (p.ncb1 > 0) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map1h)) : "memory");
+                if (!F16) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map1l)) : "memory");
+            }
+            for (int s = 0; s < 4; ++s) {
+                t3_mbar_init(full_bar(s), 1);      // the producer's arrive.expect_tx (+ TMA bytes)
+                t3_mbar_init(empty_bar(s), 1);     // one tcgen05.commit
+            }
+            for (int s = 0; s < SL_NSA; ++s) {
+                t3_mbar_init(afull_bar(s), 1);
+                t3_mbar_init(aempty_bar(s), 1);
+            }
+            t3_mbar_init(ebar, 1);
+            for (int a = 0; a < 2; ++a) {
+                t3_mbar_init(tfull_bar(a), 1);     // one tcgen05.commit
+                t3_mbar_init(tempty_bar(a), T3_EPI_WARPS);    // one arrive per epilogue warp
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        if (p.staged >= 4) {                     // tensor-map epilogues: their descriptors too (a cold descriptor costs ~1 us at first use)
+        __threadfence_block();
+        __syncwarp();
+        asm volatile("bar.arrive 2, %0;" ::"n"(T3_THREADS) : "memory");
+    } else {
+        if (warp == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        if (tid == 64 && p.staged >= 4) {        // tensor-map epilogues: their descriptors (a cold descriptor costs ~1 us at first use)
             if (d.y16_hi != nullptr || d.aux1_16_hi != nullptr) {
                 asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&omap_hi)) : "memory");
                 asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&omap_lo)) : "memory");
@@ -255,33 +285,11 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&amap)) : "memory");
             }
         }
+        t3_fence_before();
+        asm volatile("bar.sync 2, %0;" ::"n"(T3_THREADS) : "memory");
+        t3_fence_after();
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     }
-    tl_begin(p.tl);
-    if (tid == 0) {
-        for (int s = 0; s < 4; ++s) {
-            t3_mbar_init(full_bar(s), 1);      // the producer's arrive.expect_tx (+ TMA bytes)
-            t3_mbar_init(empty_bar(s), 1);     // one tcgen05.commit
-        }
-        for (int s = 0; s < SL_NSA; ++s) {
-            t3_mbar_init(afull_bar(s), 1);
-            t3_mbar_init(aempty_bar(s), 1);
-        }
-        t3_mbar_init(ebar, 1);
-        for (int a = 0; a < 2; ++a) {
-            t3_mbar_init(tfull_bar(a), 1);     // one tcgen05.commit
-            t3_mbar_init(tempty_bar(a), T3_EPI_WARPS);    // one arrive per epilogue warp
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    t3_fence_before();
-    __syncthreads();
-    t3_fence_after();
-    uint32_t tmem_base;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     // PDL: everything above touched only shared memory / TMEM; let the next kernel's CTAs set themselves up on idle SMs, then
     // wait for the previous kernel's results before the first global access
     pdl_trigger();
@@ -329,17 +337,20 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
             // converged warp: every lane waits on the stage barrier, one elected lane issues (operands stay in uniform registers)
             uint32_t it = 0, ps_ = 0, pph = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int m_tile = tile / p.n_ntiles, n_tile = tile - m_tile * p.n_ntiles;
+                const int m_tile = (int)fastdiv((unsigned)tile, p.fd_ntiles), n_tile = tile - m_tile * p.n_ntiles;
                 const int m0 = m_tile * T3_BM;
-                const int ow = m0 % d.Wo;
-                const int t = m0 / d.Wo;
-                const int oh = t % d.Ho;
-                const int n = t / d.Ho;
+                const int t = (int)fastdiv((unsigned)m0, p.fd_wo);
+                const int ow = m0 - t * d.Wo;
+                const int n = (int)fastdiv((unsigned)t, p.fd_ho);
+                const int oh = t - n * d.Ho;
                 const int cw = ow * d.stride - d.pad_w, ch = oh * d.stride - d.pad_h;
                 const uint8_t* wt = wtc + (size_t)n_tile * p.nkb * (2 * B_BYTES);
-                int kb = 0;
-                for (int tap = 0; tap < p.ntaps; ++tap) {
-                    const int kh = tap / d.KW, kw = tap - kh * d.KW;
+                int kb = 0, kh = 0, kw = 0;
+                for (int tap = 0; tap < p.ntaps; ++tap, ++kw) {
+                    if (kw == d.KW) {
+                        kw = 0;
+                        ++kh;
+                    }
                     for (int cb = 0; cb < p.ncb0 + p.ncb1; ++cb, ++kb, ++it) {
                         const int s = (int)ps_;
                         t3_mbar_wait(empty_bar(s), pph ^ 1u, err);
@@ -2211,6 +2222,9 @@ static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* om
         p.n_mtiles = (int)nm;
     }
     p.n_ntiles = (d.Cout + bn - 1) / bn;
+    p.fd_ntiles = bflow::make_fastdiv((unsigned)p.n_ntiles);
+    p.fd_wo = bflow::make_fastdiv((unsigned)d.Wo);
+    p.fd_ho = bflow::make_fastdiv((unsigned)d.Ho);
     p.ntaps = d.KH * d.KW;
     p.ncb0 = (d.c0 + 63) / 64;
     p.ncb1 = (d.c1 + 63) / 64;

@@ -158,6 +158,12 @@ __global__ void __launch_bounds__(LK_WARPS * 32) corr_lookup_kernel(const bflow_
 constexpr int LK2_WARPS = 8;
 constexpr int LK2_PITCH = 20;      // floats per patch row in shared memory (16 used; 20 spreads the tap reads over banks)
 
+// Host-precomputed divisors (query pixel index -> sample, row, column; unit index -> pixel, slot): the integer divisions were a
+// quarter of the 346 instructions per unit that made this kernel issue-bound (ncu, round 1: 80 % issue slots busy at 38 % DRAM).
+struct LookupDivs {
+    FastDiv S, Q, w;
+};
+
 // one unit = (query pixel bq, slot): fetch the 3x3..4x4 tiles under the 10x10 window, blend the 81 taps, store them
 __device__ __forceinline__ void lookup_unit(const bflow_lookup_desc& d, const unsigned bq, const unsigned b, const unsigned q, const float gx,
                                             const float gy, const int slot, float* ps, const int (&soff)[3], const int lane, const int Q) {
@@ -173,11 +179,20 @@ __device__ __forceinline__ void lookup_unit(const bflow_lookup_desc& d, const un
     } else {
         // coords1 = pixel grid + sum_i coef[t][i] * P_i   (raft.py:180-181, bezier.py:165-186)
         const float* prm = d.params + (size_t)bq * d.params_ld;
-        float fxv = 0.f, fyv = 0.f;
-        for (int k = 0; k < d.degree; ++k) {
-            const float ck = d.coef[t][k];
-            fxv = fmaf(ck, __ldg(prm + k), fxv);
-            fyv = fmaf(ck, __ldg(prm + d.degree + k), fyv);
+        float fxv, fyv;
+        if (d.degree == 2 && (d.params_ld & 3) == 0) {    // [P1x P2x P1y P2y]: one 16-byte load (host contract: 16-byte aligned rows)
+            const float4 p4 = *reinterpret_cast<const float4*>(prm);
+            const float c0 = d.coef[t][0], c1 = d.coef[t][1];
+            fxv = fmaf(c1, p4.y, c0 * p4.x);
+            fyv = fmaf(c1, p4.w, c0 * p4.z);
+        } else {
+            fxv = 0.f;
+            fyv = 0.f;
+            for (int k = 0; k < d.degree; ++k) {
+                const float ck = d.coef[t][k];
+                fxv = fmaf(ck, prm[k], fxv);
+                fyv = fmaf(ck, prm[d.degree + k], fyv);
+            }
         }
         cx = gx + fxv;
         cy = gy + fyv;
@@ -197,10 +212,11 @@ __device__ __forceinline__ void lookup_unit(const bflow_lookup_desc& d, const un
     float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
     {
         const int txx = tx0 + tcA;
-        const bool colok = tcA < ntx && txx >= 0 && txx < tw;
-        const int tya = ty0 + trA, tyb = ty0 + trA + 2;
-        if (colok && tya >= 0 && tya < th) va = __ldg(reinterpret_cast<const float4*>(pl + ((tya * tw + txx) << 4) + (rrA << 2)));
-        if (colok && (trA + 2) < nty && tyb >= 0 && tyb < th) vb = __ldg(reinterpret_cast<const float4*>(pl + ((tyb * tw + txx) << 4) + (rrA << 2)));
+        const bool colok = tcA < ntx && (unsigned)txx < (unsigned)tw;
+        const int tya = ty0 + trA, tyb = tya + 2;
+        const float* pa = pl + ((tya * tw + txx) << 4) + (rrA << 2);
+        if (colok && (unsigned)tya < (unsigned)th) va = __ldg(reinterpret_cast<const float4*>(pa));
+        if (colok && (trA + 2) < nty && (unsigned)tyb < (unsigned)th) vb = __ldg(reinterpret_cast<const float4*>(pa + (tw << 5)));
     }
     __syncwarp();                                     // previous unit's tap reads are done
     *reinterpret_cast<float4*>(ps + rgA * LK2_PITCH + tcA * 4) = va;
@@ -208,18 +224,35 @@ __device__ __forceinline__ void lookup_unit(const bflow_lookup_desc& d, const un
     __syncwarp();
     const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
     const float* f0 = ps + oy * LK2_PITCH + ox;
+    float val[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        if (lane + 32 * j < 81) {
-            const float* f = f0 + soff[j];
-            const float val = w00 * f[0] + w01 * f[1] + w10 * f[LK2_PITCH] + w11 * f[LK2_PITCH + 1];
-            if (d.out16_hi != nullptr) {
-                const size_t e = (size_t)bq * d.out16_ld + slot * 81 + lane + 32 * j;
-                if (d.out16_lo != nullptr) store_split1(d.out16_hi, d.out16_lo, e, val);
-                else reinterpret_cast<__half*>(d.out16_hi)[e] = __float2half_rn(fminf(fmaxf(val, -65504.f), 65504.f));      // BFLOW_PREC_F16 consumers
-            } else
-                d.out[(size_t)bq * d.out_ld + slot * 81 + lane + 32 * j] = val;
+        const float* f = f0 + soff[j];                // j == 2: lanes >= 17 read inside the patch (soff clamped) and do not store
+        val[j] = w00 * f[0] + w01 * f[1] + w10 * f[LK2_PITCH] + w11 * f[LK2_PITCH + 1];
+    }
+    if (d.out16_hi != nullptr) {
+        const size_t e = (size_t)bq * d.out16_ld + slot * 81 + lane;
+        __half* ph = reinterpret_cast<__half*>(d.out16_hi) + e;
+        if (d.out16_lo != nullptr) {
+            __half* plo = reinterpret_cast<__half*>(d.out16_lo) + e;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                if (j < 2 || lane < 17) {
+                    const __half h = __float2half_rn(fminf(fmaxf(val[j], -65504.f), 65504.f));
+                    ph[32 * j] = h;
+                    plo[32 * j] = __float2half_rn(val[j] - __half2float(h));
+                }
+            }
+        } else {                                      // BFLOW_PREC_F16 consumers: hi plane only
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                if (j < 2 || lane < 17) ph[32 * j] = __float2half_rn(fminf(fmaxf(val[j], -65504.f), 65504.f));
         }
+    } else {
+        float* po = d.out + (size_t)bq * d.out_ld + slot * 81 + lane;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if (j < 2 || lane < 17) po[32 * j] = val[j];
     }
 }
 
@@ -228,7 +261,8 @@ __device__ __forceinline__ void lookup_unit(const bflow_lookup_desc& d, const un
 // FLAT = true:  units (pixel, slot) are dealt round-robin to the warps of a one-wave grid -- the batch-1 regime, where the launch is a few
 //               latency chains long and an uneven tail (a partial second wave of CTAs) would double it.
 template <bool FLAT>
-__global__ void __launch_bounds__(LK2_WARPS * 32) corr_lookup_tiled_kernel(const bflow_lookup_desc d, const long long n_units, const int slots_per_group, unsigned long long* tl) {
+__global__ void __launch_bounds__(LK2_WARPS * 32) corr_lookup_tiled_kernel(const bflow_lookup_desc d, const LookupDivs dv, const long long n_units, const int slots_per_group,
+                                                                           unsigned long long* tl) {
     __shared__ __align__(16) float patch[LK2_WARPS][16 * LK2_PITCH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = d.n_slots;
@@ -240,7 +274,7 @@ __global__ void __launch_bounds__(LK2_WARPS * 32) corr_lookup_tiled_kernel(const
     int soff[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        const int k = lane + 32 * j;
+        const int k = min(lane + 32 * j, 80);
         const int iy = k / 9, ix = k - iy * 9;
         soff[j] = iy * LK2_PITCH + ix;
     }
@@ -248,19 +282,19 @@ __global__ void __launch_bounds__(LK2_WARPS * 32) corr_lookup_tiled_kernel(const
         const unsigned nu = (unsigned)n_units, nw = gridDim.x * LK2_WARPS;
 #pragma unroll 1
         for (unsigned u = blockIdx.x * LK2_WARPS + warp; u < nu; u += nw) {
-            const unsigned bq = u / (unsigned)S;
+            const unsigned bq = fastdiv(u, dv.S);
             const int slot = (int)(u - bq * (unsigned)S);
-            const unsigned b = bq / (unsigned)Q;
+            const unsigned b = fastdiv(bq, dv.Q);
             const unsigned q = bq - b * (unsigned)Q;
-            const unsigned qy = q / (unsigned)d.w;
+            const unsigned qy = fastdiv(q, dv.w);
             lookup_unit(d, bq, b, q, (float)(q - qy * (unsigned)d.w), (float)qy, slot, ps, soff, lane, Q);
         }
     } else {
         const unsigned n_bq = (unsigned)(n_units / S);
         for (unsigned bq = blockIdx.x * LK2_WARPS + warp; bq < n_bq; bq += gridDim.x * LK2_WARPS) {
-            const unsigned b = bq / (unsigned)Q;
+            const unsigned b = fastdiv(bq, dv.Q);
             const unsigned q = bq - b * (unsigned)Q;
-            const unsigned qy = q / (unsigned)d.w;
+            const unsigned qy = fastdiv(q, dv.w);
             const float gx = (float)(q - qy * (unsigned)d.w), gy = (float)qy;
             const int s_beg = (int)blockIdx.y * slots_per_group, s_end = min(S, s_beg + slots_per_group);
             // (a two-deep software pipeline over the slots was measured 10 % slower: 60 registers cost more occupancy than the
@@ -306,12 +340,18 @@ extern "C" int bflow_corr_lookup(const bflow_lookup_desc* dp, void* stream) {
         const int sms = bflow::num_sms();
         cudaError_t le;
         unsigned long long* tls = bflow::timeline_next_slot("corr_lookup");
+        bflow::LookupDivs dv;
+        dv.S = bflow::make_fastdiv((unsigned)d.n_slots);
+        dv.Q = bflow::make_fastdiv((unsigned)(d.h * d.w));
+        dv.w = bflow::make_fastdiv((unsigned)d.w);
+        BFLOW_REQUIRE(d.params == nullptr || d.degree != 2 || (d.params_ld & 3) != 0 || (reinterpret_cast<uintptr_t>(d.params) & 15) == 0,
+                      "lookup: degree-2 Bezier parameters with a row stride that is a multiple of 4 floats must be 16-byte aligned");
         const long long resident_warps = (long long)sms * occ * bflow::LK2_WARPS;
         if (mode == 1 && n_units <= 8 * resident_warps) {
             // one wave of CTAs, units dealt round-robin (at most 8 units per warp; beyond that the per-pixel walk below is as balanced)
             long long g = bflow::ceil_div_ll(n_units, bflow::LK2_WARPS);
             if (g > (long long)sms * occ) g = (long long)sms * occ;
-            le = bflow::launch_pdl(bflow::corr_lookup_tiled_kernel<true>, dim3((unsigned)g), dim3(bflow::LK2_WARPS * 32), 0, (cudaStream_t)stream, d, n_units, 0, tls);
+            le = bflow::launch_pdl(bflow::corr_lookup_tiled_kernel<true>, dim3((unsigned)g), dim3(bflow::LK2_WARPS * 32), 0, (cudaStream_t)stream, d, dv, n_units, 0, tls);
         } else {
             long long g = bflow::ceil_div_ll(BQ, bflow::LK2_WARPS);
             const long long cap = (long long)sms * 8 * 8;
@@ -322,7 +362,7 @@ extern "C" int bflow_corr_lookup(const bflow_lookup_desc* dp, void* stream) {
             if (groups > d.n_slots) groups = d.n_slots;
             const int spg = (int)bflow::ceil_div_ll(d.n_slots, groups);
             dim3 grid2((unsigned)g, (unsigned)bflow::ceil_div(d.n_slots, spg));
-            le = bflow::launch_pdl(bflow::corr_lookup_tiled_kernel<false>, grid2, dim3(bflow::LK2_WARPS * 32), 0, (cudaStream_t)stream, d, n_units, spg, tls);
+            le = bflow::launch_pdl(bflow::corr_lookup_tiled_kernel<false>, grid2, dim3(bflow::LK2_WARPS * 32), 0, (cudaStream_t)stream, d, dv, n_units, spg, tls);
         }
         if (le != cudaSuccess) {
             bflow::set_error(cudaGetErrorString(le));

@@ -45,7 +45,9 @@ bool pdl_enabled() {
     static int on = -1;
     if (on < 0) {
         const char* e = getenv("BFLOW_PDL");
-        on = (e != nullptr && strcmp(e, "1") == 0) ? 1 : 0;      // measured on B200: no gain inside the captured graph, so opt-in
+        // on by default: measured on B200 inside the captured graph, 3.875 -> 3.762 ms per forward (the update block's launches fill at
+        // most 114 of 148 SMs, so the next kernel's CTAs run their prologue on the idle ones and sit in griddepcontrol.wait)
+        on = (e != nullptr && strcmp(e, "0") == 0) ? 0 : 1;
     }
     return on == 1;
 }
