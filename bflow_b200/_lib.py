@@ -67,12 +67,31 @@ class LookupDesc(_Desc):
                 ('tiled', C.c_int)]
 
 
+class LookupOtfDesc(_Desc):
+    _fields_ = [('struct_size', C.c_int),
+                ('n_slots', C.c_int), ('n_targets', C.c_int), ('B', C.c_int), ('h', C.c_int), ('w', C.c_int), ('radius', C.c_int), ('D', C.c_int),
+                ('f1', C.c_void_p * MAX_SLOTS), ('ld1', C.c_int),
+                ('f2', C.c_void_p * MAX_SLOTS), ('ld2', C.c_int),
+                ('hl', C.c_int * MAX_SLOTS), ('wl', C.c_int * MAX_SLOTS),
+                ('target', C.c_int * MAX_SLOTS),
+                ('inv_scale', C.c_float * MAX_SLOTS),
+                ('scale', C.c_float),
+                ('coords', C.c_void_p),
+                ('params', C.c_void_p), ('params_ld', C.c_int), ('degree', C.c_int),
+                ('coef', (C.c_float * MAX_DEGREE) * MAX_TARGETS),
+                ('out', C.c_void_p), ('out_ld', C.c_int),
+                ('out16_hi', C.c_void_p), ('out16_lo', C.c_void_p), ('out16_ld', C.c_int)]
+
+
 _SIGNATURES = {
     'bflow_abi_version': (C.c_int, []),
     'bflow_last_error': (C.c_char_p, []),
     'bflow_built_for_sm': (C.c_int, []),
     'bflow_sizeof_conv_desc': (C.c_int, []),
     'bflow_sizeof_lookup_desc': (C.c_int, []),
+    'bflow_sizeof_lookup_otf_desc': (C.c_int, []),
+    'bflow_corr_lookup_otf': (C.c_int, [C.POINTER(LookupOtfDesc), C.c_void_p]),
+    'bflow_feat_pool': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
     'bflow_source_hash': (C.c_char_p, []),
     'bflow_zero': (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_void_p]),
     'bflow_nchw_to_nhwc': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_float, C.c_float, C.c_void_p]),
@@ -134,7 +153,8 @@ def lib() -> C.CDLL:
             fn.argtypes = args
         if handle.bflow_abi_version() != ABI_VERSION:
             raise RuntimeError(f'libbflow_b200.so has ABI version {handle.bflow_abi_version()}, this binding needs {ABI_VERSION}')
-        if (handle.bflow_sizeof_conv_desc(), handle.bflow_sizeof_lookup_desc()) != (C.sizeof(ConvDesc), C.sizeof(LookupDesc)):
+        if ((handle.bflow_sizeof_conv_desc(), handle.bflow_sizeof_lookup_desc(), handle.bflow_sizeof_lookup_otf_desc()) !=
+                (C.sizeof(ConvDesc), C.sizeof(LookupDesc), C.sizeof(LookupOtfDesc))):
             raise RuntimeError('descriptor layouts of libbflow_b200.so and bflow_b200/_lib.py differ')
         if handle.bflow_source_hash().decode() != _build.source_hash():
             raise RuntimeError('libbflow_b200.so was not built from the sources in this tree (python -m bflow_b200.build --force)')

@@ -53,8 +53,10 @@ class _Weight:
 
 
 class Engine:
-    def __init__(self, model, device: torch.device, precision: str = 'f32x3'):
+    def __init__(self, model, device: torch.device, precision: str = 'f32x3', correlation: str = 'volume'):
         self.cfg = model.model_params
+        assert correlation in ('volume', 'otf'), correlation
+        self.corr_mode = correlation
         self.device = device
         self.lib = _lib.lib()
         assert precision in PREC, f'precision must be one of {sorted(PREC)}'
@@ -63,6 +65,7 @@ class Engine:
         self.use_graph = os.environ.get('BFLOW_GRAPH', '1') != '0'
         self.use_tc = os.environ.get('BFLOW_TC', '1') != '0'      # tcgen05 convolutions (0: exact-fp32 CUDA-core kernels, the numerical anchor)
         assert self.use_tc or self.prec == 0, 'BFLOW_TC=0 is the exact-fp32 anchor: it has no reduced-precision form'
+        assert self.use_tc or correlation == 'volume', 'BFLOW_TC=0 is the exact-fp32 anchor of the volume path'
         self.use_side_stream = os.environ.get('BFLOW_STREAMS', '1') != '0'
         self.max_plans = max(1, int(os.environ.get('BFLOW_MAX_PLANS', '4')))
         with torch.cuda.device(device):

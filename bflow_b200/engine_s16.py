@@ -16,7 +16,7 @@ import torch
 
 from . import _lib
 from ._lib import ACT, EPI, ConvDesc, check
-from .ops import make_lookup_desc, tiled_plane_size, dev_zeros
+from .ops import make_lookup_desc, make_lookup_otf_desc, tiled_plane_size, dev_zeros
 
 
 class _S16:
@@ -361,6 +361,67 @@ class S16Recorder:
             Hc, Wc, Cc = Ho, Wo, Co
         final(X, Np, Hc, Wc, Cc)
 
+    def _record_volume(self, fm_ev, fm_img, fm_ev16, fm_img16, T_ev, T):
+        """Correlation volume (tensor-core GEMM, granule-tiled planes) + pyramid (corr.py:264-272, 293-305) and the lookup descriptor."""
+        eng, L = self.eng, self.eng.lib
+        dev = eng.device
+        B, h, w, Q, R = self.B, self.h, self.w, self.Q, self.R
+        f32 = dict(device=dev, dtype=torch.float32)
+        deg, fd = eng.deg, eng.fdim
+        hx, poff, gw = self.hx.data_ptr(), self.poff, self.gw
+        self.tiled = True
+        bnv = 128
+        Np0 = tiled_plane_size(h, w)
+        self.vol0 = torch.empty(T, R, Np0, **f32)
+        img_bytes = ((Np0 + bnv - 1) // bnv) * ((fd + 63) // 64) * 2 * bnv * 128
+        self.f2img = dev_zeros(T, B, img_bytes, device=dev, dtype=torch.uint8)
+        srcs = [(fm_ev, (t + 1) * B, fm_ev16) for t in range(T_ev)] + ([(fm_img, B, fm_img16)] if self.use_img else [])
+        for t, (fm2, n0, fm1_16) in enumerate(srcs):
+            for b in range(B):
+                self._add(L.bflow_pack_b_tc, fm2.data_ptr() + (n0 + b) * Q * fd * 4, fd, self.f2img[t, b].data_ptr(), Q, fd, bnv, h, w)
+                # corr[bq, n] = <f1[bq, :], f2[n, :]> / sqrt(D): a 1x1 "convolution" over the Q query pixels of sample b whose weight
+                # image is the packed target feature map
+                d = ConvDesc()
+                d.precision = self.eng.prec
+                d.c0, d.ld0 = fd, fd
+                d.y, d.ldy = self.vol0[t].data_ptr() + b * Q * Np0 * 4, Np0
+                d.N, d.H, d.W, d.Ho, d.Wo, d.Cout = 1, 1, Q, 1, Q, Np0
+                d.KH, d.KW, d.stride = 1, 1, 1
+                d.scale = 1.0 / (fd ** 0.5)
+                self.keep.append(d)
+                sub = fm1_16.rows_from(b * Q, Q)
+                maps = (C.c_uint8 * 512)()
+                for j, base in enumerate((sub.hi(), sub.lo())):
+                    check(L.bflow_tma_im2col_map(C.addressof(maps) + 128 * j, base, 1, 1, Q, fd, fd, 1, 1, 1, 0, 0), 'tma_im2col_map')
+                self.keep.append(maps)
+                self._add(L.bflow_conv2d_nhwc_tc3, C.byref(d), C.addressof(maps), self.f2img[t, b].data_ptr(), bnv, 1.0, eng.err.data_ptr(),
+                          label=f'corr_volume_tc3 Q={Q} D={fd}', flops=2.0 * Q * Q * fd)
+        pyr = [(list(range(T)), self.vol0, h, w)]
+        for lvl in range(1, max(eng.levels)):
+            prev_idx, prev, hp_, wp_ = pyr[-1]
+            keep = [t for t in range(T) if eng.levels[t] > lvl]
+            hl, wl = hp_ // 2, wp_ // 2
+            cur = torch.empty(len(keep), R, tiled_plane_size(hl, wl), **f32)
+            for j, t in enumerate(keep):
+                self._add(L.bflow_corr_pool_tiled, prev[prev_idx.index(t)].data_ptr(), cur[j].data_ptr(), R, hp_, wp_)
+            pyr.append((keep, cur, hl, wl))
+        self.pyr = pyr
+
+        # ---- lookup: centres from the fp32 Bezier params, output written as split planes for convc1 ----
+        slots = [(lvl, t, pyr[lvl][1][pyr[lvl][0].index(t)], pyr[lvl][2], pyr[lvl][3]) for (lvl, t) in eng.slots]
+        ld = make_lookup_desc(slots, T, B, h, w, True)
+        ld.coords = None
+        ld.params, ld.params_ld, ld.degree = hx + poff * 4, gw, deg
+        for t in range(T):
+            for k in range(deg):
+                ld.coef[t][k] = float(eng.coef[t, k])
+        ld.out, ld.out_nhwc, ld.out_ld = None, 1, eng.ldc
+        ld.out16_hi, ld.out16_lo, ld.out16_ld = self.corr16.hi(), (None if eng.prec == 1 else self.corr16.lo()), eng.ldc
+        self.keep.append(ld)
+        self.lookup_desc = ld
+        self.lookup_fn = L.bflow_corr_lookup
+
+
     # ---- the whole forward ---------------------------------------------------------------------------------------------------
     def _record_s16(self):
         from .engine import _ceil
@@ -441,58 +502,38 @@ class S16Recorder:
             fm_img, fm_img16 = fnet('fnet_img', [self._stem_window(self.img_in[i], 3, 0, 3, B, H, W, 2.0 / 255.0, -1.0, shared=shared) for i in range(2)], 2 * B)
         self.fm_ev, self.fm_img, self.fm_ev16, self.fm_img16 = fm_ev, fm_img, fm_ev16, fm_img16
 
-        # ---- correlation volume (tensor-core GEMM, granule-tiled planes) + pyramid (corr.py:264-272, 293-305) ----
-        self.tiled = True
-        bnv = 128
-        Np0 = tiled_plane_size(h, w)
-        self.vol0 = torch.empty(T, R, Np0, **f32)
-        img_bytes = ((Np0 + bnv - 1) // bnv) * ((fd + 63) // 64) * 2 * bnv * 128
-        self.f2img = dev_zeros(T, B, img_bytes, device=dev, dtype=torch.uint8)
-        srcs = [(fm_ev, (t + 1) * B, fm_ev16) for t in range(T_ev)] + ([(fm_img, B, fm_img16)] if self.use_img else [])
-        for t, (fm2, n0, fm1_16) in enumerate(srcs):
-            for b in range(B):
-                self._add(L.bflow_pack_b_tc, fm2.data_ptr() + (n0 + b) * Q * fd * 4, fd, self.f2img[t, b].data_ptr(), Q, fd, bnv, h, w)
-                # corr[bq, n] = <f1[bq, :], f2[n, :]> / sqrt(D): a 1x1 "convolution" over the Q query pixels of sample b whose weight
-                # image is the packed target feature map
-                d = ConvDesc()
-                d.precision = self.eng.prec
-                d.c0, d.ld0 = fd, fd
-                d.y, d.ldy = self.vol0[t].data_ptr() + b * Q * Np0 * 4, Np0
-                d.N, d.H, d.W, d.Ho, d.Wo, d.Cout = 1, 1, Q, 1, Q, Np0
-                d.KH, d.KW, d.stride = 1, 1, 1
-                d.scale = 1.0 / (fd ** 0.5)
-                self.keep.append(d)
-                sub = fm1_16.rows_from(b * Q, Q)
-                maps = (C.c_uint8 * 512)()
-                for j, base in enumerate((sub.hi(), sub.lo())):
-                    check(L.bflow_tma_im2col_map(C.addressof(maps) + 128 * j, base, 1, 1, Q, fd, fd, 1, 1, 1, 0, 0), 'tma_im2col_map')
-                self.keep.append(maps)
-                self._add(L.bflow_conv2d_nhwc_tc3, C.byref(d), C.addressof(maps), self.f2img[t, b].data_ptr(), bnv, 1.0, eng.err.data_ptr(),
-                          label=f'corr_volume_tc3 Q={Q} D={fd}', flops=2.0 * Q * Q * fd)
-        pyr = [(list(range(T)), self.vol0, h, w)]
-        for lvl in range(1, max(eng.levels)):
-            prev_idx, prev, hp_, wp_ = pyr[-1]
-            keep = [t for t in range(T) if eng.levels[t] > lvl]
-            hl, wl = hp_ // 2, wp_ // 2
-            cur = torch.empty(len(keep), R, tiled_plane_size(hl, wl), **f32)
-            for j, t in enumerate(keep):
-                self._add(L.bflow_corr_pool_tiled, prev[prev_idx.index(t)].data_ptr(), cur[j].data_ptr(), R, hp_, wp_)
-            pyr.append((keep, cur, hl, wl))
-        self.pyr = pyr
-
-        # ---- lookup: centres from the fp32 Bezier params, output written as split planes for convc1 ----
-        slots = [(lvl, t, pyr[lvl][1][pyr[lvl][0].index(t)], pyr[lvl][2], pyr[lvl][3]) for (lvl, t) in eng.slots]
         self.corr16 = _S16(R, eng.ldc, dev)                 # zero-filled: the channels padding S*81 up to ldc stay zero
-        ld = make_lookup_desc(slots, T, B, h, w, True)
-        ld.coords = None
-        ld.params, ld.params_ld, ld.degree = hx + poff * 4, gw, deg
-        for t in range(T):
-            for k in range(deg):
-                ld.coef[t][k] = float(eng.coef[t, k])
-        ld.out, ld.out_nhwc, ld.out_ld = None, 1, eng.ldc
-        ld.out16_hi, ld.out16_lo, ld.out16_ld = self.corr16.hi(), (None if eng.prec == 1 else self.corr16.lo()), eng.ldc
-        self.keep.append(ld)
-        self.lookup_desc = ld
+        if eng.corr_mode == 'otf':
+            # ---- row (f3): no volume.  Pooled TARGET FEATURE pyramid (avg_pool2d is linear: pooled features give the pooled correlation
+            #      planes of corr.py:119 exactly) + on-the-fly lookup (bflow_corr_lookup_otf) ----
+            self.tiled = False
+            feats = [(fm_ev, 0, (t + 1) * B) for t in range(T_ev)] + ([(fm_img, 0, B)] if self.use_img else [])     # (tensor, f1 image, f2 image)
+            pyr_f = []                                      # per target: [level-0 view, pooled level 1, ...]
+            self.fpool = []
+            for t, (fm, i1, i2) in enumerate(feats):
+                lv = [fm[i2:i2 + B]]
+                hh, ww = h, w
+                for _ in range(1, eng.levels[t]):
+                    nxt = torch.empty(B, hh // 2, ww // 2, fd, **f32)
+                    self._add(L.bflow_feat_pool, lv[-1].data_ptr(), nxt.data_ptr(), B, hh, ww, fd, fd, fd)
+                    lv.append(nxt)
+                    hh, ww = hh // 2, ww // 2
+                pyr_f.append(lv)
+                self.fpool.append(lv)
+            slots = [(lvl, t, feats[t][0][feats[t][1]:feats[t][1] + B], pyr_f[t][lvl]) for (lvl, t) in eng.slots]
+            ld = make_lookup_otf_desc(slots, T, B, h, w, fd)
+            ld.coords = None
+            ld.params, ld.params_ld, ld.degree = hx + poff * 4, gw, deg
+            for t in range(T):
+                for k in range(deg):
+                    ld.coef[t][k] = float(eng.coef[t, k])
+            ld.out, ld.out_ld = None, 0
+            ld.out16_hi, ld.out16_lo, ld.out16_ld = self.corr16.hi(), (None if eng.prec == 1 else self.corr16.lo()), eng.ldc
+            self.keep.append(ld)
+            self.lookup_desc = ld
+            self.lookup_fn = L.bflow_corr_lookup_otf
+        else:
+            self._record_volume(fm_ev, fm_img, fm_ev16, fm_img16, T_ev, T)
 
         self._join()                                        # context branch done
 
@@ -525,7 +566,7 @@ class S16Recorder:
             self._conv_simt16(U['convf1'], hx + poff * 4, 2 * deg, gw, B, h, w, y16=(f1_16, 0), act1='relu', kernel='thin7' if thin else 'auto')
             self._conv3(U['convf2'], [(f1_16, 0, 128)], B, h, w, y16=(cb16, 192), act1='relu')
             self._main()
-            self._add(L.bflow_corr_lookup, C.byref(ld))
+            self._add(self.lookup_fn, C.byref(self.lookup_desc), label='corr_lookup' if eng.corr_mode != 'otf' else 'corr_lookup_otf')
             self._conv3(U['convc1'], [(self.corr16, 0, eng.ldc)], B, h, w, y16=(c1_16, 0), act1='relu')
             self._conv3(U['convc2'], [(c1_16, 0, 256)], B, h, w, y16=(cb16, 0), act1='relu')
             self._join()

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ACT, ConvDesc, LookupDesc, check
+from ._lib import ACT, ConvDesc, LookupDesc, LookupOtfDesc, check
 
 
 def _stream() -> int:
@@ -384,6 +384,55 @@ def corr_lookup(slots: Sequence[tuple], coords: torch.Tensor, nhwc: bool = False
     d.out, d.out_nhwc, d.out_ld = out.data_ptr(), int(nhwc), S * 81
     check(_lib.lib().bflow_corr_lookup(C.byref(d), _stream()), 'corr_lookup')
     return out
+
+
+@_on_tensor_device
+def feat_pool(x_nhwc: torch.Tensor) -> torch.Tensor:
+    """avg_pool2d(2, 2) (floor) of NHWC features (N, H, W, C) -> (N, H//2, W//2, C)."""
+    x = _f32c(x_nhwc, 'x')
+    N, H, W, Cc = x.shape
+    out = torch.empty(N, H // 2, W // 2, Cc, device=x.device, dtype=torch.float32)
+    check(_lib.lib().bflow_feat_pool(x.data_ptr(), out.data_ptr(), N, H, W, Cc, Cc, Cc, _stream()), 'feat_pool')
+    return out
+
+
+def make_lookup_otf_desc(slots: Sequence[tuple], n_targets: int, B: int, h: int, w: int, D: int) -> LookupOtfDesc:
+    """slots: (level, base target, f1 NHWC (B,h,w,D), f2 NHWC (B,hl,wl,D)) in output order."""
+    d = LookupOtfDesc()
+    d.n_slots, d.n_targets, d.B, d.h, d.w, d.radius, d.D = len(slots), n_targets, B, h, w, 4, D
+    d.ld1 = d.ld2 = D
+    d.scale = 1.0 / math.sqrt(D)
+    for s, (lvl, t, f1, f2) in enumerate(slots):
+        for x in (f1, f2):
+            assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[0] == B and x.shape[-1] == D
+        assert f1.shape[1:3] == (h, w)
+        d.f1[s], d.f2[s] = f1.data_ptr(), f2.data_ptr()
+        d.hl[s], d.wl[s] = f2.shape[1], f2.shape[2]
+        d.target[s] = t
+        d.inv_scale[s] = 1.0 / (2 ** lvl)
+    return d
+
+
+@_on_tensor_device
+def corr_lookup_otf(fmap1: torch.Tensor, fmap2: torch.Tensor, levels: Sequence[int], coords: torch.Tensor) -> torch.Tensor:
+    """On-the-fly form of CorrComputation + CorrBlockParallelMultiTarget (corr.py:128-350): fmap1 (B,D,h,w), fmap2 (T,B,D,h,w) in the
+    reference layout, levels per target, coords (T,B,2,h,w) -> (B, S*81, h, w), without building the correlation volume."""
+    from . import config as _cfg
+    fmap1, fmap2, coords = _f32c(fmap1, 'fmap1'), _f32c(fmap2, 'fmap2'), _f32c(coords, 'coords')
+    T, B, D, h, w = fmap2.shape
+    f1 = nchw_to_nhwc(fmap1)
+    pyr = [[nchw_to_nhwc(fmap2[t])] for t in range(T)]
+    for t in range(T):
+        for _ in range(1, levels[t]):
+            pyr[t].append(feat_pool(pyr[t][-1]))
+    slots = [(lvl, t, f1, pyr[t][lvl]) for (lvl, t) in _cfg.slot_table(list(levels))]
+    d = make_lookup_otf_desc(slots, T, B, h, w, D)
+    S = len(slots)
+    out = torch.empty(B, h, w, S * 81, device=coords.device, dtype=torch.float32)
+    d.coords, d.params, d.params_ld, d.degree = coords.data_ptr(), None, 0, 0
+    d.out, d.out_ld = out.data_ptr(), S * 81
+    check(_lib.lib().bflow_corr_lookup_otf(C.byref(d), _stream()), 'corr_lookup_otf')
+    return out.permute(0, 3, 1, 2).contiguous()
 
 
 # ---- Bezier ------------------------------------------------------------------------------------------------

@@ -17,7 +17,7 @@ import torch
 from . import _lib
 
 # entry points whose kernels take a timeline slot, in the order bflow_timeline_name reports them
-INSTRUMENTED = ('conv2d_nhwc_tc3', 'conv2d_nhwc_tc3o', 'conv2d_nhwc_tc3s', 'conv2d_slab64', 'conv2d_stem7', 'corr_lookup', 'conv2d_small_n',
+INSTRUMENTED = ('conv2d_nhwc_tc3', 'conv2d_nhwc_tc3o', 'conv2d_nhwc_tc3s', 'conv2d_slab64', 'conv2d_stem7', 'corr_lookup', 'corr_lookup_otf', 'conv2d_small_n',
                 'conv2d_thin7', 'conv2d_nhwc', 'instnorm_relu16', 'im2col_split16')
 
 

@@ -128,13 +128,19 @@ def _update_block(cfg: Dict[str, Any], hdim: int) -> nn.Module:
 class RAFTSpline(nn.Module):
     """``precision``: arithmetic of the tensor-core convolutions.  ``'f32x3'`` (default): split-fp16 operands, three MMAs per product,
     fp32-equivalent (the 1e-3 px configuration of BASELINE.json).  ``'f16'``: one fp16 MMA per product on the hi planes (the reduced-
-    precision configuration, 1e-2 px bar).  Default from the environment variable BFLOW_PRECISION."""
+    precision configuration, 1e-2 px bar).  Default from the environment variable BFLOW_PRECISION.
+    ``correlation``: ``'volume'`` (default) or ``'otf'`` (on-the-fly, no materialised volume; BFLOW_CORR)."""
 
-    def __init__(self, model_params: Dict[str, Any], seed: Optional[int] = 0, verbose: bool = False, precision: Optional[str] = None):
+    def __init__(self, model_params: Dict[str, Any], seed: Optional[int] = 0, verbose: bool = False, precision: Optional[str] = None,
+                 correlation: Optional[str] = None):
         super().__init__()
         import os
         self.precision = precision if precision is not None else os.environ.get('BFLOW_PRECISION', 'f32x3')
         assert self.precision in ('f32x3', 'f16'), self.precision
+        # 'volume' (default): all-pairs correlation volume + pyramid as in the reference; 'otf': on-the-fly correlation against a pooled
+        # target-feature pyramid (no T x (B*Q) x Q volume: 369 MB at 480x640, the only reason the batch is capped by memory)
+        self.correlation = correlation if correlation is not None else os.environ.get('BFLOW_CORR', 'volume')
+        assert self.correlation in ('volume', 'otf'), self.correlation
         p = model_params
         nctx, ncorr = p['num_bins']['context'], p['num_bins']['correlation']
         self.bezier_degree = p['bezier_degree']
@@ -251,9 +257,9 @@ class RAFTSpline(nn.Module):
             raise RuntimeError('bflow_b200.RAFTSpline runs only on CUDA (sm_100a); there is no CPU path')
         ver = self._versions()
         if (self._engine is None or self._engine.device != device or self._engine.precision != self.precision or
-                self._engine_versions != ver):
+                self._engine.corr_mode != self.correlation or self._engine_versions != ver):
             from .engine import Engine
-            self._engine = Engine(self, device, self.precision)
+            self._engine = Engine(self, device, self.precision, self.correlation)
             self._engine_versions = ver
         return self._engine
 

@@ -246,6 +246,35 @@ typedef struct bflow_lookup_desc {
 int bflow_corr_lookup(const bflow_lookup_desc* d, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * On-the-fly correlation lookup (scope row f3): the same output as bflow_corr_lookup WITHOUT a materialised volume.  For every unit
+ * (query pixel, slot) the 10 x 10 footprint of correlation values is computed directly as <f1[q], f2_level[p]> * scale against an
+ * average-pooled TARGET FEATURE pyramid (bflow_feat_pool: avg_pool2d(2, 2, floor) of NHWC features; pooling is linear, so this equals
+ * the pooled correlation planes of corr.py:119) and blended exactly like bflow_corr_lookup.  Replaces corr.py:108-125,264-272,307-350.
+ * f1[s]: query features of slot s, NHWC rows (B*Q) x D at stride ld1; f2[s]: the target features of slot s's (target, level), NHWC (B, hl, wl, D)
+ * rows at stride ld2; D % 4 == 0, D <= 512; scale = 1/sqrt(D) (corr.py:267).  Output NHWC rows: fp32 `out` (stride out_ld) or, when
+ * out16_hi != NULL, split-fp16 planes (out16_lo == NULL: hi plane only).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct bflow_lookup_otf_desc {
+    int struct_size;                       /* sizeof(bflow_lookup_otf_desc) of the caller */
+    int n_slots, n_targets, B, h, w, radius, D;
+    const float* f1[BFLOW_MAX_SLOTS]; int ld1;   /* per slot: event targets and the image target have different query feature maps */
+    const float* f2[BFLOW_MAX_SLOTS]; int ld2;
+    int hl[BFLOW_MAX_SLOTS], wl[BFLOW_MAX_SLOTS];
+    int target[BFLOW_MAX_SLOTS];
+    float inv_scale[BFLOW_MAX_SLOTS];      /* 1 / 2^level */
+    float scale;
+    const float* coords;                   /* (T,B,2,h,w) or NULL */
+    const float* params; int params_ld; int degree;
+    float coef[BFLOW_MAX_TARGETS][BFLOW_MAX_DEGREE];
+    float* out; int out_ld;
+    void* out16_hi; void* out16_lo; int out16_ld;
+} bflow_lookup_otf_desc;
+int bflow_sizeof_lookup_otf_desc(void);
+int bflow_corr_lookup_otf(const bflow_lookup_otf_desc* d, void* stream);
+/* avg_pool2d(2, stride 2, floor) of NHWC fp32 features: (N, H, W, C) rows at ld_in -> (N, H/2, W/2, C) rows at ld_out; C % 4 == 0 */
+int bflow_feat_pool(const float* in, float* out, int N, int H, int W, int C, int ld_in, int ld_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * SepConvGRU gate arithmetic (update.py:37-40,44-47) on NHWC rows:
  *   bflow_gru_rh:      rh = r * h            (r = zr[:, C:2C])
  *   bflow_gru_update:  h  = (1-z)*h + z*q    (z = zr[:, 0:C]), in place

@@ -161,6 +161,26 @@ def test_reduced_precision_configuration_meets_1e_2_on_the_benchmark_workload():
     assert mx > 1e-4
 
 
+@pytest.mark.parametrize('name', ['d_128_i4_bn', 'm_128_i3_bn', 'd_480x640_i12'])
+def test_on_the_fly_correlation_forward_matches_reference_fixture(name):
+    """Row (f3): correlation='otf' -- no correlation volume, lookups computed from a pooled target-feature pyramid -- meets the same 1e-3 px
+    bar against the reference fixtures, and really is the other path (no volume tensor in the plan)."""
+    g = load_golden(name)
+    cfg, net, sd, vg, im = build_case(g)
+    net.correlation = 'otf'
+    low, up = run_cuda(net, vg, im, iters=int(g['iters']), test_mode=True)
+    plan = net.engine().plan(int(g['B']), int(g['H']), int(g['W']), int(g['iters']), True)
+    assert net.engine().corr_mode == 'otf' and not hasattr(plan, 'vol0') and any('corr_lookup_otf' == lab for lab, _ in plan.labels)
+    low, up = low.get_params().cpu(), up.get_params().cpu()
+    mx, mean = flow_epe(low, torch.from_numpy(g['low']))
+    assert 8 * mx <= EPE_BAR, f'low-res EPE {mx} (x8 in full-res pixels)'
+    if 'up' in g.files:
+        assert flow_epe(up, torch.from_numpy(g['up']))[0] <= EPE_BAR
+    else:
+        got = up.reshape(-1)[torch.from_numpy(g['up_index'])].numpy()
+        assert np.abs(got - g['up_samples']).max() <= EPE_BAR / 1.4
+
+
 def test_pipelined_forward_with_host_buffers_equals_blocking_forward():
     """forward(non_blocking=True): pinned host inputs, H2D / graph / D2H on three streams over two alternating buffer sets."""
     cfg = config.preset('E_LU4_BD2')

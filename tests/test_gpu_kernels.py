@@ -282,6 +282,31 @@ def test_tiled_lookup_and_pool_match_oracle(B, h, w, levels):
     assert (out2 - want).abs().max() < 3e-5
 
 
+def test_on_the_fly_lookup_matches_reference_fixture_and_oracle():
+    """Row (f3): bflow_corr_lookup_otf (no materialised volume, pooled target-feature pyramid) gives the reference's lookup output."""
+    gd = load_golden('lookup_16x24')
+    B, h, w, D = int(gd['B']), int(gd['h']), int(gd['w']), int(gd['D'])
+    levels = [int(v) for v in gd['levels']]
+    f1, f2, coords = synthetic.lookup_case(B, h, w, dim=D, targets=len(levels), seed=7)
+    out = ops.corr_lookup_otf(f1.to(DEV), f2.to(DEV), levels, coords.to(DEV))
+    assert np.abs(out.cpu().numpy() - gd['out']).max() < 3e-5
+    # feature pooling == correlation pooling (avg_pool2d is linear), including the floor rule on odd sizes
+    x = torch.randn(2, 15, 22, 64, generator=g(3))
+    want = F.avg_pool2d(x.permute(0, 3, 1, 2), 2, stride=2).permute(0, 2, 3, 1)
+    assert (ops.feat_pool(x.to(DEV)).cpu() - want).abs().max() < 1e-6
+    for (B, h, w, levels, D) in [(1, 60, 80, [4], 256), (2, 24, 40, [1, 1, 1, 1, 4, 4], 128), (2, 9, 13, [2, 1], 32), (1, 15, 22, [3], 384)]:
+        T = len(levels)
+        f1, f2, coords = synthetic.lookup_case(B, h, w, dim=D, targets=T, seed=17)
+        coords[0, 0, :, 0, 0] = torch.tensor([-30.0, 1e9])            # far outside: all taps zero-padded
+        coords[0, 0, :, 0, 1] = torch.tensor([float(w - 1), float(h - 1)])
+        coords[0, 0, :, 0, 2] = torch.tensor([-3.25, -2.5])           # window straddles the top-left corner
+        want = O.corr_lookup(O.corr_pyramid(O.corr_volume(f1, f2), levels), coords)
+        got = ops.corr_lookup_otf(f1.to(DEV), f2.to(DEV), levels, coords.to(DEV)).cpu()
+        assert got.shape == want.shape
+        assert (got - want).abs().max() < 1e-4 * max(1.0, float(want.abs().max()))
+        assert got[0, :81, 0, 0].abs().max() == 0
+
+
 def test_lookup_known_answer_centre_tap():
     h, w = 12, 20
     vol = torch.randn(1, h * w, 1, h, w, generator=g(5))

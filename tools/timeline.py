@@ -24,6 +24,7 @@ def main():
     ap.add_argument('--w', type=int, default=640)
     ap.add_argument('--iters', type=int, default=12)
     ap.add_argument('--precision', default='f32x3')
+    ap.add_argument('--correlation', default='volume')
     ap.add_argument('--raw', action='store_true')
     ap.add_argument('--cta', type=int, default=-1, help='per-CTA stamps of the nth tc3 launch of the step')
     ap.add_argument('--cta-label', default='', help='... or of the launch whose label contains this text')
@@ -34,7 +35,7 @@ def main():
     L = profiling._dev_lib()
     L.bflow_tc3_cta_trace_range.argtypes = [C.c_void_p, C.c_int, C.c_int]
     cfg = config.preset(a.preset)
-    net = RAFTSpline(cfg, seed=0, precision=a.precision).to(dev)
+    net = RAFTSpline(cfg, seed=0, precision=a.precision, correlation=a.correlation).to(dev)
     vg, im = synthetic.inputs(cfg, a.batch, a.h, a.w)
     vg = vg.to(dev) if vg is not None else None
     im = [t.to(dev) for t in im] if im is not None else None
@@ -93,7 +94,7 @@ def main():
     print(f'{"label":52s} {"n":>4s} {"in-kernel us":>13s} {"gap before us":>14s}')
     for (lab, st), (cnt, dur, gap) in sorted(agg.items(), key=lambda kv: -(kv[1][1] + kv[1][2])):
         print(f's{st} {lab:50s} {cnt:4d} {dur / cnt:13.2f} {gap / cnt:14.2f}   total {(dur + gap) / 1e3:7.3f} ms')
-    it = [r for r in rows if r['label'] == 'corr_lookup']
+    it = [r for r in rows if r['label'].startswith('corr_lookup')]
     if len(it) >= 3:
         print(f'update-block iteration (lookup start to lookup start): {(it[-1]["start_us"] - it[1]["start_us"]) / (len(it) - 2):.2f} us')
 
