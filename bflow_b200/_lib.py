@@ -125,6 +125,16 @@ _SIGNATURES = {
                                      C.c_void_p, C.c_void_p]),
     'bflow_voxel_norm': (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     'bflow_epe_masked': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
+    'bflow_forward_load': (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    'bflow_forward_info': (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    'bflow_forward_run': (C.c_int, [C.c_void_p] * 8),
+    'bflow_forward_destroy': (None, [C.c_void_p]),
+    'bflow_arena_open': (C.c_int, [C.c_ulonglong, C.c_ulonglong]),
+    'bflow_arena_alloc': (C.c_void_p, [C.c_long, C.c_int, C.c_void_p]),
+    'bflow_arena_free': (None, [C.c_void_p, C.c_long, C.c_int, C.c_void_p]),
+    'bflow_arena_used': (C.c_ulonglong, []),
+    'bflow_arena_read': (C.c_int, [C.c_ulonglong, C.c_void_p, C.c_ulonglong]),
+    'bflow_arena_close': (C.c_int, []),
     'bflow_gru_rh': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
     'bflow_gru_update': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
     'bflow_bezier_eval': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),

@@ -323,6 +323,33 @@ int bflow_epe_masked(const float* src, const float* tgt, const unsigned char* va
 int bflow_flow_metrics(const float* src, const float* tgt, const unsigned char* valid, int N, int C, long long HW, float src_scale,
                        const float* thresholds_host, int n_thresholds, double* out8, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Whole-forward native entry: RAFTSpline.forward(voxel_grid, images, iters, test_mode=True) (models/raft_spline/raft.py:101-200) for ONE
+ * (batch, height, width, iterations), replayed from a plan file without Python or torch.  `python -m bflow_b200.export` records the launch
+ * list the Python engine replays (the same C entry points as above, in order, with their descriptors and tensor maps), packs the weights and
+ * writes everything to the plan file; every device allocation of the exporter lives in one arena mapped at a FIXED virtual address with
+ * the CUDA virtual-memory API, so the loader maps fresh memory at the same address and no pointer needs relocating.
+ *   bflow_forward_load     maps the arena, restores the weights, replays the launch list once (warm-up) and captures it in a CUDA graph
+ *                          (two-stream fork / join branches included).  Fails with BFLOW_ERR_CUDA if the address range is not free.
+ *   bflow_forward_info     info16 = {B, voxel channels, H, W, h, w, 2*degree, iters, use_events, use_images, precision, correlation, 0, 0, 0, ABI}
+ *   bflow_forward_run      copies the inputs in (host or device pointers; NULL flow_init = zeros; images NULL for an events-only plan),
+ *                          launches the graph and copies low (B, 2*deg, H/8, W/8) and up (B, 2*deg, H, W) out (NULL = skip), all on
+ *                          `stream`, asynchronously: synchronise the stream before reading host results.
+ * The arena functions are the exporter's side (a torch.cuda.memory.CUDAPluggableAllocator binds bflow_arena_alloc / bflow_arena_free).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct bflow_forward bflow_forward;
+int bflow_forward_load(const char* plan_path, bflow_forward** out);
+int bflow_forward_info(const bflow_forward* f, int* info16);
+int bflow_forward_run(bflow_forward* f, const float* voxel, const float* image0, const float* image1, const float* flow_init,
+                      float* low_out, float* up_out, void* stream);
+void bflow_forward_destroy(bflow_forward* f);
+int bflow_arena_open(unsigned long long base_address, unsigned long long reserve_bytes);
+void* bflow_arena_alloc(long size, int device, void* stream);
+void bflow_arena_free(void* ptr, long size, int device, void* stream);
+unsigned long long bflow_arena_used(void);
+int bflow_arena_read(unsigned long long offset, void* dst_host, unsigned long long bytes);
+int bflow_arena_close(void);
+
 #ifdef __cplusplus
 }
 #endif
