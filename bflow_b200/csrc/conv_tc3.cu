@@ -16,6 +16,7 @@
 #include <cuda.h>
 #include <string.h>
 #include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
 
 namespace bflow {
@@ -435,10 +436,14 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
             }
             // The issuing thread is the bottleneck of this kernel's main loop, so the loop runs warp-converged (every lane waits on the barrier,
             // stage index and phase are carried, descriptors are base + constant) and only the MMA / commit instructions sit under elect.sync.
-            for (int kb = 0; kb < p.nkb; ++kb) {
+            // The first k-block is peeled off: it alone starts the accumulator (accumulate = 0 on its first MMA), so the steady-state loop
+            // issues eight unconditional MMAs per k-block.  Measured: ONE more uniform predicate per MMA pair in this loop cost 10 % of
+            // the update block -- the issue sequence of the single MMA thread is on the critical path of these short-N kernels.
+            auto kblock = [&](auto first) {
+                constexpr bool FIRST = decltype(first)::value;
                 t3_mbar_wait(full_bar(ms), mph, err);
                 t3_fence_after();
-                if (kb == 0 && lt == 0 && lane == 0) T3_CTA(3);
+                if (FIRST && lt == 0 && lane == 0) T3_CTA(3);
                 const uint32_t a_hi = smem_base + ms * (uint32_t)STAGE_BYTES;
                 const uint64_t dah0 = t3_umma_desc(a_hi);
                 const uint64_t dal0 = dah0 + (uint64_t)(T3_A_BYTES >> 4);
@@ -449,29 +454,34 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t ko = (uint64_t)(k * 2);             // 32 bytes along K, in 16-byte descriptor units
+                        const uint32_t acc0 = (FIRST && k == 0) ? 0u : 1u;
                         if (F16) {
-                            t3_umma(tacc, dah0 + ko, dbh0 + ko, idesc, (kb > 0 || k > 0) ? 1u : 0u);       // hi*hi alone
+                            t3_umma(tacc, dah0 + ko, dbh0 + ko, idesc, acc0);       // hi*hi alone
                         } else if (STACK) {
-                            t3_umma(tacc, dah0 + ko, dbh0 + ko, idesc2, (kb > 0 || k > 0) ? 1u : 0u);      // hi*hi | hi*lo
-                            t3_umma(tacc, dal0 + ko, dbh0 + ko, idesc, 1u);                               // lo*hi
+                            t3_umma(tacc, dah0 + ko, dbh0 + ko, idesc2, acc0);      // hi*hi | hi*lo
+                            t3_umma(tacc, dal0 + ko, dbh0 + ko, idesc, 1u);         // lo*hi
                         } else {
-                            t3_umma(tacc, dah0 + ko, dbh0 + ko, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            t3_umma(tacc, dah0 + ko, dbh0 + ko, idesc, acc0);
                             t3_umma(tacc, dah0 + ko, dbl0 + ko, idesc, 1u);
                             t3_umma(tacc, dal0 + ko, dbh0 + ko, idesc, 1u);
                         }
                     }
                     t3_commit(ebar_s);
-                    if (kb == p.nkb - 1) {
-                        t3_commit(tfull_bar(acc));
-                        T3_CTA(4);
-                    }
                 }
                 __syncwarp();
                 if (++ms == (uint32_t)STAGES) {
                     ms = 0;
                     mph ^= 1u;
                 }
+            };
+            kblock(std::true_type{});
+#pragma unroll 1
+            for (int kb = 1; kb < p.nkb; ++kb) kblock(std::false_type{});
+            if (t3_elect_one()) {
+                t3_commit(tfull_bar(acc));      // arrives when every MMA issued above has completed
+                T3_CTA(4);
             }
+            __syncwarp();
         }
         t3_fence_before();
     } else {
