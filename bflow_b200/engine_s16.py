@@ -549,9 +549,13 @@ class S16Recorder:
         zr, hh, mk = self.zr.data_ptr(), self.hh.data_ptr(), self.mask.data_ptr()
         c1_16, cb16, f1_16, rh16, hm16 = self.c1_16, self.cb16, self.f1_16, self.rh16, self.hm16
 
-        def upsample(out_t):
+        def mask_head():
             self._conv3(U['mask0'], [(hx16, 0, hd)], B, h, w, y16=(hm16, 0), act1='relu')
             self._conv3(U['mask2'], [(hm16, 0, 256)], B, h, w, y=mk, ldy=576, scale=0.25)
+
+        def upsample(out_t, mask_done=False):
+            if not mask_done:
+                mask_head()
             self._add(L.bflow_cvx_upsample, hx + poff * 4, gw, 0, mk, 576, 0, out_t.data_ptr(), B, 2 * deg, h, w)
 
         self.iter_start = len(self.launches)
@@ -577,6 +581,12 @@ class S16Recorder:
                             res=pre['zr' + sfx], ldr=2 * hd, epi='gru_zr', aux0=hx, ld_aux0=gw, aux1_16=(rh16, 0))
                 self._conv3(U['q' + sfx + '_dyn'], [(rh16, 0, hd), (hx16, hd + cd, md)], B, h, w, y=hx, ldy=gw, y16=(hx16, 0), bias=False,
                             res=pre['q' + sfx], ldr=hd, epi='gru_q', aux0=zr, ld_aux0=2 * hd)
+            # the mask head only reads the new hidden state: in test mode (last iteration only) it runs beside the Bezier head on the second stream
+            side_mask = self.test_mode and itr == self.iters - 1 and 2 * deg <= 8
+            if side_mask:
+                self._fork()
+                mask_head()
+                self._main()
             # Bezier head + delta update in place (update.py:17-18, bezier.py:137-139): fp32 master and split copy
             if 2 * deg <= 8:      # tiny head: warp-per-pixel CUDA-core kernel on the fp32 hidden tensor
                 self._conv3(U['head1'], [(hx16, 0, hd)], B, h, w, y=hh, ldy=256, act1='relu')
@@ -584,11 +594,13 @@ class S16Recorder:
             else:
                 self._conv3(U['head1'], [(hx16, 0, hd)], B, h, w, y16=(hm16, 0), act1='relu')
                 self._conv3(U['head2'], [(hm16, 0, 256)], B, h, w, y=hx + poff * 4, ldy=gw, y16=(hx16, poff), res=hx + poff * 4, ldr=gw)
+            if side_mask:
+                self._join()
             if not self.test_mode:
                 upsample(self.ups[itr])
         if self.iters == 1:
             self.iter_len = len(self.launches) - self.iter_start
         if self.test_mode:
-            upsample(self.ups[0])
+            upsample(self.ups[0], mask_done=2 * deg <= 8)
         self._add(L.bflow_nhwc_to_nchw, hx + poff * 4, self.low.data_ptr(), B, 2 * deg, h, w, gw)
         self.n_launches = len(self.launches)
