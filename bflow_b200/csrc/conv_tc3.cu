@@ -17,167 +17,10 @@
 #include <string.h>
 #include <stdlib.h>
 #include <type_traits>
-#include "common.cuh"
+#include "tc3_common.cuh"
 
 namespace bflow {
 
-constexpr int T3_BM = 128;
-constexpr int T3_A_BYTES = T3_BM * 128;   // one fp16 A tile (hi or lo): 128 rows x 64 channels
-constexpr int T3_EPI_WARPS = 8;            // two per TMEM lane quadrant, each takes half of the tile's columns
-constexpr int T3_THREADS = 64 + 32 * T3_EPI_WARPS;
-
-__device__ __forceinline__ uint32_t t3_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void t3_mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void t3_mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void t3_mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool t3_mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ bool t3_mbar_test_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// development: per-role clock64 stamps of CTA 0 (bflow_tc3_trace); the pointer travels as a kernel parameter
-#define T3_CTA(i) do { if (p.cta != nullptr) p.cta[blockIdx.x * 16 + (i)] = global_ns(); } while (0)
-#define T3_TRACE(slot, idx) do { if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 256) p.trace[(slot) * 256 + (idx)] = clock64(); } while (0)
-// bounded: a protocol bug cannot hang the GPU.  After 2^24 failed polls (>= 0.3 s; no legitimate wait is longer than a few hundred
-// microseconds) the error word is set and the role carries on, so the kernel still terminates; the result of that forward is
-// garbage and the HOST makes it loud: the engine copies the word back with every forward's outputs and raises (Engine._poll_err,
-// BezierCurves of a pipelined call, _Plan.check).  A __trap() here was measured: even out of line it costs 1.2 % of the whole
-// forward (4.18 -> 4.23 ms, code layout of the ~20 inlined waits), which buys nothing over the host-side check.
-__device__ __forceinline__ void t3_mbar_wait(uint32_t bar, uint32_t parity, int* err) {
-#pragma unroll 1
-    for (uint32_t it = 0; it < (1u << 24); ++it)
-        if (t3_mbar_try_wait(bar, parity)) return;
-    if (err != nullptr) atomicExch(err, 1);
-}
-// one lane of a CONVERGED warp (elect.sync): the branch it guards is the idiom under which nvcc keeps warp-uniform operands in uniform
-// registers and issues UTCHMMA / UTCBAR directly.  Under `if (lane == 0)` it wraps every tcgen05.mma in an ELECT + 5 x R2UR + loop
-// "waterfall" -- ~70 cycles per instruction on the one thread that feeds the tensor pipe (measured: 576 of 1094 cycles per k-block).
-__device__ __forceinline__ bool t3_elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void t3_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void t3_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void t3_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
-                 "r"(bar)
-                 : "memory");
-}
-// im2col tile load: {c, w, h, n} = first channel and the input coordinates of the first output pixel's tap (0,0);
-// {off_w, off_h} = filter tap
-__device__ __forceinline__ void t3_tma_im2col(uint32_t dst, const CUtensorMap* map, int c, int w, int h, int n, uint16_t off_w, uint16_t off_h,
-                                              uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
-        : "memory");
-}
-__device__ __forceinline__ uint64_t t3_umma_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)(1024 >> 4) << 32;     // 8-row groups are 1024 bytes apart
-    d |= (uint64_t)1 << 46;               // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;               // SWIZZLE_128B
-    return d;
-}
-__device__ __forceinline__ void t3_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void t3_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void t3_tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void t3_tmem_ld16_nowait(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// 16 consecutive accumulator columns of this thread's TMEM lane (= tile row) <- registers
-__device__ __forceinline__ void t3_tmem_st16(uint32_t taddr, const float* v) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
-        "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])),
-        "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
-        "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
-        : "memory");
-}
-
-__host__ __device__ constexpr int t3_area_bytes(int bn, int stages) {
-    return bn <= 128 ? 224 * 1024 : stages * (2 * T3_A_BYTES + 2 * bn * 128);
-}
-__device__ __forceinline__ void t3_bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void sl_tma_tile(uint32_t dst, const CUtensorMap* map, int c, int x, int y, int n, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-                 "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(x), "r"(y), "r"(n)
-                 : "memory");
-}
-
-__device__ __forceinline__ void t3_tma_store2d(const CUtensorMap* map, uint32_t src, int c, int r) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c),
-                 "r"(r)
-                 : "memory");
-}
-
-__device__ __forceinline__ void t3_tma_load2d(uint32_t dst, const CUtensorMap* map, int c, int r, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-                 "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(r)
-                 : "memory");
-}
 
 struct T3Params {
     int M, n_mtiles, n_ntiles, ntaps, ncb0, ncb1, nkb;
@@ -1682,309 +1525,6 @@ conv_slab64_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Fused 7x7 / stride 2 / pad 3 stem (extractor.py:112) for thin inputs (K = 49 * Cin <= 256: event windows of 5 bins, RGB images).
-// Before: a patch-matrix kernel wrote 128 x 256 split-fp16 values per tile to HBM (79 MB per window) and a 1x1 GEMM read them back:
-// 88 us per 1x5x480x640 window.  Here the patch matrix never leaves the SM: per 8 x 16 tile of output pixels the worker warps fetch the
-// (2*8+5) x (2*16+5) x Cin fp32 input footprint with 16-byte cp.async (out-of-image = zero fill; a 3-D fp32 TMA box faulted on B200), the 8 worker warps expand it into the SWIZZLE_128B A
-// tile (4 k-blocks, hi | lo) in shared memory, warp 1 issues the MMAs against the resident weights, and the same 8 warps run the
-// epilogue of the previous tile while the tensor pipe works (two TMEM accumulators).
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int ST_PW = 28, ST_PH = 37;               // footprint: x in [16 tx - 4, 16 tx + 24) (7 aligned float4), y in [32 ty - 3, 32 ty + 34)
-constexpr int ST_MAXC = 5;
-constexpr int ST_XSHIFT = 1;                        // the footprint starts one pixel left of the first tap so that its rows are 16-byte aligned
-constexpr int ST_NKB = 4;                           // K padded to 256
-constexpr int ST_A_BYTES = ST_NKB * 2 * T3_A_BYTES; // 131072
-constexpr int ST_B_BYTES = ST_NKB * 2 * SL_BN * 128;// 65536
-constexpr int ST_PATCH_BYTES = ST_MAXC * ST_PH * ST_PW * 4;   // 28416
-
-struct StemParams {
-    int tiles_x, tiles_y, n_tiles, cin, c_total, K;
-    int n_win, ns, c_off[8];      // image n = window * ns + sample: channels [c_off[window], +cin) of input sample `sample`
-    int f16;
-    float acc_scale, in_scale, in_shift;
-    unsigned long long* tl;
-};
-
-__global__ void __launch_bounds__(T3_THREADS, 1)
-conv_stem7_kernel(const bflow_conv_desc d, const uint8_t* __restrict__ wtc, const StemParams p, int* err) {
-    constexpr int ACC_COLS = 2 * SL_BN;
-    constexpr int TMEM_COLS = 2 * ACC_COLS;
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (t3_smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t a_base = smem_base;                       // [kb][hi | lo][128][128 B]
-    const uint32_t b_base = a_base + ST_A_BYTES;             // resident weights
-    const uint32_t patch_u32 = b_base + ST_B_BYTES;          // [cin][37][32] fp32
-    const uint32_t bars = patch_u32 + ST_PATCH_BYTES;
-    const uint32_t a_full = bars + 8u, a_empty = bars + 16u, wbar = bars + 24u;
-    auto tfull_bar = [&](int a) { return bars + 32u + 8u * (uint32_t)a; };
-    const uint32_t tmem_slot = bars + 48u;
-    uint8_t* gen = smem_raw + (smem_base - t3_smem_u32(smem_raw));
-    const float* patch = reinterpret_cast<const float*>(gen + ST_A_BYTES + ST_B_BYTES);
-    int* koff = reinterpret_cast<int*>(gen + ST_A_BYTES + ST_B_BYTES + ST_PATCH_BYTES + 64);       // [256] patch offset of k, -1 beyond K
-    float* s_bias = reinterpret_cast<float*>(koff + 256);                                           // [64]
-    float* s_stat = s_bias + SL_BN;                                                                  // [2][64]
-    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;      // warp-uniform role index (see conv_tc3_kernel)
-    tl_begin(p.tl);
-    if (tid == 0) {
-        t3_mbar_init(a_full, 256);
-        t3_mbar_init(a_empty, 1);
-        t3_mbar_init(wbar, 1);
-        t3_mbar_init(tfull_bar(0), 1);
-        t3_mbar_init(tfull_bar(1), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    for (int k = tid; k < 256; k += T3_THREADS) {
-        int off = -1;
-        if (k < p.K) {
-            const int tap = k / p.cin, c = k - tap * p.cin;
-            const int kh = tap / 7, kw = tap - kh * 7;
-            off = (c * ST_PH + kh) * ST_PW + kw + ST_XSHIFT;
-        }
-        koff[k] = off;
-    }
-    t3_fence_before();
-    __syncthreads();
-    t3_fence_after();
-    uint32_t tmem_base;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-    const int tiles_per_img = p.tiles_x * p.tiles_y;
-    // footprint loader (worker threads): 16-byte cp.async with zero fill outside the image (W % 4 == 0, so a float4 is entirely in or out)
-    auto load_patch = [&](int tile, int etid_) {
-        const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
-        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-        const int gx0 = tx * 16 - 4, gy0 = ty * 32 - 3;
-        const int win = n / p.ns, nl = n - win * p.ns;
-        const float* src0 = d.x0 + ((size_t)nl * p.c_total + p.c_off[win]) * d.H * d.W;
-        const int total = p.cin * ST_PH * (ST_PW / 4);
-        for (int i = etid_; i < total; i += 256) {
-            const int x4 = i % (ST_PW / 4);
-            const int t = i / (ST_PW / 4);
-            const int yy = t % ST_PH, c = t / ST_PH;
-            const int gx = gx0 + x4 * 4, gy = gy0 + yy;
-            const bool ok = gx >= 0 && gx < d.W && gy >= 0 && gy < d.H;
-            const float* src = src0 + ((size_t)c * d.H + (ok ? gy : 0)) * d.W + (ok ? gx : 0);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(patch_u32 + (uint32_t)(i * 16)), "l"(src), "r"(ok ? 16 : 0) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
-    if (warp == 0) {
-        if (lane == 0) {
-            t3_mbar_arrive_expect_tx(wbar, ST_B_BYTES);
-            for (int kb = 0; kb < ST_NKB; ++kb) t3_bulk_g2s(b_base + (uint32_t)kb * (2 * SL_BN * 128), wtc + (size_t)kb * (2 * SL_BN * 128), 2 * SL_BN * 128, wbar);
-        }
-    } else if (warp == 1) {
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(SL_BN >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
-        const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * SL_BN) >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
-        t3_mbar_wait(wbar, 0u, err);
-        uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
-            t3_mbar_wait(a_full, lt & 1u, err);
-            t3_fence_after();
-            if (t3_elect_one()) {
-                const uint32_t tacc = tmem_base + (lt & 1u) * ACC_COLS;
-#pragma unroll
-                for (int kb = 0; kb < ST_NKB; ++kb) {
-                    const uint32_t a_hi = a_base + (uint32_t)kb * (2 * T3_A_BYTES), a_lo = a_hi + T3_A_BYTES;
-                    const uint32_t b = b_base + (uint32_t)kb * (2 * SL_BN * 128);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t ko = (uint32_t)k * 32u;
-                        const uint64_t dbh = t3_umma_desc(b + ko);
-                        if (p.f16) {
-                            t3_umma(tacc, t3_umma_desc(a_hi + ko), dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                        } else {
-                            t3_umma(tacc, t3_umma_desc(a_hi + ko), dbh, idesc2, (kb > 0 || k > 0) ? 1u : 0u);
-                            t3_umma(tacc, t3_umma_desc(a_lo + ko), dbh, idesc, 1u);
-                        }
-                    }
-                }
-                t3_commit(a_empty);
-                t3_commit(tfull_bar(lt & 1u));
-            }
-            __syncwarp();
-        }
-        t3_fence_before();
-    } else {
-        const int quad = warp & 3, chalf = (warp - 2) >> 2, etid = tid - 64;
-        for (int j = etid; j < SL_BN; j += 256) {
-            s_bias[j] = d.bias != nullptr ? __ldg(d.bias + j) : 0.f;
-            s_stat[j] = 0.f;
-            s_stat[SL_BN + j] = 0.f;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float lo1 = d.act1 == BFLOW_ACT_RELU ? 0.f : -INFINITY;
-        const float post = d.scale;
-        const bool affine = p.in_scale != 1.f || p.in_shift != 0.f;
-        int cur_img = -1;
-        auto flush_stats = [&](int img) {
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            for (int j = etid; j < SL_BN; j += 256) {
-                if (img >= 0) {
-                    atomicAdd(d.stats + ((size_t)img * d.Cout + j) * 2, (double)s_stat[j]);
-                    atomicAdd(d.stats + ((size_t)img * d.Cout + j) * 2 + 1, (double)s_stat[SL_BN + j]);
-                }
-                s_stat[j] = 0.f;
-                s_stat[SL_BN + j] = 0.f;
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-        };
-        // epilogue of local tile `lt_e` (global tile index `tile_e`): thread = pixel row, half of the 64 channels
-        auto epilogue = [&](int tile_e, uint32_t lt_e) {
-            const int n = tile_e / tiles_per_img, r = tile_e - n * tiles_per_img;
-            const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-            const int row = quad * 32 + lane;
-            const int y = ty * 16 + (row >> 3), x = tx * 8 + (row & 7);
-            const bool valid = y < d.Ho && x < d.Wo;
-            const size_t m = ((size_t)n * d.Ho + y) * d.Wo + x;
-            if (d.stats != nullptr && n != cur_img) {
-                flush_stats(cur_img);
-                cur_img = n;
-            }
-            t3_mbar_wait(tfull_bar(lt_e & 1u), (lt_e >> 1) & 1u, err);
-            t3_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (lt_e & 1u) * ACC_COLS + (uint32_t)(chalf * 32);
-            float v[32], u[32];
-            t3_tmem_ld16_nowait(taddr, v);
-            t3_tmem_ld16_nowait(taddr + 16u, v + 16);
-            if (!p.f16) {
-                t3_tmem_ld16_nowait(taddr + (uint32_t)SL_BN, u);
-                t3_tmem_ld16_nowait(taddr + (uint32_t)SL_BN + 16u, u + 16);
-            } else {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) u[c] = 0.f;
-            }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            t3_fence_before();
-            const int nb0 = chalf * 32;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = post * fmaf(v[c] + u[c], p.acc_scale, s_bias[nb0 + c]);
-            if (d.stats != nullptr) {
-#pragma unroll
-                for (int c = 0; c < 32; c += 16) {
-                    float sv[16], sq[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float xx = valid ? v[c + j] : 0.f;
-                        sv[j] = xx;
-                        sq[j] = xx * xx;
-                    }
-#pragma unroll
-                    for (int width = 8, bit = 16; width >= 1; width >>= 1, bit >>= 1) {
-                        const bool upper = (lane & bit) != 0;
-#pragma unroll
-                        for (int i = 0; i < width; ++i) {
-                            const float keep_s = upper ? sv[width + i] : sv[i], send_s = upper ? sv[i] : sv[width + i];
-                            const float keep_q = upper ? sq[width + i] : sq[i], send_q = upper ? sq[i] : sq[width + i];
-                            sv[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
-                            sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
-                        }
-                    }
-                    const float ts = sv[0] + __shfl_xor_sync(0xffffffffu, sv[0], 1);
-                    const float tq = sq[0] + __shfl_xor_sync(0xffffffffu, sq[0], 1);
-                    if ((lane & 1) == 0) {
-                        const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                        atomicAdd(s_stat + nb0 + c + col, ts);
-                        atomicAdd(s_stat + SL_BN + nb0 + c + col, tq);
-                    }
-                }
-            }
-            if (valid) {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], lo1);
-                if (d.y != nullptr) {
-                    float* yrow = d.y + m * d.ldy + nb0;
-#pragma unroll
-                    for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(yrow + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-                }
-                if (d.y16_hi != nullptr) {
-#pragma unroll
-                    for (int c = 0; c < 32; c += 8) {
-                        uint4 h4, l4;
-                        split2(v[c], v[c + 1], h4.x, l4.x);
-                        split2(v[c + 2], v[c + 3], h4.y, l4.y);
-                        split2(v[c + 4], v[c + 5], h4.z, l4.z);
-                        split2(v[c + 6], v[c + 7], h4.w, l4.w);
-                        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y16_hi) + m * d.ldy16 + nb0 + c) = h4;
-                        if (!p.f16) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y16_lo) + m * d.ldy16 + nb0 + c) = l4;
-                    }
-                }
-            }
-        };
-
-        // builder mapping: thread -> tile row (tid & 127) and one half of the 32 sixteen-byte chunks of the row's 256 k values
-        const int brow = etid & 127, bhalf = etid >> 7;
-        const int bpy = brow >> 3, bpx = brow & 7;
-        const int pbase = (2 * bpy) * ST_PW + 2 * bpx;                       // patch offset of tap (0, 0), channel 0
-        uint32_t lt = 0;
-        int prev_tile = -1;
-        if ((int)blockIdx.x < p.n_tiles) load_patch(blockIdx.x, etid);
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            asm volatile("bar.sync 1, 256;" ::: "memory");                    // every worker's share of the footprint has landed
-            if (lt > 0) t3_mbar_wait(a_empty, (lt - 1) & 1u, err);          // the MMAs of the previous tile have finished reading A
-            int iy0 = 0, ix0 = 0;
-            if (affine) {
-                const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
-                const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-                iy0 = 2 * (ty * 16 + bpy) - 3;
-                ix0 = 2 * (tx * 8 + bpx) - 3;
-            }
-#pragma unroll 1
-            for (int cc = 0; cc < 16; ++cc) {
-                const int chunk = bhalf * 16 + cc;                           // 0..31: k = chunk*8 .. chunk*8+7
-                const int kb = chunk >> 3, j = chunk & 7;
-                const int4 o0 = *reinterpret_cast<const int4*>(koff + chunk * 8), o1 = *reinterpret_cast<const int4*>(koff + chunk * 8 + 4);
-                const int offs[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-                float xv[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    float x = 0.f;
-                    if (offs[e] >= 0) {
-                        x = patch[pbase + offs[e]];
-                        if (affine) {
-                            // padding must stay zero AFTER the affine input map (raft.py:134 normalises before the conv pads)
-                            const int rem = offs[e] % (ST_PH * ST_PW);
-                            const int kh = rem / ST_PW, kw = rem - kh * ST_PW - ST_XSHIFT;
-                            const int iy = iy0 + kh, ix = ix0 + kw;
-                            x = (iy >= 0 && iy < d.H && ix >= 0 && ix < d.W) ? fmaf(x, p.in_scale, p.in_shift) : 0.f;
-                        }
-                    }
-                    xv[e] = x;
-                }
-                uint4 h4, l4;
-                split2(xv[0], xv[1], h4.x, l4.x);
-                split2(xv[2], xv[3], h4.y, l4.y);
-                split2(xv[4], xv[5], h4.z, l4.z);
-                split2(xv[6], xv[7], h4.w, l4.w);
-                uint8_t* dst = gen + kb * (2 * T3_A_BYTES) + brow * 128 + ((j ^ (brow & 7)) << 4);
-                *reinterpret_cast<uint4*>(dst) = h4;
-                if (!p.f16) *reinterpret_cast<uint4*>(dst + T3_A_BYTES) = l4;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of A -> visible to the tensor core
-            t3_mbar_arrive(a_full);
-            // the footprint buffer is free once every worker has read it: fetch the next tile's while the epilogue below runs
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (tile + (int)gridDim.x < p.n_tiles) load_patch(tile + gridDim.x, etid);
-            if (prev_tile >= 0) epilogue(prev_tile, lt - 1);
-            prev_tile = tile;
-        }
-        if (prev_tile >= 0) epilogue(prev_tile, lt - 1);
-        if (d.stats != nullptr) flush_stats(cur_img);
-    }
-    __syncthreads();
-    tl_end(p.tl);
-    if (warp == 1) {
-        t3_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*, const int*,
@@ -2490,56 +2030,4 @@ extern "C" int bflow_conv2d_slab64(const bflow_conv_desc* dp, const void* maps, 
     const int grid = p.n_tiles < bflow::num_sms() ? p.n_tiles : bflow::num_sms();
     bflow::conv_slab64_kernel<<<grid, bflow::T3_THREADS, smem, (cudaStream_t)stream>>>(tm[0], tm[1], d, reinterpret_cast<const uint8_t*>(w_tc), p, err);
     return bflow::check_launch("bflow_conv2d_slab64");
-}
-
-// Fused stem: 7x7 / stride 2 / pad 3, channels [c_off, c_off + cin) of an fp32 NCHW input (49 * cin <= 256) -> 64 channels, input mapped
-// x -> in_scale * x + in_shift first (raft.py:134).  d carries the output side (N, H, W, Ho, Wo, Cout = 64, bias, act1, y / y16, stats);
-// x0: the fp32 NCHW input; w_tc: tc3 weight image (bn 64) of the [64][256] matrix with K = (kh*7+kw)*cin + c.
-extern "C" int bflow_conv2d_stem7(const bflow_conv_desc* dp, const void* w_tc, int c_total, const int* c_offs, int n_windows, float in_scale,
-                                  float in_shift, float acc_scale, int* err, void* stream) {
-    BFLOW_CHECK_DESC(dp, bflow_conv_desc, "conv_stem7");
-    BFLOW_REQUIRE(w_tc != nullptr, "conv_stem7: null argument");
-    BFLOW_REQUIRE(dp->x0 != nullptr && bflow::aligned16(dp->x0) && dp->W % 4 == 0, "conv_stem7: x0 = 16-byte aligned fp32 NCHW input, W % 4 == 0");
-    const bflow_conv_desc& d = *dp;
-    BFLOW_REQUIRE(d.c0 > 0 && d.c0 <= bflow::ST_MAXC && 49 * d.c0 <= 256 && d.c1 == 0 && d.Cout == 64, "conv_stem7: cin <= 5, Cout == 64");
-    BFLOW_REQUIRE(d.KH == 7 && d.KW == 7 && d.stride == 2 && d.pad_h == 3 && d.pad_w == 3, "conv_stem7: 7x7 / 2 / pad 3 only");
-    BFLOW_REQUIRE(d.N > 0 && d.H > 0 && d.W > 0 && d.Ho == (d.H - 1) / 2 + 1 && d.Wo == (d.W - 1) / 2 + 1, "conv_stem7: Ho/Wo mismatch");
-    BFLOW_REQUIRE(c_offs != nullptr && n_windows >= 1 && n_windows <= 8 && d.N % n_windows == 0, "conv_stem7: 1..8 channel windows, N = windows * samples");
-    for (int i = 0; i < n_windows; ++i) BFLOW_REQUIRE(c_offs[i] >= 0 && c_offs[i] + d.c0 <= c_total, "conv_stem7: channel window");
-    BFLOW_REQUIRE(d.epi == BFLOW_EPI_STD && d.res == nullptr && d.res16_hi == nullptr && d.act1 <= BFLOW_ACT_RELU && d.act2 == BFLOW_ACT_NONE, "conv_stem7: plain epilogue (none / relu)");
-    BFLOW_REQUIRE((d.y == nullptr || (d.ldy >= 64 && d.ldy % 4 == 0 && bflow::aligned16(d.y))), "conv_stem7: fp32 output alignment");
-    BFLOW_REQUIRE(d.y16_hi == nullptr || (d.y16_lo != nullptr && d.ldy16 % 8 == 0 && bflow::aligned16(d.y16_hi) && bflow::aligned16(d.y16_lo)), "conv_stem7: split output alignment");
-    BFLOW_REQUIRE(d.stats == nullptr || d.act1 == BFLOW_ACT_NONE, "conv_stem7: fused statistics need the plain epilogue");
-    if (const char* msg = bflow::check_epilogue(d)) { bflow::set_error(msg); return BFLOW_ERR_INVALID; }
-    bflow::StemParams p;
-    p.tiles_x = (d.Wo + 7) / 8;
-    p.tiles_y = (d.Ho + 15) / 16;
-    const long long nt = (long long)d.N * p.tiles_x * p.tiles_y;
-    BFLOW_REQUIRE(nt < (1ll << 31), "conv_stem7: too large");
-    p.n_tiles = (int)nt;
-    p.cin = d.c0;
-    p.c_total = c_total;
-    p.n_win = n_windows;
-    p.ns = d.N / n_windows;
-    for (int i = 0; i < 8; ++i) p.c_off[i] = i < n_windows ? c_offs[i] : 0;
-    p.K = 49 * d.c0;
-    p.acc_scale = acc_scale;
-    p.in_scale = in_scale;
-    p.in_shift = in_shift;
-    BFLOW_REQUIRE(d.precision == BFLOW_PREC_SPLIT3 || d.precision == BFLOW_PREC_F16, "conv_stem7: unknown precision");
-    p.f16 = d.precision == BFLOW_PREC_F16 ? 1 : 0;
-    p.tl = bflow::timeline_next_slot("stem7");
-    constexpr int smem = bflow::ST_A_BYTES + bflow::ST_B_BYTES + bflow::ST_PATCH_BYTES + 64 + 256 * 4 + 3 * 64 * 4 + 1024;
-    static bflow::PerDeviceFlag configured;
-    if (!configured.get()) {
-        cudaError_t e = cudaFuncSetAttribute(bflow::conv_stem7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) {
-            bflow::set_error(cudaGetErrorString(e));
-            return BFLOW_ERR_CUDA;
-        }
-        configured.set();
-    }
-    const int grid = p.n_tiles < bflow::num_sms() ? p.n_tiles : bflow::num_sms();
-    bflow::conv_stem7_kernel<<<grid, bflow::T3_THREADS, smem, (cudaStream_t)stream>>>(d, reinterpret_cast<const uint8_t*>(w_tc), p, err);
-    return bflow::check_launch("bflow_conv2d_stem7");
 }

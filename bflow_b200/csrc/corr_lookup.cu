@@ -339,6 +339,7 @@ extern "C" int bflow_corr_lookup(const bflow_lookup_desc* dp, void* stream) {
         }
         const int sms = bflow::num_sms();
         cudaError_t le;
+        static const bool lk_pdl = [] { const char* e = getenv("BFLOW_LOOKUP_PDL"); return !(e != nullptr && e[0] == '0'); }();
         unsigned long long* tls = bflow::timeline_next_slot("corr_lookup");
         bflow::LookupDivs dv;
         dv.S = bflow::make_fastdiv((unsigned)d.n_slots);
@@ -351,7 +352,7 @@ extern "C" int bflow_corr_lookup(const bflow_lookup_desc* dp, void* stream) {
             // one wave of CTAs, units dealt round-robin (at most 8 units per warp; beyond that the per-pixel walk below is as balanced)
             long long g = bflow::ceil_div_ll(n_units, bflow::LK2_WARPS);
             if (g > (long long)sms * occ) g = (long long)sms * occ;
-            le = bflow::launch_pdl(bflow::corr_lookup_tiled_kernel<true>, dim3((unsigned)g), dim3(bflow::LK2_WARPS * 32), 0, (cudaStream_t)stream, d, dv, n_units, 0, tls);
+            le = bflow::launch_pdl_if(lk_pdl, bflow::corr_lookup_tiled_kernel<true>, dim3((unsigned)g), dim3(bflow::LK2_WARPS * 32), 0, (cudaStream_t)stream, d, dv, n_units, 0, tls);
         } else {
             long long g = bflow::ceil_div_ll(BQ, bflow::LK2_WARPS);
             const long long cap = (long long)sms * 8 * 8;
@@ -362,7 +363,7 @@ extern "C" int bflow_corr_lookup(const bflow_lookup_desc* dp, void* stream) {
             if (groups > d.n_slots) groups = d.n_slots;
             const int spg = (int)bflow::ceil_div_ll(d.n_slots, groups);
             dim3 grid2((unsigned)g, (unsigned)bflow::ceil_div(d.n_slots, spg));
-            le = bflow::launch_pdl(bflow::corr_lookup_tiled_kernel<false>, grid2, dim3(bflow::LK2_WARPS * 32), 0, (cudaStream_t)stream, d, dv, n_units, spg, tls);
+            le = bflow::launch_pdl_if(lk_pdl, bflow::corr_lookup_tiled_kernel<false>, grid2, dim3(bflow::LK2_WARPS * 32), 0, (cudaStream_t)stream, d, dv, n_units, spg, tls);
         }
         if (le != cudaSuccess) {
             bflow::set_error(cudaGetErrorString(le));

@@ -570,7 +570,7 @@ class _Plan(S16Recorder):
     def launch_all(self):
         main = torch.cuda.current_stream(self.eng.device)
         if self.side_stream is None:
-            self.side_stream = torch.cuda.Stream(device=self.eng.device)
+            self.side_stream = torch.cuda.Stream(device=self.eng.device, priority=int(os.environ.get('BFLOW_SIDE_PRIORITY', '0')))
         side = self.side_stream
         handles = (main.cuda_stream, side.cuda_stream)
         use_side = self.eng.use_side_stream
