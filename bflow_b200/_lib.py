@@ -47,7 +47,7 @@ class ConvDesc(_Desc):
                 ('y16_hi', C.c_void_p), ('y16_lo', C.c_void_p), ('ldy16', C.c_int),
                 ('res16_hi', C.c_void_p), ('res16_lo', C.c_void_p), ('ldr16', C.c_int),
                 ('aux1_16_hi', C.c_void_p), ('aux1_16_lo', C.c_void_p), ('ld_aux1_16', C.c_int),
-                ('stats', C.c_void_p), ('stats_hw', C.c_int)]
+                ('stats', C.c_void_p), ('stats_hw', C.c_int), ('max_ctas', C.c_int)]
 
 
 class LookupDesc(_Desc):

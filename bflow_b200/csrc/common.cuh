@@ -259,6 +259,8 @@ __device__ __forceinline__ void tl_end(unsigned long long* slot) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool pdl_enabled();      // runtime.cu: BFLOW_PDL != 0 (default on)
+// CTA budget of a persistent launch: one per SM, or fewer when the descriptor says so (bflow_conv_desc::max_ctas)
+inline int grid_cap(const bflow_conv_desc& d) { const int s = num_sms(); return (d.max_ctas > 0 && d.max_ctas < s) ? d.max_ctas : s; }
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl_if(bool on, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {

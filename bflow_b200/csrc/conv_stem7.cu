@@ -8,9 +8,13 @@
 //                       96 of its 194 us in this expansion);
 //   warp 1              issues the MMAs of k-block kb as soon as that block is built (per-k-block full / empty barriers: the expansion
 //                       of tile i+1 overwrites block kb while the MMAs of tile i still read blocks kb+1..3) against the resident weights;
-//   epilogue warps (8)  drain the other TMEM accumulator: InstanceNorm statistics, bias / ReLU, fp32 and split-fp16 stores.
+//   epilogue warps (8)  drain the other TMEM accumulator; an 8 x 8 in-warp transpose turns TMEM's row-per-thread layout into whole 128-byte
+//                       rows per store instruction (row-per-thread stores touched 32 lines per instruction: 33 us of 109), and leaves the
+//                       InstanceNorm column sums two shuffle steps away; bias / ReLU, fp32 and split-fp16 stores.
 // Before (one set of 8 worker warps doing expansion and epilogue in turn, one A buffer handed over whole): 9.5 us per tile, 194 us per
-// 5 x 480 x 640 window batch.  Measured split of that: expansion 96 us, epilogue 59 us, MMA + hand-overs 44 us, all serial.
+// 5 x 480 x 640 window batch; measured split of that: expansion 96 us, epilogue 59 us, MMA + hand-overs 44 us, all serial.
+// Now 87 us (MMAs alone: 36 us; what remains is shared-memory traffic -- 128 KB of A written and 224 KB of operands read per tile --
+// shared by the three roles).
 #include <cuda.h>
 #include <stdlib.h>
 #include "tc3_common.cuh"
@@ -34,45 +38,53 @@ struct StemParams {
     int tiles_x, tiles_y, n_tiles, c_total;
     int n_win, ns, c_off[8];      // image n = window * ns + sample: channels [c_off[window], +cin) of input sample `sample`
     int f16;
-    int dbg;
     float acc_scale, in_scale, in_shift;
     unsigned long long* tl;
 };
 
-// footprint offset (relative to the pixel's tap (0, 0) of channel 0) of K index k = (kh*7 + kw)*CIN + c; -1 beyond K
-template <int CIN>
-__host__ __device__ constexpr int st_koff(int k) {
-    return k < 49 * CIN ? ((k % CIN) * ST_PH + (k / CIN) / 7) * ST_PW + (k / CIN) % 7 + ST_XSHIFT : -1;
-}
+// footprint offset (relative to the pixel's tap (0, 0) of channel 0) of K index k = (c*7 + kh)*7 + kw (the natural OIHW order of the
+// weights: consecutive k walk along a footprint row, so two neighbouring taps are one 8-byte shared-memory load)
+__host__ __device__ constexpr int st_koff(int k) { return ((k / 49) * ST_PH + (k % 49) / 7) * ST_PW + k % 7 + ST_XSHIFT; }
 
-// four 16-byte chunks (j = 4 Q .. 4 Q + 3) of k-block KB of one A row: 32 footprint values, split, swizzled stores
+// four 16-byte chunks (j = 4 Q .. 4 Q + 3) of k-block KB of one A row: 32 footprint values, split, swizzled stores.  px (the pixel's
+// tap (0, 0) of channel 0) is 8-byte aligned and st_koff is even for odd kw: taps (1,2), (3,4), (5,6) of a row are loaded as pairs.
 template <int CIN, bool AFFINE, int KB, int Q>
 __device__ __forceinline__ void st_build(const float* __restrict__ px, uint8_t* a_row, const int row7, const bool f16, const unsigned rowmask,
                                          const unsigned colmask, const float in_scale, const float in_shift) {
+    constexpr int K = 49 * CIN, k0 = KB * 64 + Q * 32;
+    float xv[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+        const int k = k0 + e, kw = k % 7;
+        if (k >= K) {
+            xv[e] = 0.f;
+        } else if (kw >= 2 && (kw & 1) == 0 && e >= 1) {
+            // second half of the pair loaded at e - 1
+        } else if ((kw & 1) && e + 1 < 32 && k + 1 < K) {
+            const float2 t = *reinterpret_cast<const float2*>(px + st_koff(k));
+            xv[e] = t.x;
+            xv[e + 1] = t.y;
+        } else {
+            xv[e] = px[st_koff(k)];
+        }
+    }
+    if (AFFINE) {
+        // padding must stay zero AFTER the affine input map (raft.py:134 normalises before the conv pads)
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const int k = k0 + e, kh = (k % 49) / 7, kw = k % 7;
+            if (k < K) xv[e] = (((rowmask >> kh) & (colmask >> kw)) & 1u) ? fmaf(xv[e], in_scale, in_shift) : 0.f;
+        }
+    }
 #pragma unroll
     for (int cj = 0; cj < 4; ++cj) {
         const int j = Q * 4 + cj;
-        float xv[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int k = KB * 64 + j * 8 + e;
-            const int off = st_koff<CIN>(k);
-            float x = 0.f;
-            if (off >= 0) {
-                x = px[off];
-                if (AFFINE) {
-                    // padding must stay zero AFTER the affine input map (raft.py:134 normalises before the conv pads)
-                    const int kh = (k / CIN) / 7, kw = (k / CIN) % 7;
-                    x = (((rowmask >> kh) & (colmask >> kw)) & 1u) ? fmaf(x, in_scale, in_shift) : 0.f;
-                }
-            }
-            xv[e] = x;
-        }
+        const float* x8 = xv + cj * 8;
         uint4 h4, l4;
-        split2(xv[0], xv[1], h4.x, l4.x);
-        split2(xv[2], xv[3], h4.y, l4.y);
-        split2(xv[4], xv[5], h4.z, l4.z);
-        split2(xv[6], xv[7], h4.w, l4.w);
+        split2(x8[0], x8[1], h4.x, l4.x);
+        split2(x8[2], x8[3], h4.y, l4.y);
+        split2(x8[4], x8[5], h4.z, l4.z);
+        split2(x8[6], x8[7], h4.w, l4.w);
         uint8_t* dst = a_row + KB * (2 * T3_A_BYTES) + ((j ^ row7) << 4);
         *reinterpret_cast<uint4*>(dst) = h4;
         if (!f16) *reinterpret_cast<uint4*>(dst + T3_A_BYTES) = l4;
@@ -176,7 +188,7 @@ conv_stem7_kernel(const bflow_conv_desc d, const uint8_t* __restrict__ wtc, cons
             const int win = n / p.ns, nl = n - win * p.ns;
             const float* src0 = d.x0 + ((size_t)nl * p.c_total + p.c_off[win]) * d.H * d.W;
             const uint32_t dst0 = patch_u32 + buf * ST_PATCH_BYTES;
-            const int total = (p.dbg & 4) ? 0 : CIN * ST_PH * (ST_PW / 4);
+            constexpr int total = CIN * ST_PH * (ST_PW / 4);
             for (int i = btid; i < total; i += 256) {
                 const int x4 = i % (ST_PW / 4);
                 const int t = i / (ST_PW / 4);
@@ -217,7 +229,6 @@ conv_stem7_kernel(const bflow_conv_desc d, const uint8_t* __restrict__ wtc, cons
             const uint32_t eph = (lt & 1u) ^ 1u;          // the MMAs of the previous tile have finished reading the k-block
 #define ST_BUILD_KB(KB)                                                                                                       \
             t3_mbar_wait(aempty_bar(KB), eph, err);                                                                           \
-            if (p.dbg & 1) {} else                                                                                            \
             if (q == 0) st_build<CIN, AFFINE, KB, 0>(px, a_row, row7, f16, rowmask, colmask, p.in_scale, p.in_shift);         \
             else st_build<CIN, AFFINE, KB, 1>(px, a_row, row7, f16, rowmask, colmask, p.in_scale, p.in_shift);                \
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      /* generic-proxy writes of A -> visible to the tensor core */ \
@@ -252,16 +263,14 @@ conv_stem7_kernel(const bflow_conv_desc d, const uint8_t* __restrict__ wtc, cons
             }
             asm volatile("bar.sync 2, 256;" ::: "memory");
         };
-        const int row = quad * 32 + lane;
         const int nb0 = chalf * 32;
+        const int b4 = (lane & 7) * 4;                 // after the in-warp transpose a lane owns columns nb0 + b4 .. + 3
+        const float bias4[4] = {s_bias[nb0 + b4], s_bias[nb0 + b4 + 1], s_bias[nb0 + b4 + 2], s_bias[nb0 + b4 + 3]};
         uint32_t lt = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
-            // thread = pixel row of the tile, half of the 64 channels
+            // TMEM: thread = pixel row of the tile (quad*32 + lane), half of the 64 channels
             const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
             const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-            const int y = ty * 8 + (row >> 4), x = tx * 16 + (row & 15);
-            const bool valid = y < d.Ho && x < d.Wo;
-            const size_t m = ((size_t)n * d.Ho + y) * d.Wo + x;
             if (d.stats != nullptr && n != cur_img) {
                 flush_stats(cur_img);
                 cur_img = n;
@@ -287,56 +296,74 @@ conv_stem7_kernel(const bflow_conv_desc d, const uint8_t* __restrict__ wtc, cons
                 __syncwarp();
                 if (lane == 0) t3_mbar_arrive(tempty_bar(acc));        // the MMAs of tile lt + 2 may overwrite this accumulator
 #pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = post * fmaf(v[c] + u[c], p.acc_scale, s_bias[nb0 + c]);
+                for (int c = 0; c < 32; ++c) v[c] += u[c];
             }
-            if (d.stats != nullptr && !(p.dbg & 16)) {
+            // 8 x 8 transpose inside every group of 8 lanes (3 butterfly steps over the 16-byte chunks): afterwards lane (g, b) holds columns
+            // nb0 + 4b .. 4b + 3 of the tile rows quad*32 + 8g + c, c = 0..7, so that one store instruction writes whole 128-byte rows
+            // (row-per-thread stores touched 32 lines per instruction; measured 33 of the kernel's 109 us)
 #pragma unroll
-                for (int c = 0; c < 32; c += 16) {
-                    float sv[16], sq[16];
+            for (int bit = 4; bit >= 1; bit >>= 1) {
+                const bool upper = (lane & bit) != 0;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float xx = valid ? v[c + j] : 0.f;
-                        sv[j] = xx;
-                        sq[j] = xx * xx;
+                for (int c = 0; c < 8; ++c) {
+                    if (c & bit) continue;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float send = upper ? v[4 * c + j] : v[4 * (c | bit) + j];
+                        const float recv = __shfl_xor_sync(0xffffffffu, send, bit);
+                        if (upper) v[4 * c + j] = recv;
+                        else v[4 * (c | bit) + j] = recv;
                     }
+                }
+            }
+            const int g = lane >> 3;
 #pragma unroll
-                    for (int width = 8, bit = 16; width >= 1; width >>= 1, bit >>= 1) {
-                        const bool upper = (lane & bit) != 0;
+            for (int c = 0; c < 8; ++c)
 #pragma unroll
-                        for (int i = 0; i < width; ++i) {
-                            const float keep_s = upper ? sv[width + i] : sv[i], send_s = upper ? sv[i] : sv[width + i];
-                            const float keep_q = upper ? sq[width + i] : sq[i], send_q = upper ? sq[i] : sq[width + i];
-                            sv[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
-                            sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
+                for (int j = 0; j < 4; ++j) v[4 * c + j] = post * fmaf(v[4 * c + j], p.acc_scale, bias4[j]);
+            const int yy = ty * 8 + quad * 2 + (g >> 1), x0 = tx * 16 + (g & 1) * 8;
+            const size_t m0 = ((size_t)n * d.Ho + yy) * d.Wo + x0;
+            const int nvalid = yy < d.Ho ? min(8, d.Wo - x0) : 0;             // rows c < nvalid are inside the image
+            if (d.stats != nullptr) {
+                float s[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c < nvalid) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            s[j] += v[4 * c + j];
+                            sq[j] = fmaf(v[4 * c + j], v[4 * c + j], sq[j]);
                         }
                     }
-                    const float ts = sv[0] + __shfl_xor_sync(0xffffffffu, sv[0], 1);
-                    const float tq = sq[0] + __shfl_xor_sync(0xffffffffu, sq[0], 1);
-                    if ((lane & 1) == 0) {
-                        const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                        atomicAdd(s_stat + nb0 + c + col, ts);
-                        atomicAdd(s_stat + ST_BN + nb0 + c + col, tq);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    s[j] += __shfl_xor_sync(0xffffffffu, s[j], 8);
+                    sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], 8);
+                    s[j] += __shfl_xor_sync(0xffffffffu, s[j], 16);
+                    sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], 16);
+                }
+                if (g == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        atomicAdd(s_stat + nb0 + b4 + j, s[j]);
+                        atomicAdd(s_stat + ST_BN + nb0 + b4 + j, sq[j]);
                     }
                 }
             }
-            if (valid && !(p.dbg & 2)) {
+            {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], lo1);
-                if (d.y != nullptr) {
-                    float* yrow = d.y + m * d.ldy + nb0;
-#pragma unroll
-                    for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(yrow + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-                }
-                if (d.y16_hi != nullptr) {
-#pragma unroll
-                    for (int c = 0; c < 32; c += 8) {
-                        uint4 h4, l4;
-                        split2(v[c], v[c + 1], h4.x, l4.x);
-                        split2(v[c + 2], v[c + 3], h4.y, l4.y);
-                        split2(v[c + 4], v[c + 5], h4.z, l4.z);
-                        split2(v[c + 6], v[c + 7], h4.w, l4.w);
-                        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y16_hi) + m * d.ldy16 + nb0 + c) = h4;
-                        if (!p.f16) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y16_lo) + m * d.ldy16 + nb0 + c) = l4;
+                for (int c = 0; c < 8; ++c) {
+                    if (c < nvalid) {
+                        const float o0 = fmaxf(v[4 * c], lo1), o1 = fmaxf(v[4 * c + 1], lo1), o2 = fmaxf(v[4 * c + 2], lo1), o3 = fmaxf(v[4 * c + 3], lo1);
+                        if (d.y != nullptr) *reinterpret_cast<float4*>(d.y + (m0 + c) * d.ldy + nb0 + b4) = make_float4(o0, o1, o2, o3);
+                        if (d.y16_hi != nullptr) {
+                            uint2 h2, l2;
+                            split2(o0, o1, h2.x, l2.x);
+                            split2(o2, o3, h2.y, l2.y);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(d.y16_hi) + (m0 + c) * d.ldy16 + nb0 + b4) = h2;
+                            if (!p.f16) *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(d.y16_lo) + (m0 + c) * d.ldy16 + nb0 + b4) = l2;
+                        }
                     }
                 }
             }
@@ -367,7 +394,7 @@ static cudaError_t stem7_launch(int grid, cudaStream_t stream, const bflow_conv_
 
 // Fused stem: 7x7 / stride 2 / pad 3, channels [c_off, c_off + cin) of an fp32 NCHW input (49 * cin <= 256) -> 64 channels, input mapped
 // x -> in_scale * x + in_shift first (raft.py:134).  d carries the output side (N, H, W, Ho, Wo, Cout = 64, bias, act1, y / y16, stats);
-// x0: the fp32 NCHW input; w_tc: tc3 weight image (bn 64) of the [64][256] matrix with K = (kh*7+kw)*cin + c.
+// x0: the fp32 NCHW input; w_tc: tc3 weight image (bn 64) of the [64][256] matrix with K = (c*7+kh)*7+kw (OIHW order).
 extern "C" int bflow_conv2d_stem7(const bflow_conv_desc* dp, const void* w_tc, int c_total, const int* c_offs, int n_windows, float in_scale,
                                   float in_shift, float acc_scale, int* err, void* stream) {
     BFLOW_CHECK_DESC(dp, bflow_conv_desc, "conv_stem7");
@@ -399,10 +426,8 @@ extern "C" int bflow_conv2d_stem7(const bflow_conv_desc* dp, const void* w_tc, i
     p.in_shift = in_shift;
     BFLOW_REQUIRE(d.precision == BFLOW_PREC_SPLIT3 || d.precision == BFLOW_PREC_F16, "conv_stem7: unknown precision");
     p.f16 = d.precision == BFLOW_PREC_F16 ? 1 : 0;
-    static const int stem_dbg = [] { const char* e = getenv("BFLOW_STEM_DBG"); return e != nullptr ? atoi(e) : 0; }();
-    p.dbg = stem_dbg;
     p.tl = bflow::timeline_next_slot("stem7");
-    const int grid = p.n_tiles < bflow::num_sms() ? p.n_tiles : bflow::num_sms();
+    const int grid = p.n_tiles < bflow::grid_cap(d) ? p.n_tiles : bflow::grid_cap(d);
     const bool affine = in_scale != 1.f || in_shift != 0.f;
     const uint8_t* w8 = reinterpret_cast<const uint8_t*>(w_tc);
     cudaStream_t st = (cudaStream_t)stream;

@@ -1419,97 +1419,129 @@ conv_slab64_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
         };
+        const int nb0 = chalf * 32;
+        const int b4 = (lane & 7) * 4;                 // after the in-warp transpose a lane owns channels nb0 + b4 .. + 3
+        const float bias4[4] = {s_bias[nb0 + b4], s_bias[nb0 + b4 + 1], s_bias[nb0 + b4 + 2], s_bias[nb0 + b4 + 3]};
         uint32_t lt = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
             const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
             const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-            const int row = quad * 32 + lane;
-            const int y = ty * 16 + (row >> 3), x = tx * 8 + (row & 7);
-            const bool valid = y < d.H;
-            const size_t m = ((size_t)n * d.H + y) * d.W + x;
             if (d.stats != nullptr && n != cur_img) {
                 flush_stats(cur_img);
                 cur_img = n;
             }
+            // after the in-warp transpose below, lane (g, b) owns channels nb0 + 4b .. + 3 of the 8 pixels of image row ty*16 + quad*4 + g
+            const int g = lane >> 3;
+            const int y = ty * 16 + quad * 4 + g;
+            const bool valid = y < d.H;
+            const size_t m0 = ((size_t)n * d.H + y) * d.W + tx * 8;
+            // the residual rows are requested BEFORE the wait for the accumulator: their latency (several microseconds when the other
+            // stream's InstanceNorm pass saturates HBM) then hides behind this tile's MMAs instead of stretching the epilogue
+            // (raw 8-byte loads, converted after the wait: written as load_res16_4 calls the compiler kept one branch per row and the 16
+            // loads went out one after the other -- 4.3 us per tile, twice the tile's MMA time)
+            uint2 rh[8], rl[8];
+            {
+                const bool has_res = valid && d.res16_hi != nullptr, has_lo = has_res && d.precision != BFLOW_PREC_F16;
+                const __half* rhp = reinterpret_cast<const __half*>(d.res16_hi) + m0 * d.ldr16 + nb0 + b4;
+                const __half* rlp = reinterpret_cast<const __half*>(d.res16_lo) + m0 * d.ldr16 + nb0 + b4;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    rh[c] = has_res ? *reinterpret_cast<const uint2*>(rhp + (size_t)c * d.ldr16) : make_uint2(0u, 0u);
+                    rl[c] = has_lo ? *reinterpret_cast<const uint2*>(rlp + (size_t)c * d.ldr16) : make_uint2(0u, 0u);
+                }
+            }
             const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
             t3_mbar_wait(tfull_bar(acc), aph, err);
             t3_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_COLS + (uint32_t)(chalf * 32);
-            float v[32], u[32];
-            t3_tmem_ld16_nowait(taddr, v);
-            t3_tmem_ld16_nowait(taddr + 16u, v + 16);
-            if (!p.f16) {
-                t3_tmem_ld16_nowait(taddr + (uint32_t)SL_BN, u);
-                t3_tmem_ld16_nowait(taddr + (uint32_t)SL_BN + 16u, u + 16);
-            } else {
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_COLS + (uint32_t)nb0;
+            float v[32];
+            {
+                float u[32];
+                t3_tmem_ld16_nowait(taddr, v);
+                t3_tmem_ld16_nowait(taddr + 16u, v + 16);
+                if (!p.f16) {
+                    t3_tmem_ld16_nowait(taddr + (uint32_t)SL_BN, u);
+                    t3_tmem_ld16_nowait(taddr + (uint32_t)SL_BN + 16u, u + 16);
+                } else {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) u[c] = 0.f;
+                    for (int c = 0; c < 32; ++c) u[c] = 0.f;
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                t3_fence_before();
+                __syncwarp();
+                if (lane == 0) t3_mbar_arrive(tempty_bar(acc));
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] += u[c];
             }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            t3_fence_before();
-            __syncwarp();
-            if (lane == 0) t3_mbar_arrive(tempty_bar(acc));
-            const int nb0 = chalf * 32;
+            // TMEM hands a thread one tile row (= pixel) and 32 consecutive channels.  8 x 8 transpose inside every group of 8 lanes (3
+            // butterfly steps over the 16-byte chunks): afterwards lane (g, b) holds channels nb0 + 4b .. 4b + 3 of the 8 pixels of image row
+            // ty*16 + quad*4 + g, so one store instruction writes whole 128-byte rows instead of touching 32 lines, and the column sums of
+            // the InstanceNorm statistics need 2 shuffle steps instead of 5 (measured on the stem kernel: stores 33 -> 11 us of 109)
 #pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = post * fmaf(v[c] + u[c], p.acc_scale, s_bias[nb0 + c]);
+            for (int bit = 4; bit >= 1; bit >>= 1) {
+                const bool upper = (lane & bit) != 0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c & bit) continue;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float send = upper ? v[4 * c + j] : v[4 * (c | bit) + j];
+                        const float recv = __shfl_xor_sync(0xffffffffu, send, bit);
+                        if (upper) v[4 * c + j] = recv;
+                        else v[4 * (c | bit) + j] = recv;
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[4 * c + j] = post * fmaf(v[4 * c + j], p.acc_scale, bias4[j]);
             if (d.stats != nullptr) {
-                // column sums over the warp's 32 rows: butterfly transpose-reduce, 16 columns at a time (as in conv_tc3_kernel)
+                float s[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+                if (valid) {
 #pragma unroll
-                for (int c = 0; c < 32; c += 16) {
-                    float sv[16], sq[16];
+                    for (int c = 0; c < 8; ++c)
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float xx = valid ? v[c + j] : 0.f;
-                        sv[j] = xx;
-                        sq[j] = xx * xx;
-                    }
-#pragma unroll
-                    for (int width = 8, bit = 16; width >= 1; width >>= 1, bit >>= 1) {
-                        const bool upper = (lane & bit) != 0;
-#pragma unroll
-                        for (int i = 0; i < width; ++i) {
-                            const float keep_s = upper ? sv[width + i] : sv[i], send_s = upper ? sv[i] : sv[width + i];
-                            const float keep_q = upper ? sq[width + i] : sq[i], send_q = upper ? sq[i] : sq[width + i];
-                            sv[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
-                            sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
+                        for (int j = 0; j < 4; ++j) {
+                            s[j] += v[4 * c + j];
+                            sq[j] = fmaf(v[4 * c + j], v[4 * c + j], sq[j]);
                         }
-                    }
-                    const float ts = sv[0] + __shfl_xor_sync(0xffffffffu, sv[0], 1);
-                    const float tq = sq[0] + __shfl_xor_sync(0xffffffffu, sq[0], 1);
-                    if ((lane & 1) == 0) {
-                        const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                        atomicAdd(s_stat + nb0 + c + col, ts);
-                        atomicAdd(s_stat + SL_BN + nb0 + c + col, tq);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    s[j] += __shfl_xor_sync(0xffffffffu, s[j], 8);
+                    sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], 8);
+                    s[j] += __shfl_xor_sync(0xffffffffu, s[j], 16);
+                    sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], 16);
+                }
+                if (g == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        atomicAdd(s_stat + nb0 + b4 + j, s[j]);
+                        atomicAdd(s_stat + SL_BN + nb0 + b4 + j, sq[j]);
                     }
                 }
             }
             if (valid) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], lo1);
-                if (d.res16_hi != nullptr) {
+                for (int c = 0; c < 8; ++c) {
+                    float o[4];
 #pragma unroll
-                    for (int c = 0; c < 32; c += 4) {
-                        const float4 r4 = load_res16_4(d, m * d.ldr16 + nb0 + c);
-                        v[c] += r4.x; v[c + 1] += r4.y; v[c + 2] += r4.z; v[c + 3] += r4.w;
+                    for (int j = 0; j < 4; ++j) o[j] = fmaxf(v[4 * c + j], lo1);
+                    {
+                        const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&rh[c].x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&rh[c].y));
+                        const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&rl[c].x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&rl[c].y));
+                        o[0] += h0.x + l0.x; o[1] += h0.y + l0.y; o[2] += h1.x + l1.x; o[3] += h1.y + l1.y;
                     }
-                }
 #pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], lo2);
-                if (d.y != nullptr) {
-                    float* yrow = d.y + m * d.ldy + nb0;
-#pragma unroll
-                    for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(yrow + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-                }
-                if (d.y16_hi != nullptr) {
-#pragma unroll
-                    for (int c = 0; c < 32; c += 8) {
-                        uint4 h4, l4;
-                        split2(v[c], v[c + 1], h4.x, l4.x);
-                        split2(v[c + 2], v[c + 3], h4.y, l4.y);
-                        split2(v[c + 4], v[c + 5], h4.z, l4.z);
-                        split2(v[c + 6], v[c + 7], h4.w, l4.w);
-                        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y16_hi) + m * d.ldy16 + nb0 + c) = h4;
-                        if (!p.f16) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y16_lo) + m * d.ldy16 + nb0 + c) = l4;
+                    for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], lo2);
+                    if (d.y != nullptr) *reinterpret_cast<float4*>(d.y + (m0 + c) * d.ldy + nb0 + b4) = make_float4(o[0], o[1], o[2], o[3]);
+                    if (d.y16_hi != nullptr) {
+                        uint2 h2, l2;
+                        split2(o[0], o[1], h2.x, l2.x);
+                        split2(o[2], o[3], h2.y, l2.y);
+                        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(d.y16_hi) + (m0 + c) * d.ldy16 + nb0 + b4) = h2;
+                        if (!p.f16) *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(d.y16_lo) + (m0 + c) * d.ldy16 + nb0 + b4) = l2;
                     }
                 }
             }
@@ -1563,8 +1595,9 @@ static int launch_tc3(const CUtensorMap* maps, const bflow_conv_desc& d, const v
         configured.set();
     }
     const int n_tiles = p.n_mtiles * p.n_ntiles;
-    const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
-    cudaError_t le = launch_pdl(conv_tc3_kernel<BN, STAGES, F16>, dim3(grid), dim3(T3_THREADS), smem, stream, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
+    const int grid = n_tiles < grid_cap(d) ? n_tiles : grid_cap(d);
+    // a CTA budget means another chain owns the other SMs: no early launch then (an early-launched CTA holds a whole SM while it waits)
+    cudaError_t le = launch_pdl_if(d.max_ctas <= 0, conv_tc3_kernel<BN, STAGES, F16>, dim3(grid), dim3(T3_THREADS), smem, stream, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
                                 maps[6], maps[7], maps[8], d, reinterpret_cast<const uint8_t*>(wtc), p, err);
     if (le != cudaSuccess) {
         set_error(cudaGetErrorString(le));
@@ -1785,7 +1818,7 @@ static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* om
     p.f16 = d.precision == BFLOW_PREC_F16 ? 1 : 0;
     p.dbg = bflow::g_tc3_debug;
     {
-        const int sms = bflow::num_sms();
+        const int sms = bflow::grid_cap(d);
         static int staged_on = -1;
         if (staged_on < 0) {
             const char* e = getenv("BFLOW_TC3_STAGED");
@@ -1855,7 +1888,7 @@ static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* om
             const char* e = getenv("BFLOW_TC3_OSTORE");
             ostore_on = (e != nullptr && e[0] == '0') ? 0 : 1;
         }
-        const bool single1 = d.stats == nullptr && p.n_mtiles * p.n_ntiles <= bflow::num_sms();
+        const bool single1 = d.stats == nullptr && p.n_mtiles * p.n_ntiles <= bflow::grid_cap(d);
         // Cout % 8: measured on B200, a tensor-map store whose box is clipped inside a 16-byte chunk still writes the whole chunk (it
         // overwrote the 4 Bezier-parameter channels behind the motion encoder's 124) -- so the caller's fp16 maps must cover only Cout & ~7 channels;
         // the kernel writes a 4-channel tail itself
@@ -2027,7 +2060,7 @@ extern "C" int bflow_conv2d_slab64(const bflow_conv_desc* dp, const void* maps, 
     }
     alignas(64) CUtensorMap tm[2];
     memcpy(tm, maps, sizeof(tm));
-    const int grid = p.n_tiles < bflow::num_sms() ? p.n_tiles : bflow::num_sms();
+    const int grid = p.n_tiles < bflow::grid_cap(d) ? p.n_tiles : bflow::grid_cap(d);
     bflow::conv_slab64_kernel<<<grid, bflow::T3_THREADS, smem, (cudaStream_t)stream>>>(tm[0], tm[1], d, reinterpret_cast<const uint8_t*>(w_tc), p, err);
     return bflow::check_launch("bflow_conv2d_slab64");
 }

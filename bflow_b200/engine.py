@@ -116,7 +116,8 @@ class Engine:
         if KH * KW * I <= 512:      # stem as a GEMM over the materialised patch matrix (engine_s16: 'im2col' stem)
             kp = 256 if KH * KW * I <= 256 else _ceil(KH * KW * I, 64)      # bflow_conv2d_stem7 wants exactly 4 k-blocks
             wm = torch.zeros(O, kp, 1, 1, dtype=torch.float32)
-            wm[:, :KH * KW * I, 0, 0] = w1.oihw.permute(0, 2, 3, 1).reshape(O, -1)
+            # K order: (c, kh, kw) for the fused stem (bflow_conv2d_stem7, K <= 256), (kh, kw, c) for the patch-matrix kernel (bflow_im2col_split16)
+            wm[:, :KH * KW * I, 0, 0] = w1.oihw.reshape(O, -1) if kp == 256 else w1.oihw.permute(0, 2, 3, 1).reshape(O, -1)
             wp, ldw = pack_conv_weight(wm)
             out['conv1_mat'] = _Weight(wp.to(self.device), ldw, w1.b, O, kp, 1, 1, 1, (0, 0), wm, None, self.device)
         for layer in (enc.layer1, enc.layer2, enc.layer3):

@@ -76,6 +76,7 @@ class S16Recorder:
         assert c0 + c1 == wt.cin, (c0, c1, wt.cin)
         d = ConvDesc()
         d.precision = self.eng.prec
+        d.max_ctas = getattr(self, '_max_ctas', 0)
         d.x0, d.c0, d.ld0 = None, c0, srcs[0][0].ld
         d.x1, d.c1, d.ld1 = None, c1, (srcs[1][0].ld if c1 else 0)
         d.w, d.ldw, d.bias = None, 0, (wt.b.data_ptr() if bias else None)
@@ -195,7 +196,8 @@ class S16Recorder:
         from .engine import _ceil
         L, dev = self.eng.lib, self.eng.device
         shared = {} if shared is None else shared
-        if 49 * cin <= 256 and W % 4 == 0 and os.environ.get('BFLOW_STEM7', '1') != '0':
+        if 49 * cin <= 256:
+            assert W % 4 == 0, 'bflow_b200: the fused stem needs W % 4 == 0 (the model itself needs H, W % 8 == 0)'
             # fused stem: input footprint -> patch matrix in shared memory -> tcgen05 (bflow_conv2d_stem7)
             return dict(kind='stem7', src=src_nchw.data_ptr(), C_total=C_total, c_off=c_off, cin=cin, ns=ns, scale=scale, shift=shift)
         if 49 * cin <= 512:
@@ -266,6 +268,7 @@ class S16Recorder:
                 img, acc_scale = wm.tc3_image(64, wm.cin)
                 d = ConvDesc()
                 d.precision = self.eng.prec
+                d.max_ctas = getattr(self, '_max_ctas', 0)
                 d.x0, d.c0, d.c1, d.bias = win['src'], win['cin'], 0, wm.b.data_ptr()
                 d.y, d.ldy = y, 64
                 d.N, d.H, d.W, d.Ho, d.Wo, d.Cout = ns, H, W, H2, W2, 64
@@ -455,6 +458,13 @@ class S16Recorder:
         #      (raft.py:144-147); then the iteration-invariant GRU terms conv(inp) + bias ----
         U = eng.upd
         self._fork()
+        # The two encoders are the same network on 1 (context) and T+1 or 2 (features) images per sample.  Left alone, their one-CTA-per-SM
+        # launches queue behind each other and each pays its own wave quantisation (a 600-tile context layer needs 5 waves of 148 for
+        # 4.05 waves of work); with disjoint CTA budgets the two chains run side by side.  BFLOW_ENC_SPLIT = SMs of the context chain.
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        split = int(os.environ.get('BFLOW_ENC_SPLIT', '20')) if eng.use_side_stream else 0
+        split = max(0, min(split, n_sm // 2))
+        self._max_ctas = split
         ctx_c = (nctx if self.use_ev else 0) + (3 if self.use_img else 0)
         if self.use_ev and self.use_img:
             # context = cat(voxel[:, -nctx:], image0) (raft.py:137-138): NHWC fp32 -> split planes -> 7x7 im2col-TMA stem
@@ -483,6 +493,7 @@ class S16Recorder:
         self._add(L.bflow_nchw_to_nhwc, self.init_in.data_ptr(), hx + poff * 4, B, 2 * deg, h, w, 0, 2 * deg, gw, 1.0, 0.0)
         self._add(L.bflow_split_f16, hx + poff * 4, gw, hx16.hi(poff), hx16.lo(poff), gw, R, 2 * deg)
         self._main()
+        self._max_ctas = n_sm - split if split else 0
 
         # ---- feature encoders: fp32 feature map for the volume GEMM's B operand, split copy for its A operand ----
         def fnet(name, windows, Np):
@@ -501,6 +512,7 @@ class S16Recorder:
             shared = {}
             fm_img, fm_img16 = fnet('fnet_img', [self._stem_window(self.img_in[i], 3, 0, 3, B, H, W, 2.0 / 255.0, -1.0, shared=shared) for i in range(2)], 2 * B)
         self.fm_ev, self.fm_img, self.fm_ev16, self.fm_img16 = fm_ev, fm_img, fm_ev16, fm_img16
+        self._max_ctas = 0
 
         self.corr16 = _S16(R, eng.ldc, dev)                 # zero-filled: the channels padding S*81 up to ldc stay zero
         if eng.corr_mode == 'otf':

@@ -239,7 +239,7 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         in_scale, in_shift = getattr(conv2d, 'stem_affine', (1.0, 0.0))
         L = _lib.lib()
         wm = torch.zeros(O, 256, 1, 1, device=x.device, dtype=torch.float32)
-        wm[:, :KH * KW * Cin, 0, 0] = _f32c(weight, 'weight').permute(0, 2, 3, 1).reshape(O, -1)
+        wm[:, :KH * KW * Cin, 0, 0] = _f32c(weight, 'weight').reshape(O, -1)       # K = (c, kh, kw): bflow_conv2d_stem7's order
         wtc, acc_scale = pack_conv_weight_tc(wm, 64, block_per_tap=True)
         err = torch.zeros(1, device=x.device, dtype=torch.int32)
         d.x0 = x.data_ptr()

@@ -109,6 +109,9 @@ typedef struct bflow_conv_desc {
      * stats[(m / stats_hw) * Cout + n] += (v, v*v) of every value v written to y — the (sum, sum of squares) table that
      * bflow_instnorm_relu(16) consumes, so no separate bflow_plane_sums pass.  stats_hw = rows per image (0: Ho*Wo). */
     double* stats; int stats_hw;
+    /* persistent tensor-core kernels (tc3 family, slab64, stem7): at most this many CTAs (0 = one per SM).  Lets two independent chains of
+     * launches on two streams own disjoint sets of SMs instead of queueing behind each other's one-CTA-per-SM grids. */
+    int max_ctas;
 } bflow_conv_desc;
 int bflow_conv2d_nhwc(const bflow_conv_desc* d, void* stream);
 
