@@ -35,6 +35,10 @@ struct T3Params {
     FastDiv fd_ntiles, fd_wo, fd_ho;      // tile -> (m_tile, n_tile), first output pixel -> (n, oh, ow) on the producer's critical path
     int staged;   // every CTA owns exactly one tile: the epilogue goes through shared memory (coalesced, batched global accesses)
     int dbg;      // development switch (bflow_tc3_debug): 1 = no TMA loads (the producer only arrives: MMA + epilogue path alone)
+    // 64-channel block index (within a tap) whose channels 32..63 lie beyond the source's channel count (c % 64 in 1..32), or -1: the TMA
+    // unit zero-fills them and the weight image holds zeros there, so the MMA warp issues only the first two of the block's four k-steps
+    // (the main loops are bound by the number of tcgen05.mma instructions: 96-channel layers otherwise spend a quarter of them on zeros)
+    int half0, half1;
 };
 
 template <int BN, int STAGES, bool F16>
@@ -282,8 +286,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
             // The first k-block is peeled off: it alone starts the accumulator (accumulate = 0 on its first MMA), so the steady-state loop
             // issues eight unconditional MMAs per k-block.  Measured: ONE more uniform predicate per MMA pair in this loop cost 10 % of
             // the update block -- the issue sequence of the single MMA thread is on the critical path of these short-N kernels.
-            auto kblock = [&](auto first) {
+            auto kblock = [&](auto first, auto half) {
                 constexpr bool FIRST = decltype(first)::value;
+                constexpr int NK = decltype(half)::value ? 2 : 4;
                 t3_mbar_wait(full_bar(ms), mph, err);
                 t3_fence_after();
                 if (FIRST && lt == 0 && lane == 0) T3_CTA(3);
@@ -295,7 +300,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 const uint32_t ebar_s = empty_bar(ms);
                 if (t3_elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int k = 0; k < NK; ++k) {
                         const uint64_t ko = (uint64_t)(k * 2);             // 32 bytes along K, in 16-byte descriptor units
                         const uint32_t acc0 = (FIRST && k == 0) ? 0u : 1u;
                         if (F16) {
@@ -317,9 +322,16 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                     mph ^= 1u;
                 }
             };
-            kblock(std::true_type{});
+            if (p.half0 == 0) kblock(std::true_type{}, std::true_type{});
+            else kblock(std::true_type{}, std::false_type{});
+            const int ncb_ = p.ncb0 + p.ncb1;
+            int cbi = ncb_ > 1 ? 1 : 0;
 #pragma unroll 1
-            for (int kb = 1; kb < p.nkb; ++kb) kblock(std::false_type{});
+            for (int kb = 1; kb < p.nkb; ++kb) {
+                if (cbi == p.half0 || cbi == p.half1) kblock(std::false_type{}, std::true_type{});
+                else kblock(std::false_type{}, std::false_type{});
+                if (++cbi == ncb_) cbi = 0;
+            }
             if (t3_elect_one()) {
                 t3_commit(tfull_bar(acc));      // arrives when every MMA issued above has completed
                 T3_CTA(4);
@@ -1281,8 +1293,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
 constexpr int SL_BN = 64;
 constexpr int SL_B_BYTES = 9 * 2 * SL_BN * 128;          // resident weights: 147456
 constexpr int SL_PLANE = 8 * 18 * 128;                   // one fp16 slab plane: 18432
-constexpr int SL_STAGE = 2 * SL_PLANE;                   // hi + lo
-constexpr int SL_STAGES = 2;
+constexpr int SL_STAGE = SL_PLANE;                       // one plane (hi or lo) of one slab
+constexpr int SL_STAGES = 4;
 
 struct SlabParams {
     int tiles_x, tiles_y, n_tiles, f16;
@@ -1342,17 +1354,22 @@ conv_slab64_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
             const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
             const int x0 = tx * 8, y0 = ty * 16;
-            for (int kw = 0; kw < 3; ++kw, ++it) {
-                const int s = (int)(it % SL_STAGES);
-                const uint32_t ph = (it / SL_STAGES) & 1u;
-                t3_mbar_wait(empty_bar(s), ph ^ 1u, err);
-                const uint32_t st = stage0 + (uint32_t)s * SL_STAGE;
-                if (t3_elect_one()) {
-                    t3_mbar_arrive_expect_tx(full_bar(s), p.f16 ? SL_PLANE : SL_STAGE);
-                    sl_tma_tile(st, &map_hi, 0, x0 + kw - 1, y0 - 1, n, full_bar(s));
-                    if (!p.f16) sl_tma_tile(st + SL_PLANE, &map_lo, 0, x0 + kw - 1, y0 - 1, n, full_bar(s));
+            // one stage = ONE plane of a slab (18 KB).  Measured with the epilogue, the MMAs and the loads switched off in turn (128 SMs, 23.4 tiles per
+            // CTA): loads alone 40 us (63 GB/s per SM), epilogue alone 52 us, MMAs alone 84 us (~100 cycles per tcgen05.mma whatever its N: the kernel
+            // is bound by MMA issue), everything 94 us.  Four small stages instead of two 36 KB ones keep three loads in flight: 99 -> 94 us.
+            const int npl = p.f16 ? 1 : 2;
+            for (int kw = 0; kw < 3; ++kw) {
+                for (int pl = 0; pl < npl; ++pl, ++it) {
+                    const int s = (int)(it % SL_STAGES);
+                    const uint32_t ph = (it / SL_STAGES) & 1u;
+                    t3_mbar_wait(empty_bar(s), ph ^ 1u, err);
+                    const uint32_t st = stage0 + (uint32_t)s * SL_STAGE;
+                    if (t3_elect_one()) {
+                        t3_mbar_arrive_expect_tx(full_bar(s), SL_PLANE);
+                        sl_tma_tile(st, pl == 0 ? &map_hi : &map_lo, 0, x0 + kw - 1, y0 - 1, n, full_bar(s));
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else if (warp == 1) {
@@ -1365,32 +1382,31 @@ conv_slab64_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             t3_mbar_wait(tempty_bar(acc), aph ^ 1u, err);
             t3_fence_after();
             const uint32_t tacc = tmem_base + acc * ACC_COLS;
-            for (int kw = 0; kw < 3; ++kw, ++it) {
-                const int s = (int)(it % SL_STAGES);
-                const uint32_t ph = (it / SL_STAGES) & 1u;
-                t3_mbar_wait(full_bar(s), ph, err);
-                t3_fence_after();
-                if (t3_elect_one()) {
-                    const uint32_t a_hi = stage0 + (uint32_t)s * SL_STAGE, a_lo = a_hi + SL_PLANE;
+            const int npl = p.f16 ? 1 : 2;
+            for (int kw = 0; kw < 3; ++kw) {
+                for (int pl = 0; pl < npl; ++pl, ++it) {
+                    const int s = (int)(it % SL_STAGES);
+                    const uint32_t ph = (it / SL_STAGES) & 1u;
+                    t3_mbar_wait(full_bar(s), ph, err);
+                    t3_fence_after();
+                    if (t3_elect_one()) {
+                        const uint32_t a = stage0 + (uint32_t)s * SL_STAGE;
+                        // hi plane: A_hi x [B_hi | B_lo] (N = 128, or N = 64 in f16 mode); lo plane: A_lo x B_hi (N = 64)
+                        const uint32_t id = (pl == 0 && !p.f16) ? idesc2 : idesc;
 #pragma unroll
-                    for (int kh = 0; kh < 3; ++kh) {
-                        const uint32_t b = bres + (uint32_t)(kh * 3 + kw) * (2 * SL_BN * 128);
+                        for (int kh = 0; kh < 3; ++kh) {
+                            const uint32_t b = bres + (uint32_t)(kh * 3 + kw) * (2 * SL_BN * 128);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint32_t ko = (uint32_t)k * 32u;
-                            const uint64_t dbh = t3_umma_desc(b + ko);
-                            if (p.f16) {
-                                t3_umma(tacc, t3_umma_desc(a_hi + (uint32_t)kh * 1024u + ko), dbh, idesc, (kw > 0 || kh > 0 || k > 0) ? 1u : 0u);
-                            } else {
-                                t3_umma(tacc, t3_umma_desc(a_hi + (uint32_t)kh * 1024u + ko), dbh, idesc2, (kw > 0 || kh > 0 || k > 0) ? 1u : 0u);
-                                t3_umma(tacc, t3_umma_desc(a_lo + (uint32_t)kh * 1024u + ko), dbh, idesc, 1u);
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t ko = (uint32_t)k * 32u;
+                                t3_umma(tacc, t3_umma_desc(a + (uint32_t)kh * 1024u + ko), t3_umma_desc(b + ko), id, (kw > 0 || pl > 0 || kh > 0 || k > 0) ? 1u : 0u);
                             }
                         }
+                        t3_commit(empty_bar(s));
+                        if (kw == 2 && pl == npl - 1) t3_commit(tfull_bar(acc));
                     }
-                    t3_commit(empty_bar(s));
-                    if (kw == 2) t3_commit(tfull_bar(acc));
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
         t3_fence_before();
@@ -1812,6 +1828,8 @@ static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* om
     p.ncb0 = (d.c0 + 63) / 64;
     p.ncb1 = (d.c1 + 63) / 64;
     p.nkb = p.ntaps * (p.ncb0 + p.ncb1);
+    p.half0 = (d.c0 % 64 >= 1 && d.c0 % 64 <= 32) ? p.ncb0 - 1 : -1;
+    p.half1 = (d.c1 % 64 >= 1 && d.c1 % 64 <= 32) ? p.ncb0 + p.ncb1 - 1 : -1;
     p.acc_scale = acc_scale;
     BFLOW_REQUIRE(d.precision == BFLOW_PREC_SPLIT3 || d.precision == BFLOW_PREC_F16, "conv_tc3: unknown precision");
     BFLOW_REQUIRE(d.precision == BFLOW_PREC_SPLIT3 || !slab, "conv_tc3s: the halo-slab mode has no single-MMA form");

@@ -386,6 +386,7 @@ class S16Recorder:
                 # image is the packed target feature map
                 d = ConvDesc()
                 d.precision = self.eng.prec
+                d.max_ctas = getattr(self, '_vol_max_ctas', 0)
                 d.c0, d.ld0 = fd, fd
                 d.y, d.ldy = self.vol0[t].data_ptr() + b * Q * Np0 * 4, Np0
                 d.N, d.H, d.W, d.Ho, d.Wo, d.Cout = 1, 1, Q, 1, Q, Np0
@@ -512,6 +513,9 @@ class S16Recorder:
             shared = {}
             fm_img, fm_img16 = fnet('fnet_img', [self._stem_window(self.img_in[i], 3, 0, 3, B, H, W, 2.0 / 255.0, -1.0, shared=shared) for i in range(2)], 2 * B)
         self.fm_ev, self.fm_img, self.fm_ev16, self.fm_img16 = fm_ev, fm_img, fm_ev16, fm_img16
+        # the context chain is still running when the feature encoder is done: the all-pairs GEMMs keep to the feature chain's SMs too (a
+        # 148-CTA launch whose last 20 CTAs start late was measured at 58-64 us instead of 38)
+        self._vol_max_ctas = self._max_ctas
         self._max_ctas = 0
 
         self.corr16 = _S16(R, eng.ldc, dev)                 # zero-filled: the channels padding S*81 up to ldc stay zero
