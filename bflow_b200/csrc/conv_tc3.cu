@@ -39,6 +39,10 @@ struct T3Params {
     // unit zero-fills them and the weight image holds zeros there, so the MMA warp issues only the first two of the block's four k-steps
     // (the main loops are bound by the number of tcgen05.mma instructions: 96-channel layers otherwise spend a quarter of them on zeros)
     int half0, half1;
+    // rows of one half (hi or lo) of a weight tile = N of the MMAs = TMEM column of the accumulator's second half.  Normally BN; a launch with a
+    // single column tile and Cout < BN (the 96-channel encoder layers under BN = 128) packs and multiplies only bn_eff = Cout rows: N 192 + 96
+    // instead of 256 + 128 per k-step, and a quarter less weight traffic
+    int bn_eff;
 };
 
 template <int BN, int STAGES, bool F16>
@@ -192,7 +196,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 const int n = (int)fastdiv((unsigned)t, p.fd_ho);
                 const int oh = t - n * d.Ho;
                 const int cw = ow * d.stride - d.pad_w, ch = oh * d.stride - d.pad_h;
-                const uint8_t* wt = wtc + (size_t)n_tile * p.nkb * (2 * B_BYTES);
+                const uint32_t bb = (uint32_t)p.bn_eff * 128u;              // bytes of one half of a weight tile
+                const uint8_t* wt = wtc + (size_t)n_tile * p.nkb * (2 * bb);
                 int kb = 0, kh = 0, kw = 0;
                 for (int tap = 0; tap < p.ntaps; ++tap, ++kw) {
                     if (kw == d.KW) {
@@ -216,14 +221,14 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                                 t3_mbar_arrive(bar);
                             } else {
                                 if (F16) {               // hi plane and the hi half of the weight tile only
-                                    t3_mbar_arrive_expect_tx(bar, T3_A_BYTES + B_BYTES);
+                                    t3_mbar_arrive_expect_tx(bar, T3_A_BYTES + bb);
                                     t3_tma_im2col(stage, src0 ? &map0h : &map1h, cc, cw, ch, n, (uint16_t)kw, (uint16_t)kh, bar);
-                                    t3_bulk_g2s(stage + 2 * T3_A_BYTES, wt + (size_t)kb * (2 * B_BYTES), B_BYTES, bar);
+                                    t3_bulk_g2s(stage + 2 * T3_A_BYTES, wt + (size_t)kb * (2 * bb), bb, bar);
                                 } else {
-                                    t3_mbar_arrive_expect_tx(bar, TX_BYTES);
+                                    t3_mbar_arrive_expect_tx(bar, 2 * T3_A_BYTES + 2 * bb);
                                     t3_tma_im2col(stage, src0 ? &map0h : &map1h, cc, cw, ch, n, (uint16_t)kw, (uint16_t)kh, bar);
                                     t3_tma_im2col(stage + T3_A_BYTES, src0 ? &map0l : &map1l, cc, cw, ch, n, (uint16_t)kw, (uint16_t)kh, bar);
-                                    t3_bulk_g2s(stage + 2 * T3_A_BYTES, wt + (size_t)kb * (2 * B_BYTES), 2 * B_BYTES, bar);
+                                    t3_bulk_g2s(stage + 2 * T3_A_BYTES, wt + (size_t)kb * (2 * bb), 2 * bb, bar);
                                 }
                             }
                         }
@@ -235,8 +240,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer ------------------------------------------------
         // fp16 x fp16 -> fp32, K-major, M 128, N = BN (idesc) or 2 BN (idesc2)
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
-        const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(p.bn_eff >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
+        const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * p.bn_eff) >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
         uint32_t lt = 0, ia = 0, ib = 0, ms = 0, mph = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
             const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
@@ -349,6 +354,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
         const int quad = warp & 3;
         const int chalf = (warp - 2) >> 2;
         const int etid = tid - 64;                   // 0 .. 255
+        const int hoff = p.bn_eff;                   // TMEM column of the accumulator's second half (hi*lo)
         float* s_bias = reinterpret_cast<float*>(smem_raw + (bars - t3_smem_u32(smem_raw)) + 128);   // BN floats behind the barriers
         const float lo1 = d.act1 == BFLOW_ACT_RELU ? 0.f : -INFINITY, lo2 = d.act2 == BFLOW_ACT_RELU ? 0.f : -INFINITY;
         const bool slow1 = d.act1 >= BFLOW_ACT_SIGMOID, slow2 = d.act2 >= BFLOW_ACT_SIGMOID;
@@ -443,7 +449,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 if (hasY) t3_tmem_ld16_nowait(t_y + (uint32_t)c0, yv);
                 if (two_halves) {
                     float u[16];
-                    t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0), u);
+                    t3_tmem_ld16_nowait(taddr + (uint32_t)(hoff + c0), u);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                     for (int c = 0; c < 16; ++c) v[c] += u[c];
@@ -650,8 +656,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                     t3_tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), v + 16);
                     if (two_halves) {
                         float u[32];
-                        t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0), u);
-                        t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0 + 16), u + 16);
+                        t3_tmem_ld16_nowait(taddr + (uint32_t)(hoff + c0), u);
+                        t3_tmem_ld16_nowait(taddr + (uint32_t)(hoff + c0 + 16), u + 16);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                         for (int c = 0; c < 32; ++c) v[c] += u[c];
@@ -747,8 +753,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                     t3_tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), v + 16);
                     if (two_halves) {
                         float u[32];
-                        t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0), u);
-                        t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0 + 16), u + 16);
+                        t3_tmem_ld16_nowait(taddr + (uint32_t)(hoff + c0), u);
+                        t3_tmem_ld16_nowait(taddr + (uint32_t)(hoff + c0 + 16), u + 16);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                         for (int c = 0; c < 32; ++c) v[c] += u[c];
@@ -845,8 +851,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                         t3_tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), v + 16);
                         if (two_halves) {
                             float u[32];
-                            t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0), u);
-                            t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0 + 16), u + 16);
+                            t3_tmem_ld16_nowait(taddr + (uint32_t)(hoff + c0), u);
+                            t3_tmem_ld16_nowait(taddr + (uint32_t)(hoff + c0 + 16), u + 16);
                             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                             for (int c = 0; c < 32; ++c) v[c] += u[c];
@@ -936,8 +942,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                         t3_tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), v + 16);
                         if (two_halves) {
                             float u[32];
-                            t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0), u);
-                            t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0 + 16), u + 16);
+                            t3_tmem_ld16_nowait(taddr + (uint32_t)(hoff + c0), u);
+                            t3_tmem_ld16_nowait(taddr + (uint32_t)(hoff + c0 + 16), u + 16);
                             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                             for (int c = 0; c < 32; ++c) v[c] += u[c];
@@ -1057,8 +1063,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                         t3_tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16), v + 16);
                         if (two_halves) {
                             float u[32];
-                            t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0), u);
-                            t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c0 + 16), u + 16);
+                            t3_tmem_ld16_nowait(taddr + (uint32_t)(hoff + c0), u);
+                            t3_tmem_ld16_nowait(taddr + (uint32_t)(hoff + c0 + 16), u + 16);
                             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                             for (int c = 0; c < 32; ++c) v[c] += u[c];
@@ -1117,7 +1123,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map0h, const __grid_constant
                 if (two_halves) {
                     float u[HALF];
 #pragma unroll
-                    for (int c = 0; c < HALF; c += 16) t3_tmem_ld16_nowait(taddr + (uint32_t)(BN + c), u + c);
+                    for (int c = 0; c < HALF; c += 16) t3_tmem_ld16_nowait(taddr + (uint32_t)(hoff + c), u + c);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                     for (int c = 0; c < HALF; ++c) v[c] += u[c];
@@ -1789,6 +1795,12 @@ static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* om
     BFLOW_CHECK_DESC(dp, bflow_conv_desc, "conv_tc3");
     BFLOW_REQUIRE(maps != nullptr && w_tc != nullptr, "conv_tc3: null argument");
     const bflow_conv_desc& d = *dp;
+    // narrow weight tile: bn = 80 / 96 / 112 covering all of Cout -> the 128-column instantiation with bn rows per weight half
+    int bn_eff = bn;
+    if (bn != 64 && bn != 128 && bn != 256) {
+        BFLOW_REQUIRE(bn > 64 && bn < 128 && bn % 16 == 0 && !slab && d.Cout <= bn, "conv_tc3: bn must be 64, 128, 256, or 80 / 96 / 112 with Cout <= bn (im2col mode)");
+        bn = 128;
+    }
     if (slab) {
         BFLOW_REQUIRE(slab == 1 || slab == 2, "conv_tc3s: orientation must be 1 (taps along y) or 2 (taps along x)");
         BFLOW_REQUIRE(d.stride == 1 && d.pad_h == d.KH / 2 && d.pad_w == d.KW / 2 && (d.KH & 1) && (d.KW & 1), "conv_tc3s: stride 1, odd window, 'same' padding");
@@ -1828,6 +1840,7 @@ static int tc3_entry(const bflow_conv_desc* dp, const void* maps, const void* om
     p.ncb0 = (d.c0 + 63) / 64;
     p.ncb1 = (d.c1 + 63) / 64;
     p.nkb = p.ntaps * (p.ncb0 + p.ncb1);
+    p.bn_eff = bn_eff;
     p.half0 = (d.c0 % 64 >= 1 && d.c0 % 64 <= 32) ? p.ncb0 - 1 : -1;
     p.half1 = (d.c1 % 64 >= 1 && d.c1 % 64 <= 32) ? p.ncb0 + p.ncb1 - 1 : -1;
     p.acc_scale = acc_scale;

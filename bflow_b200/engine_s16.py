@@ -48,6 +48,10 @@ def choose_bn(cout: int, n_mtiles: int) -> int:
     if cout <= 64:
         return 64
     if n_mtiles >= 148:
+        # one column tile that is narrower than 128: pack and multiply only `cout` weight rows (bflow_conv2d_nhwc_tc3: bn = 80 / 96 / 112
+        # runs the 128-column kernel with N = 2*bn + bn per k-step -- the 96-channel encoder layers: 192 + 96 instead of 256 + 128)
+        if 64 < cout < 128 and cout % 16 == 0:
+            return cout
         return 128
     return 128 if (cout >= 256 and cout % 128 == 0) else 64
 
@@ -114,7 +118,7 @@ class S16Recorder:
         bn = choose_bn(wt.cout, (M + 127) // 128)
         img, acc_scale = wt.tc3_image(bn, c0)
         orient = {(3, 3): 1, (5, 1): 1, (1, 5): 2}.get((wt.kh, wt.kw), 0)
-        if (orient and wt.stride == 1 and (ph, pw) == (wt.kh // 2, wt.kw // 2) and bn <= 128 and self.eng.prec == 0 and
+        if (orient and wt.stride == 1 and (ph, pw) == (wt.kh // 2, wt.kw // 2) and bn in (64, 128) and self.eng.prec == 0 and
                 os.environ.get('BFLOW_TC3_SLAB', '0') == '1'):
             # halo slabs instead of im2col rows: A traffic / 2.7 (3x3) ... / 4 (1x5, 5x1).  Opt-in: measured on B200 it buys nothing here -- the
             # main loops of these layers are bound by the tensor pipe (bn 128) or by MMA issue (bn 64), not by L2 -> SM traffic

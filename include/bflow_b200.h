@@ -122,7 +122,8 @@ int bflow_conv2d_nhwc(const bflow_conv_desc* d, void* stream);
  *   [ceil(Cout/bn)][ceil(K/64)][hi | lo (fp16)][bn rows][64 elements]
  * whose 16-byte chunks are XOR-swizzled by (row % 8), i.e. byte for byte the SWIZZLE_128B shared-memory tile
  * (bflow_b200/ops.py pack_conv_weight_tc); acc_scale (a power of two) is multiplied back onto the accumulator.
- * bn in {64,128,256}.  `err`: optional device int, set to 1 if an in-kernel pipeline wait timed out (never expected; the
+ * bn in {64,128,256}; for a launch with Cout <= bn < 128 also bn in {80,96,112}: the 128-column kernel with bn weight rows per half (w_tc packed
+ * for that bn), i.e. MMAs of N = 2*bn and bn instead of 256 and 128 -- the 96-channel encoder layers.  `err`: optional device int, set to 1 if an in-kernel pipeline wait timed out (never expected; the
  * waits are bounded so that a bug cannot hang the GPU).  The output of such a launch is invalid: the caller must read the word
  * back (bflow_b200/engine.py does so with every forward's results and raises).
  * precision = BFLOW_PREC_F16 runs ONE tcgen05.mma per k-step on the hi planes / the hi half of the weight image. */

@@ -98,6 +98,11 @@ def test_conv2d_single_mma_f16_precision(backend, N, Cin, H, W, Cout, k, s, p, a
     (1, 256, 60, 80, 124, (3, 3), 1, (1, 1), 'relu', 64),      # single-tile, ragged Cout
     (1, 256, 60, 80, 256, (1, 5), 1, (0, 2), 'sigmoid', 128),  # single-tile bulk-copy epilogue, bn 128
     (1, 128, 60, 80, 64, (3, 3), 1, (1, 1), 'tanh', 64),
+    (2, 96, 120, 160, 96, (3, 3), 1, (1, 1), 'relu', 96),      # narrow weight tile (bn = Cout = 96 on the 128-column kernel) + half k-blocks (96 = 64 + 32 channels)
+    (2, 64, 120, 160, 96, (3, 3), 2, (1, 1), 'none', 96),      # the same, stride 2, multi-tile bulk row stores
+    (1, 96, 60, 80, 96, (1, 1), 1, (0, 0), 'relu', 96),        # single-tile CTAs
+    (1, 28, 64, 96, 64, (7, 7), 2, (3, 3), 'relu', 64),        # 28 channels: every k-block is a half block (two of four k-steps issued)
+    (1, 160, 60, 80, 112, (3, 3), 1, (1, 1), 'none', 112),     # 160 = 2 x 64 + 32 channels, 112-row weight tiles
 ])
 def test_conv2d_tc3_matches_torch(N, Cin, H, W, Cout, k, s, p, act, bn):
     """TMA-fed kernel and its epilogue variants (single-tile bulk copy, multi-tile bulk row stores, direct stores, ragged Cout)."""
