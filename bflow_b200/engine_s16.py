@@ -467,7 +467,8 @@ class S16Recorder:
         # launches queue behind each other and each pays its own wave quantisation (a 600-tile context layer needs 5 waves of 148 for
         # 4.05 waves of work); with disjoint CTA budgets the two chains run side by side.  BFLOW_ENC_SPLIT = SMs of the context chain.
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        split = int(os.environ.get('BFLOW_ENC_SPLIT', '20')) if eng.use_side_stream else 0
+        # measured optimum at D, batch 1: 20 of 148 SMs (f32x3), 14 (f16: the 1-image context chain gains more from the single MMA than the feature chain)
+        split = int(os.environ.get('BFLOW_ENC_SPLIT', '14' if eng.prec == 1 else '20')) if eng.use_side_stream else 0
         split = max(0, min(split, n_sm // 2))
         self._max_ctas = split
         ctx_c = (nctx if self.use_ev else 0) + (3 if self.use_img else 0)

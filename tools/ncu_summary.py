@@ -38,7 +38,7 @@ def main():
         h = src[hrow]
         isrc, ismp, iex = h.index('Source'), h.index('# Samples'), h.index('Instructions Executed')
         stalls = [i for i, x in enumerate(h) if x.startswith('stall_') and 'Not Issued' not in x]
-        data = [r for r in src[hrow + 1:] if len(r) == len(h)]
+        data = [r for r in src[hrow + 1:] if len(r) == len(h) and (r[ismp] or '0').isdigit()]      # a multi-launch report repeats the header row per launch
         tot = sum(int(r[ismp] or 0) for r in data) or 1
         print(f'\n## hottest SASS instructions of the last launch ({tot} warp samples, {len(data)} instructions)')
         for r in sorted(data, key=lambda r: -int(r[ismp] or 0))[:14]:
