@@ -212,10 +212,19 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
             raise RuntimeError('bflow_conv2d_nhwc_tc3s: pipeline wait timed out inside the kernel')
     elif backend == 'tc3':
         x16 = split_f16(xh, (Cin + 7) // 8 * 8)
-        m = tma_im2col_maps(x16, N, H, W, Cin, KH, KW, stride, ph, pw)
         maps = (C.c_uint8 * 512)()
-        C.memmove(maps, m, 256)
-        wtc, acc_scale = pack_conv_weight_tc(weight, bn, block_per_tap=True)
+        # `conv2d.split_c0 = c` reads the input as the concatenation of two sources, channels [0, c) and [c, Cin) (update.py:35,38,42,45: torch.cat
+        # as two tensor-map pairs; c a multiple of 64)
+        sc0 = getattr(conv2d, 'split_c0', None)
+        if sc0:
+            assert 0 < sc0 < Cin and sc0 % 64 == 0
+            C.memmove(maps, tma_im2col_maps(x16, N, H, W, sc0, KH, KW, stride, ph, pw), 256)
+            C.memmove(C.addressof(maps) + 256, tma_im2col_maps(x16, N, H, W, Cin - sc0, KH, KW, stride, ph, pw, c_off=sc0), 256)
+            d.c0, d.c1 = sc0, Cin - sc0
+            wtc, acc_scale = pack_conv_weight_tc(weight, bn, block_per_tap=True, c0=sc0)
+        else:
+            C.memmove(maps, tma_im2col_maps(x16, N, H, W, Cin, KH, KW, stride, ph, pw), 256)
+            wtc, acc_scale = pack_conv_weight_tc(weight, bn, block_per_tap=True)
         err = torch.zeros(1, device=x.device, dtype=torch.int32)
         d.x0 = None
         if getattr(conv2d, 'tma_out', False):

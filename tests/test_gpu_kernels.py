@@ -115,6 +115,26 @@ def test_conv2d_tc3_matches_torch(N, Cin, H, W, Cout, k, s, p, act, bn):
     assert (out - ref).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize('N,Cin,c0,H,W,Cout,k,p,act,bn', [
+    (1, 256, 128, 60, 80, 128, (1, 5), (0, 2), 'tanh', 64),    # GRU candidate shape: cat(r*h, motion features)
+    (1, 224, 128, 60, 80, 256, (5, 1), (2, 0), 'sigmoid', 128),    # second source 96 = 64 + 32 channels: its last k-block is a half block
+    (2, 84, 64, 50, 44, 96, (3, 3), (1, 1), 'relu', 96),       # second source 20 channels (config M's Bezier parameters): half block, narrow tile, ragged M
+])
+def test_conv2d_tc3_two_sources_match_torch(N, Cin, c0, H, W, Cout, k, p, act, bn):
+    """Channel concatenation of two sources as two tensor-map pairs (update.py:35-45, 94), each padded to whole 64-channel blocks on its own."""
+    x = torch.randn(N, Cin, H, W, generator=g(1))
+    w = torch.randn(Cout, Cin, *k, generator=g(2)) / (Cin * k[0] * k[1]) ** 0.5
+    b = torch.randn(Cout, generator=g(3))
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride=1, padding=p).float()
+    ref = {'none': lambda t: t, 'relu': torch.relu, 'sigmoid': torch.sigmoid, 'tanh': torch.tanh}[act](ref)
+    ops.conv2d.split_c0 = c0
+    try:
+        out = ops.conv2d(x.to(DEV), w.to(DEV), b.to(DEV), stride=1, padding=p, act=act, backend='tc3', bn=bn).cpu()
+    finally:
+        ops.conv2d.split_c0 = None
+    assert (out - ref).abs().max() < 1e-4
+
+
 @pytest.mark.parametrize('N,Cin,H,W,Cout,k,p,act,bn', [
     (1, 64, 16, 8, 64, (3, 3), (1, 1), 'none', 64),            # one tile
     (1, 256, 60, 80, 192, (3, 3), (1, 1), 'relu', 64),         # convc2 shape: 40 x 3 single-tile CTAs, ragged tile rows (60 = 3.75 x 16)
