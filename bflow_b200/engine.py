@@ -14,6 +14,7 @@ The correlation pyramid keeps the reference's layout (target, B*Q, h_l, w_l): on
 from __future__ import annotations
 
 import ctypes as C
+import gc
 import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -602,8 +603,18 @@ class _Plan(S16Recorder):
                 torch.cuda.current_stream().synchronize()
                 self.check()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self.launch_all()
+                # A dead Python cycle that still owns CUDA objects (an earlier engine: its CUDAGraph, streams, tensors) must not be collected
+                # WHILE this capture runs: destroying a graph / stream from the garbage collector is an unsafe call in global capture mode and
+                # invalidates the capture (torch.cuda.graph no longer collects on entry).  Collect now, keep the collector off until capture_end.
+                gc.collect()
+                gc_was_enabled = gc.isenabled()
+                gc.disable()
+                try:
+                    with torch.cuda.graph(g):
+                        self.launch_all()
+                finally:
+                    if gc_was_enabled:
+                        gc.enable()
                 self.graph = g
             self.graph.replay()
 

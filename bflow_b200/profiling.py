@@ -41,9 +41,17 @@ def graph_timeline(plan, replays: int = 3) -> Tuple[List[Dict], float]:
         torch.cuda.synchronize()
         L.bflow_timeline(buf.data_ptr(), cap)  # armed: the capture below bakes slot i into launch i
         g = torch.cuda.CUDAGraph()
+        import gc
+        gc.collect()                           # see _Plan.execute: no collection of CUDA-owning garbage while the capture runs
+        gc_was_enabled = gc.isenabled()
+        gc.disable()
         try:
-            with torch.cuda.graph(g):
-                plan.launch_all()
+            try:
+                with torch.cuda.graph(g):
+                    plan.launch_all()
+            finally:
+                if gc_was_enabled:
+                    gc.enable()
             n = L.bflow_timeline_used()
             names = [L.bflow_timeline_name(i).decode() for i in range(n)]
         finally:
