@@ -238,3 +238,24 @@ def test_host_tensor_input_is_rejected_loudly():
         net(voxel_grid=torch.zeros(1, 9, 128, 128), iters=1, test_mode=True)
     with pytest.raises(AssertionError, match='too small'):      # a 1-pixel pyramid level: the reference returns NaN there
         net(voxel_grid=torch.zeros(1, 9, 64, 96, device=DEV), iters=1, test_mode=True)
+
+
+@pytest.mark.gpu
+def test_capture_survives_garbage_of_an_earlier_engine():
+    """A dead engine (reference cycles: only the cyclic collector frees its CUDAGraph and streams) must not be collected while the next plan is
+    being captured -- destroying a graph from the collector invalidates a global-mode capture.  Collector thresholds at 1 make any unguarded
+    capture hit it."""
+    import gc
+    cfg = config.preset('E_LU4_BD2')
+    vg, _ = synthetic.inputs(cfg, 1, 128, 160)
+    old = gc.get_threshold()
+    try:
+        net = RAFTSpline(cfg, seed=0).to(DEV)
+        first = net(voxel_grid=vg.to(DEV), iters=2, test_mode=True)[1].get_params().clone()
+        del net                                   # garbage now, still uncollected
+        gc.set_threshold(1, 1, 1)
+        net2 = RAFTSpline(cfg, seed=0).to(DEV)
+        second = net2(voxel_grid=vg.to(DEV), iters=2, test_mode=True)[1].get_params()
+        assert (first - second).abs().max() <= 1e-5      # same weights, same input; InstanceNorm atomics: order noise only
+    finally:
+        gc.set_threshold(*old)
