@@ -1,3 +1,6 @@
+"""Repeats the small reference fixtures N times on one GPU and prints (8 x low-res max EPE, full-res max EPE) per run: run-to-run spread of the
+parity margin (atomics order in the InstanceNorm sums) -- the margin to the 1e-3 px bar is ~10x.
+    python tools/flake_probe.py [N]"""
 import sys, os, numpy as np, torch
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 from conftest import load_golden
