@@ -226,3 +226,14 @@ def test_shard_ranges_cover_the_batch():
             assert spans[0][0] == 0 and spans[-1][1] == gb
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_tile_width_policy():
+    """engine_s16.choose_bn: 64-column tiles for narrow layers and for the 38-row-tile update block, 128 columns once the row tiles fill the machine,
+    and a narrow weight tile (bn = Cout) only where bflow_conv2d_nhwc_tc3 accepts one: a single column tile, 64 < Cout < 128, Cout % 16 == 0."""
+    from bflow_b200.engine_s16 import choose_bn
+    assert choose_bn(64, 3000) == 64 and choose_bn(48, 10) == 64
+    assert choose_bn(96, 750) == 96 and choose_bn(112, 148) == 112 and choose_bn(80, 200) == 80
+    assert choose_bn(124, 150) == 128 and choose_bn(128, 188) == 128 and choose_bn(192, 150) == 128 and choose_bn(256, 750) == 128
+    assert choose_bn(96, 38) == 64 and choose_bn(192, 38) == 64 and choose_bn(124, 38) == 64
+    assert choose_bn(256, 38) == 128 and choose_bn(576, 38) == 64
